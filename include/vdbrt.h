@@ -1,0 +1,253 @@
+/* vdbrt.h -- C ABI of the B200-native VDB ray tracer (libvdbrt.so).
+ *
+ * This is the drop-in boundary for ONE hot path of OpenVDB 13.0.1: the per-pixel loops behind
+ * openvdb::tools::LevelSetRayTracer / LevelSetRayIntersector / VolumeRender as driven by vdb_render,
+ * executed by hand-written sm_100a CUDA kernels over a NanoVDB-serialised NanoGrid<float>.
+ * Every entry point names the reference interface it replaces (paths relative to the OpenVDB tree).
+ * Plain C: POD structs, raw pointers and sizes only.  There is NO CPU fallback behind this API: without a
+ * CUDA device vdbrt_create() fails with VDBRT_ERR_CUDA.
+ *
+ * Conventions
+ *   - every function returns an int status (VDBRT_OK == 0); vdbrt_last_error() gives a thread-local message.
+ *     The reference reports the same conditions as C++ exceptions thrown at construction time
+ *     (tools/RayIntersector.h:100-112,305-311,533-539; tools/RayTracer.h:877-879); the C++ facade
+ *     (include/vdbrt/RayTracer.h) turns the codes back into exceptions of the same kind.
+ *   - "memspace" says where a caller buffer lives: host memory (copied through the library's stream, fastest
+ *     when allocated with vdbrt_host_alloc) or device memory of the context's GPU (used in place).
+ *   - a context drives exactly one GPU; multi-GPU rendering is one context (one process) per GPU, each rendering
+ *     the film tiles it owns (vdbrt_partition), with the frame gathered by the caller (NCCL / peer copy).
+ */
+#ifndef VDBRT_H_INCLUDED
+#define VDBRT_H_INCLUDED
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDBRT_VERSION 100
+
+/* ---- status codes ---------------------------------------------------------------------------------------- */
+enum {
+    VDBRT_OK = 0,
+    VDBRT_ERR_INVALID_ARG   = 1,  /* null pointer, zero-sized film, bad enum ...                               */
+    VDBRT_ERR_BAD_GRID      = 2,  /* not a NanoVDB buffer: magic / version / size (NanoVDB.h:2002-2013)          */
+    VDBRT_ERR_NOT_FLOAT     = 3,  /* grid value type is not GridType::Float                                     */
+    VDBRT_ERR_NOT_LEVELSET  = 4,  /* RuntimeError "only supports level sets"   (RayIntersector.h:105-109)       */
+    VDBRT_ERR_NONUNIFORM    = 5,  /* RuntimeError "only supports uniform voxels" (RayIntersector.h:101-104,305) */
+    VDBRT_ERR_EMPTY_GRID    = 6,  /* RuntimeError "does not supports empty grids" (RayIntersector.h:309,533)    */
+    VDBRT_ERR_ISO_RANGE     = 7,  /* ValueError "iso-value must be inside the narrow-band" (RayIntersector.h:536)*/
+    VDBRT_ERR_SPP_ZERO      = 8,  /* ValueError "pixelSamples must be larger than zero" (RayTracer.h:877-879)   */
+    VDBRT_ERR_CUDA          = 9,  /* CUDA runtime error or no usable device                                     */
+    VDBRT_ERR_UNSUPPORTED   = 10, /* e.g. a map that is not scale(+translate)                                   */
+    VDBRT_ERR_NOMEM         = 11
+};
+
+enum { VDBRT_MEM_HOST = 0, VDBRT_MEM_DEVICE = 1 };
+enum { VDBRT_CAMERA_PERSPECTIVE = 0, VDBRT_CAMERA_ORTHOGRAPHIC = 1 };
+enum { VDBRT_SHADER_MATTE = 0, VDBRT_SHADER_NORMAL = 1, VDBRT_SHADER_POSITION = 2, VDBRT_SHADER_DIFFUSE = 3 };
+enum { VDBRT_SPACE_WORLD = 0, VDBRT_SPACE_INDEX = 1 };
+enum { VDBRT_GRID_CLASS_UNKNOWN = 0, VDBRT_GRID_CLASS_LEVEL_SET = 1, VDBRT_GRID_CLASS_FOG_VOLUME = 2 };
+
+typedef struct vdbrt_ctx  vdbrt_ctx;
+typedef struct vdbrt_grid vdbrt_grid;
+
+/* ---- POD descriptions ------------------------------------------------------------------------------------ */
+
+/* math::Ray<double> (math/Ray.h:26-295): eye, direction, [t0,t1].  invDir is recomputed as 1/dir (Ray.h:67-71). */
+typedef struct vdbrt_ray {
+    double eye[3];
+    double dir[3];
+    double t0, t1;
+} vdbrt_ray;
+
+/* Flattened tools::BaseCamera (tools/RayTracer.h:351-415): the screen->world AffineMap as the 16 doubles of its
+ * Mat4d (row-vector convention, element [r*4+c]), the base ray (RayTracer.h:404-409), and the two screen scales
+ * (RayTracer.h:357-358).  Fill it with vdbrt_camera_perspective / _orthographic / _look_at.                    */
+typedef struct vdbrt_camera {
+    uint32_t kind;            /* VDBRT_CAMERA_*                                                                 */
+    uint32_t width, height;   /* film size the camera was built for                                             */
+    uint32_t reserved;
+    double   m[16];           /* mScreenToWorld                                                                 */
+    double   eye[3];          /* base ray eye  = applyMap(0,0,0)                                                */
+    double   dir[3];          /* base ray dir  = applyJacobian(0,0,-1)                                          */
+    double   scale_w, scale_h;/* mScaleWidth, mScaleHeight                                                      */
+    double   t0, t1;          /* near / far                                                                     */
+} vdbrt_camera;
+
+/* The four constant-colour shaders (tools/RayTracer.h:565-581,614-630,671-690,728-753). `rgba` is the colour
+ * the user passed to the shader's constructor (NormalShader halves it itself, RayTracer.h:618).                */
+typedef struct vdbrt_shader {
+    uint32_t kind;            /* VDBRT_SHADER_*                                                                 */
+    float    rgba[4];
+    uint32_t reserved;
+    double   bbox_min[3];     /* PositionShader: bbox.min()            (RayTracer.h:675)                        */
+    double   inv_dim[3];      /* PositionShader: 1.0 / bbox.extents()                                           */
+} vdbrt_shader;
+
+/* Which film tiles this context renders (multi-GPU): the film is cut into tile_w x tile_h tiles numbered
+ * row-major; the context renders tiles with  tile_id % count == rank  and leaves all other pixels untouched.
+ * {0,0,0,1} or a zeroed struct means "everything".                                                             */
+typedef struct vdbrt_partition {
+    uint32_t tile_w, tile_h;  /* 0 -> library default (8x4 warp tiles grouped 64x64)                            */
+    uint32_t rank, count;
+} vdbrt_partition;
+
+/* LevelSetRayTracer parameters (tools/RayTracer.h:100-126,872-889).                                             */
+typedef struct vdbrt_ls_opts {
+    float    iso;             /* LevelSetRayIntersector isoValue                                                */
+    uint32_t spp;             /* pixelSamples (>= 1)                                                            */
+    double   jitter[16];      /* mRand[16] from math::Rand01<double>(seed); see vdbrt_jitter_table              */
+    vdbrt_partition part;
+    uint32_t flags;           /* VDBRT_LS_*                                                                     */
+    uint32_t reserved;
+} vdbrt_ls_opts;
+#define VDBRT_LS_UNIFORM_BG 1u /* every film pixel currently equals bg_rgba: skip the host->device film copy    */
+
+/* VolumeRender parameters (tools/RayTracer.h:162-207; defaults :929-936).                                      */
+typedef struct vdbrt_vol_opts {
+    double primary_step, shadow_step, cutoff, light_gain;
+    double light_dir[3];      /* already normalised (setLightDir normalises, RayTracer.h:173)                   */
+    double light_color[3];
+    double absorption[3];
+    double scattering[3];
+    vdbrt_partition part;
+} vdbrt_vol_opts;
+
+/* tools::Film (tools/RayTracer.h:226-345): row-major RGBA float4, pixel (w,h) at [w + h*width].               */
+typedef struct vdbrt_film {
+    float*   pixels;          /* 4*width*height floats, in/out for level sets (misses keep the old pixel)       */
+    uint32_t width, height;
+    uint32_t memspace;        /* VDBRT_MEM_*                                                                    */
+    float    bg_rgba[4];      /* only read when VDBRT_LS_UNIFORM_BG is set                                      */
+} vdbrt_film;
+
+/* Optional per-pixel records of the PRIMARY ray, for parity checks; any pointer may be NULL.  Same memspace as
+ * the film.  `ijk` is the voxel handed to the LinearSearchImpl call that returned true.             */
+typedef struct vdbrt_aux {
+    uint8_t* hit;             /* [W*H]    1 = intersectsWS returned true                                        */
+    int32_t* ijk;             /* [W*H*3]                                                                        */
+    double*  t_index;         /* [W*H]    LinearSearchImpl::getIndexTime                                        */
+    double*  t_world;         /* [W*H]    getWorldTime                                                          */
+    double*  xyz;             /* [W*H*3]  world position                                                        */
+    double*  nml;             /* [W*H*3]  world normal                                                          */
+} vdbrt_aux;
+
+/* One result of LevelSetRayIntersector::intersectsWS/IS (tools/RayIntersector.h:119-240).                      */
+typedef struct vdbrt_hit {
+    int32_t hit;
+    int32_t ijk[3];
+    double  t_index, t_world;
+    double  xyz_index[3];
+    double  xyz_world[3];
+    double  nml[3];
+} vdbrt_hit;
+
+/* Per-launch work counters (averages feed the roofline's algorithmic bytes).                        */
+typedef struct vdbrt_counters {
+    uint64_t rays;
+    uint64_t root_probes;     /* n_R: hasNode<Upper> / root-level DDA probes                                    */
+    uint64_t upper_probes;    /* n_U: probes inside upper nodes                                                 */
+    uint64_t lower_probes;    /* n_L: probes inside lower nodes                                                 */
+    uint64_t voxel_probes;    /* n_V: LinearSearchImpl::operator() probeValue calls                             */
+    uint64_t stencil_refills; /* n_S: BoxStencil refills (8 fetches each)                                       */
+    uint64_t primary_samples; /* n_P: fog primary trilinear samples                                             */
+    uint64_t shadow_samples;  /* n_Sh: fog shadow trilinear samples                                             */
+    uint64_t shadow_rays;
+    uint64_t hits;
+} vdbrt_counters;
+
+typedef struct vdbrt_grid_info {
+    uint64_t bytes;
+    uint64_t active_voxels;
+    uint32_t leaf_count, lower_count, upper_count, root_tiles;
+    int32_t  index_bbox[6];   /* NanoVDB voxel-tight bbox (min xyz, max xyz)                                    */
+    int32_t  node_bbox[6];    /* leaf/tile-granular bbox == RootNode::evalActiveBoundingBox(bbox,false)          */
+    double   voxel_size[3];
+    double   translation[3];
+    float    background;
+    uint32_t grid_class;      /* VDBRT_GRID_CLASS_*                                                             */
+} vdbrt_grid_info;
+
+/* ---- context / memory ------------------------------------------------------------------------------------ */
+int  vdbrt_create(int device, vdbrt_ctx** out);          /* replaces: nothing (reference is in-process TBB)     */
+void vdbrt_destroy(vdbrt_ctx* ctx);
+const char* vdbrt_last_error(void);
+int  vdbrt_device_count(void);
+/* use an existing CUDA stream (e.g. torch's current stream) for every launch/copy of this context; 0 = own stream */
+int  vdbrt_set_stream(vdbrt_ctx* ctx, void* cuda_stream);
+int  vdbrt_synchronize(vdbrt_ctx* ctx);
+int  vdbrt_host_alloc(size_t bytes, void** out);         /* pinned host memory (cuda::DeviceBuffer semantics,   */
+int  vdbrt_host_free(void* p);                           /*  nanovdb/cuda/DeviceBuffer.h:316-344)               */
+
+/* ---- grids ------------------------------------------------------------------------------------------------
+ * replaces nanovdb::GridHandle<cuda::DeviceBuffer>::deviceUpload (nanovdb/cuda/DeviceBuffer.h:411-456) plus the
+ * constructor-time work of LinearSearchImpl / VolumeRayIntersector (validation, node-granular bbox:
+ * tools/RayIntersector.h:299-319,527-541).  The buffer is a complete NanoGrid<float> (GridData first).        */
+int  vdbrt_upload_grid(vdbrt_ctx* ctx, const void* nanovdb_buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out);
+int  vdbrt_free_grid(vdbrt_ctx* ctx, vdbrt_grid* grid);
+int  vdbrt_grid_get_info(const vdbrt_grid* grid, vdbrt_grid_info* info);
+/* copy the serialised grid back (device -> host), e.g. after vdbrt_build_* */
+int  vdbrt_grid_download(vdbrt_ctx* ctx, const vdbrt_grid* grid, void* dst, uint64_t bytes);
+
+/* ---- host-side helpers that flatten the reference's classes ------------------------------------------------ */
+/* tools::PerspectiveCamera ctor (RayTracer.h:436-445) / OrthographicCamera ctor (:494-502): rotation in degrees
+ * (x,y,z order), then translation.                                                                             */
+int  vdbrt_camera_perspective(vdbrt_camera* cam, uint32_t width, uint32_t height, const double rotation[3],
+                              const double translation[3], double focal_length, double aperture,
+                              double near_plane, double far_plane);
+int  vdbrt_camera_orthographic(vdbrt_camera* cam, uint32_t width, uint32_t height, const double rotation[3],
+                               const double translation[3], double frame_width, double near_plane, double far_plane);
+/* BaseCamera::lookAt (RayTracer.h:379-389); like the reference it silently keeps the camera on failure.         */
+int  vdbrt_camera_look_at(vdbrt_camera* cam, const double xyz[3], const double up[3]);
+/* the 16 doubles LevelSetRayTracer::setPixelSamples draws (RayTracer.h:883-885)                                 */
+int  vdbrt_jitter_table(unsigned int seed, double out[16]);
+/* VolumeRender defaults (RayTracer.h:929-936)                                                                   */
+int  vdbrt_vol_opts_default(vdbrt_vol_opts* opts);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------ */
+/* tools::rayTrace(grid, LevelSetRayIntersector(grid, iso), shader, camera, spp, seed, threaded)
+ * == LevelSetRayTracer::render (RayTracer.h:48-64,891-918).  Synchronous: the film is complete on return.     */
+int  vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
+                           const vdbrt_shader* shader, const vdbrt_ls_opts* opts, vdbrt_film* film, vdbrt_aux* aux);
+/* VolumeRender<VolumeRayIntersector<FloatGrid>, BoxSampler>::render (RayTracer.h:985-1070).                     */
+int  vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
+                         const vdbrt_vol_opts* opts, vdbrt_film* film);
+/* LevelSetRayIntersector::intersectsWS / intersectsIS on a batch of arbitrary rays (RayIntersector.h:119-240).  */
+int  vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n,
+                              uint32_t space, float iso, vdbrt_hit* hits, uint32_t memspace);
+/* VolumeRayIntersector::setIndexRay/setWorldRay + hits() (RayIntersector.h:368-432): spans[i*max_spans*2 ..],
+ * counts[i] = number of spans (may exceed max_spans: only the first max_spans are stored); counts[i] = -1 when the
+ * ray misses the bbox.                                                                                          */
+int  vdbrt_volume_spans(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space,
+                        uint32_t max_spans, double* spans, int32_t* counts, uint32_t memspace);
+
+/* ---- measurement ------------------------------------------------------------------------------------------- */
+/* counters of the most recent render with counting enabled (a separate instrumented launch, never timed)       */
+int  vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
+                          const vdbrt_ls_opts* opts, vdbrt_counters* out);
+int  vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
+                        const vdbrt_vol_opts* opts, vdbrt_counters* out);
+/* device time (ms, CUDA events on the context's stream) of the kernel(s) of the last render call, and how many
+ * kernels of this library that call launched                                                                   */
+int  vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches);
+
+/* ---- grid construction on the GPU (inputs for benches) ------------------------------------
+ * Same voxel values/topology as nanovdb::tools::createLevelSetSphere/Torus (nanovdb/tools/CreatePrimitives.h:
+ * 598-664) and openvdb::tools::sdfToFogVolume (tools/LevelSetUtil.h:2190), written straight into NanoVDB layout. */
+int  vdbrt_build_levelset_sphere(vdbrt_ctx* ctx, double radius, const double center[3], double voxel_size,
+                                 double half_width, vdbrt_grid** out);
+int  vdbrt_build_levelset_torus(vdbrt_ctx* ctx, double major_radius, double minor_radius, const double center[3],
+                                double voxel_size, double half_width, vdbrt_grid** out);
+/* union (voxel-wise min, tools/Composite.h:886) of n spheres: spheres[i] = {cx,cy,cz,r} in world units          */
+int  vdbrt_build_levelset_spheres(vdbrt_ctx* ctx, const double* spheres, uint32_t n, double voxel_size,
+                                  double half_width, vdbrt_grid** out);
+/* sdfToFogVolume of an existing level-set grid (cutoff = background)                                            */
+int  vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* levelset, vdbrt_grid** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDBRT_H_INCLUDED */

@@ -1,0 +1,3 @@
+// TBB shim forwarding header (test infrastructure, see ../tbb_shim.h)
+#pragma once
+#include "../tbb_shim.h"
