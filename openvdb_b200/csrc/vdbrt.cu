@@ -1,0 +1,555 @@
+// vdbrt.cu -- host side of libvdbrt.so: the C ABI declared in include/vdbrt.h.
+//
+// Everything that computes pixels runs in the CUDA kernels of vdbrt_kernels.cuh; this file validates inputs the way
+// the reference's constructors do, flattens cameras/shaders into PODs, moves buffers and launches.  There is no CPU
+// implementation of the hot path in this library: without a CUDA device vdbrt_create() fails.
+#include "../../include/vdbrt.h"
+#include "vdbrt_kernels.cuh"
+#include "vdbrt_host.h"
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace vdbrt;
+
+namespace vdbrt {
+thread_local std::string g_error;
+int setError(int code, const std::string& msg) { g_error = msg; return code; }
+int cudaFail(cudaError_t e, const char* what) { return setError(VDBRT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+} // namespace vdbrt
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cudaFail(e_, #expr); } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensureBuffer(void** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes) return VDBRT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return VDBRT_OK;
+}
+
+constexpr uint64_t MAGIC_NUMB = 0x304244566f6e614eULL, MAGIC_GRID = 0x314244566f6e614eULL; // nanovdb/NanoVDB.h:139-140
+constexpr size_t GRID_SIZE = 672, TREE_SIZE = 64;
+constexpr size_t OFF_VERSION = 16, OFF_GRIDSIZE = 32, OFF_MATD = 384, OFF_VECD = 528, OFF_CLASS = 632, OFF_TYPE = 636;
+
+template<typename T> T rd(const uint8_t* p) { T v; std::memcpy(&v, p, sizeof(T)); return v; }
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// grid registration: header parsing (host) + node-granular bbox (device)
+// ---------------------------------------------------------------------------------------------------------------
+int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
+{
+    // header: GridData + TreeData, then RootData
+    uint8_t head[GRID_SIZE + TREE_SIZE];
+    if (grid->bytes < sizeof(head)) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    CUDA_TRY(cudaMemcpyAsync(head, grid->dev, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const uint64_t magic = rd<uint64_t>(head);
+    if (magic != MAGIC_NUMB && magic != MAGIC_GRID) return setError(VDBRT_ERR_BAD_GRID, "not a NanoVDB grid (bad magic number)");
+    if ((rd<uint32_t>(head + OFF_VERSION) >> 21) != 32) return setError(VDBRT_ERR_BAD_GRID, "incompatible NanoVDB major version (need 32)");
+    if (rd<uint64_t>(head + OFF_GRIDSIZE) > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "grid size exceeds the buffer");
+    if (rd<uint32_t>(head + OFF_TYPE) != 1) return setError(VDBRT_ERR_NOT_FLOAT, "grid value type is not float");
+    const uint8_t* tree = head + GRID_SIZE;
+    const uint64_t rootOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 24));
+    if (rootOff + 64 > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "root offset outside the buffer");
+    uint8_t rootHead[64];
+    CUDA_TRY(cudaMemcpyAsync(rootHead, grid->dev + rootOff, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+
+    vdbrt_grid_info& info = grid->info;
+    std::memset(&info, 0, sizeof(info));
+    info.bytes = grid->bytes;
+    info.leaf_count = rd<uint32_t>(tree + 32); info.lower_count = rd<uint32_t>(tree + 36); info.upper_count = rd<uint32_t>(tree + 40);
+    info.active_voxels = rd<uint64_t>(tree + 56);
+    info.root_tiles = rd<uint32_t>(rootHead + kRootTableSize);
+    info.background = rd<float>(rootHead + kRootBackground);
+    for (int i = 0; i < 6; ++i) info.index_bbox[i] = rd<int32_t>(rootHead + 4 * i);
+    info.grid_class = rd<uint32_t>(head + OFF_CLASS);
+    if (rootOff + 64 + uint64_t(info.root_tiles) * kTileSize > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "root table outside the buffer");
+
+    double m[9];
+    for (int i = 0; i < 9; ++i) m[i] = rd<double>(head + OFF_MATD + 8 * i);
+    if (m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0)
+        return setError(VDBRT_ERR_UNSUPPORTED, "only scale(+translate) index->world maps are supported");
+    DevGrid& d = grid->dgrid;
+    std::memset(&d, 0, sizeof(d));
+    d.base = grid->dev; d.root_off = rootOff; d.tiles = grid->dev + rootOff + kRootTiles;
+    d.table_size = info.root_tiles; d.background = info.background; d.grid_class = info.grid_class;
+    for (int a = 0; a < 3; ++a) {
+        d.scale[a] = m[4 * a];
+        d.inv[a] = 1.0 / d.scale[a];                    // ScaleMap: mScaleValuesInverse = 1.0 / mScaleValues (math/Maps.h:674)
+        d.trans[a] = rd<double>(head + OFF_VECD + 8 * a);
+        info.voxel_size[a] = std::fabs(d.scale[a]);     // mVoxelSize = |scale| (math/Maps.h:667)
+        info.translation[a] = d.trans[a];
+    }
+    d.has_translation = (d.trans[0] != 0 || d.trans[1] != 0 || d.trans[2] != 0) ? 1u : 0u;
+    d.voxel_size0 = info.voxel_size[0];
+
+    // node-granular bbox on the device
+    int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (info.root_tiles) {
+        const unsigned long long threads = (unsigned long long)info.root_tiles << 15;
+        k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch));
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(init, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 6; ++i) info.node_bbox[i] = init[i];
+    for (int a = 0; a < 3; ++a) { d.bbox_min[a] = init[a]; d.bbox_max[a] = init[3 + a]; }
+    return VDBRT_OK;
+}
+
+namespace {
+
+// validation the reference performs when the intersectors are constructed
+int checkLevelSet(const vdbrt_grid* g, float iso)
+{
+    const vdbrt_grid_info& i = g->info;
+    if (std::fabs(i.voxel_size[0] - i.voxel_size[1]) > 5e-7 || std::fabs(i.voxel_size[0] - i.voxel_size[2]) > 5e-7)
+        return setError(VDBRT_ERR_NONUNIFORM, "LevelSetRayIntersector only supports uniform voxels!");          // RayIntersector.h:101-104
+    if (i.grid_class != VDBRT_GRID_CLASS_LEVEL_SET)
+        return setError(VDBRT_ERR_NOT_LEVELSET, "LevelSetRayIntersector only supports level sets!");           // :105-109
+    if (i.root_tiles == 0) return setError(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids"); // :533-535
+    if (iso <= -i.background || iso >= i.background)
+        return setError(VDBRT_ERR_ISO_RANGE, "The iso-value must be inside the narrow-band!");                 // :536-539
+    return VDBRT_OK;
+}
+int checkVolume(const vdbrt_grid* g)
+{
+    const vdbrt_grid_info& i = g->info;
+    if (std::fabs(i.voxel_size[0] - i.voxel_size[1]) > 5e-7 || std::fabs(i.voxel_size[0] - i.voxel_size[2]) > 5e-7)
+        return setError(VDBRT_ERR_NONUNIFORM, "VolumeRayIntersector only supports uniform voxels!");           // :305-308
+    if (i.root_tiles == 0) return setError(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids"); // :309-311
+    return VDBRT_OK;
+}
+
+DevCamera toDev(const vdbrt_camera& c)
+{
+    DevCamera d;
+    d.kind = c.kind; d.width = c.width; d.height = c.height; d.pad = 0;
+    std::memcpy(d.m, c.m, sizeof(d.m));
+    for (int a = 0; a < 3; ++a) { d.eye[a] = c.eye[a]; d.dir[a] = c.dir[a]; }
+    d.scale_w = c.scale_w; d.scale_h = c.scale_h; d.t0 = c.t0; d.t1 = c.t1;
+    return d;
+}
+
+int persistentGrid(vdbrt_ctx* ctx, const void* kernel, unsigned items)
+{
+    int perSm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlockThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
+    const unsigned full = unsigned(ctx->sm_count) * unsigned(perSm);           // a multiple of the SM count
+    const unsigned need = (items + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
+    return int(need < full ? (need ? need : 1u) : full);
+}
+
+void ls_params(const vdbrt_grid* grid, const vdbrt_ls_opts* o, const vdbrt_film* film, LsParams& p)
+{
+    p.iso = o->iso;
+    p.vmin = o->iso - float(2 * grid->info.voxel_size[0]);      // LinearSearchImpl ctor (tools/RayIntersector.h:530-531)
+    p.vmax = o->iso + float(2 * grid->info.voxel_size[0]);
+    p.sub = o->spp - 1;
+    p.frac = 1.0f / (1.0f + float(p.sub));                       // tools/RayTracer.h:905
+    p.uniform_bg = (o->flags & VDBRT_LS_UNIFORM_BG) ? 1u : 0u;
+    for (int i = 0; i < 4; ++i) p.bg[i] = film ? film->bg_rgba[i] : 0.f;
+    for (int i = 0; i < 16; ++i) p.jitter[i] = o->jitter[i];
+}
+
+void vol_params(const vdbrt_vol_opts* o, VolParams& p)
+{
+    p.pstep = o->primary_step; p.sstep = o->shadow_step; p.cutoff = o->cutoff; p.gain = o->light_gain;
+    for (int a = 0; a < 3; ++a) {
+        p.light[a] = o->light_dir[a];
+        p.ext[a] = -o->scattering[a] - o->absorption[a];                                        // tools/RayTracer.h:996
+        p.albedo[a] = o->light_color[a] * o->scattering[a] / (o->scattering[a] + o->absorption[a]); // :997
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* vdbrt_last_error(void) { return g_error.c_str(); }
+
+int vdbrt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int vdbrt_create(int device, vdbrt_ctx** out)
+{
+    if (!out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return setError(VDBRT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); }
+    if (device < 0 || device >= n) return setError(VDBRT_ERR_INVALID_ARG, "device index out of range");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return setError(VDBRT_ERR_CUDA, "kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    auto* ctx = new vdbrt_ctx;
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaMalloc(&ctx->scratch, 4096));
+    CUDA_TRY(cudaMemset(ctx->scratch, 0, 4096));
+    *out = ctx;
+    return VDBRT_OK;
+}
+
+void vdbrt_destroy(vdbrt_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->film) cudaFree(ctx->film);
+    if (ctx->aux) cudaFree(ctx->aux);
+    if (ctx->io) cudaFree(ctx->io);
+    cudaFree(ctx->scratch);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int vdbrt_set_stream(vdbrt_ctx* ctx, void* stream)
+{
+    if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
+    ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+    return VDBRT_OK;
+}
+
+int vdbrt_synchronize(vdbrt_ctx* ctx)
+{
+    if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return VDBRT_OK;
+}
+int vdbrt_host_free(void* p) { CUDA_TRY(cudaFreeHost(p)); return VDBRT_OK; }
+
+int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out)
+{
+    if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (bytes < GRID_SIZE + TREE_SIZE) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    DeviceGuard guard(ctx->device);
+    auto* g = new vdbrt_grid;
+    g->bytes = bytes; g->device = ctx->device;
+    cudaError_t e = cudaMalloc(&g->dev, bytes);
+    if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
+    e = cudaMemcpyAsync(g->dev, buffer, bytes, memspace == VDBRT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(g->dev); delete g; return cudaFail(e, "cudaMemcpyAsync(grid)"); }
+    const int rc = finishGrid(ctx, g);
+    if (rc != VDBRT_OK) { cudaFree(g->dev); delete g; return rc; }
+    *out = g;
+    return VDBRT_OK;
+}
+
+int vdbrt_free_grid(vdbrt_ctx* ctx, vdbrt_grid* grid)
+{
+    if (!grid) return VDBRT_OK;
+    DeviceGuard guard(grid->device);
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(grid->dev);
+    delete grid;
+    return VDBRT_OK;
+}
+
+int vdbrt_grid_get_info(const vdbrt_grid* grid, vdbrt_grid_info* info)
+{
+    if (!grid || !info) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    *info = grid->info;
+    return VDBRT_OK;
+}
+
+int vdbrt_grid_download(vdbrt_ctx* ctx, const vdbrt_grid* grid, void* dst, uint64_t bytes)
+{
+    if (!ctx || !grid || !dst) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (bytes < grid->bytes) return setError(VDBRT_ERR_INVALID_ARG, "destination too small");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaMemcpyAsync(dst, grid->dev, grid->bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LevelSetRayTracer::render
+// ---------------------------------------------------------------------------------------------------------------
+static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_shader* shader,
+                          const vdbrt_ls_opts* opts, const vdbrt_film* film, float4* dFilm, const AuxOut& aux, bool wantAux,
+                          unsigned long long* dCounters)
+{
+    LsParams p; ls_params(grid, opts, film, p);
+    const TileMap tm = makeTileMap(film->width, film->height, opts->part.tile_w, opts->part.tile_h, opts->part.rank, opts->part.count);
+    DevShader sh;
+    sh.kind = shader->kind; sh.r = shader->rgba[0]; sh.g = shader->rgba[1]; sh.b = shader->rgba[2]; sh.a = shader->rgba[3];
+    for (int a = 0; a < 3; ++a) { sh.bmin[a] = shader->bbox_min[a]; sh.inv[a] = shader->inv_dim[a]; }
+    const DevCamera dc = toDev(*cam);
+    unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
+    CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (dCounters) {
+        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<false, true>, tm.items);
+        k_render_levelset<false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters);
+    } else if (wantAux) {
+        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<true, false>, tm.items);
+        k_render_levelset<true, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr);
+    } else {
+        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<false, false>, tm.items);
+        k_render_levelset<false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = 1;
+    return VDBRT_OK;
+}
+
+int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_shader* shader,
+                          const vdbrt_ls_opts* opts, vdbrt_film* film, vdbrt_aux* aux)
+{
+    if (!ctx || !grid || !cam || !shader || !opts || !film || !film->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (film->width == 0 || film->height == 0) return setError(VDBRT_ERR_INVALID_ARG, "empty film");
+    if (cam->width != film->width || cam->height != film->height) return setError(VDBRT_ERR_INVALID_ARG, "camera was built for a different film size");
+    if (shader->kind > VDBRT_SHADER_DIFFUSE) return setError(VDBRT_ERR_UNSUPPORTED, "only the four constant-colour shaders run on the device");
+    if (opts->spp == 0) return setError(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
+    if (int rc = checkLevelSet(grid, opts->iso)) return rc;
+    DeviceGuard guard(ctx->device);
+    const size_t npx = size_t(film->width) * film->height;
+    const bool host = film->memspace == VDBRT_MEM_HOST;
+    float4* dFilm = reinterpret_cast<float4*>(film->pixels);
+    if (host) {
+        if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
+        dFilm = static_cast<float4*>(ctx->film);
+        // level-set misses keep the previous pixel, so the film is an input too (tools/RayTracer.h:908)
+        if (!(opts->flags & VDBRT_LS_UNIFORM_BG)) CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        else if (opts->part.count > 1) {
+            // other ranks' pixels must come back unchanged: start from the caller's film
+            CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    AuxOut a = {};
+    const bool wantAux = aux && (aux->hit || aux->ijk || aux->t_index || aux->t_world || aux->xyz || aux->nml);
+    // aux layout in the staging buffer: hit[npx] | pad | ijk[3npx] | t_index | t_world | xyz | nml
+    size_t offIjk = 0, offTi = 0, offTw = 0, offXyz = 0, offNml = 0, auxBytes = 0;
+    if (wantAux) {
+        if (host) {
+            offIjk = (npx + 255) & ~size_t(255); offTi = offIjk + npx * 12; offTi = (offTi + 255) & ~size_t(255);
+            offTw = offTi + npx * 8; offXyz = offTw + npx * 8; offNml = offXyz + npx * 24; auxBytes = offNml + npx * 24;
+            if (int rc = ensureBuffer(&ctx->aux, &ctx->aux_cap, auxBytes)) return rc;
+            CUDA_TRY(cudaMemsetAsync(ctx->aux, 0, auxBytes, ctx->stream));
+            uint8_t* b = static_cast<uint8_t*>(ctx->aux);
+            a.hit = aux->hit ? b : nullptr; a.ijk = aux->ijk ? reinterpret_cast<int32_t*>(b + offIjk) : nullptr;
+            a.t_index = aux->t_index ? reinterpret_cast<double*>(b + offTi) : nullptr;
+            a.t_world = aux->t_world ? reinterpret_cast<double*>(b + offTw) : nullptr;
+            a.xyz = aux->xyz ? reinterpret_cast<double*>(b + offXyz) : nullptr;
+            a.nml = aux->nml ? reinterpret_cast<double*>(b + offNml) : nullptr;
+        } else {
+            a.hit = aux->hit; a.ijk = aux->ijk; a.t_index = aux->t_index; a.t_world = aux->t_world; a.xyz = aux->xyz; a.nml = aux->nml;
+        }
+    }
+    if (int rc = launchLevelSet(ctx, grid, cam, shader, opts, film, dFilm, a, wantAux, nullptr)) return rc;
+    if (host) {
+        CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (wantAux) {
+            const uint8_t* b = static_cast<const uint8_t*>(ctx->aux);
+            if (aux->hit) CUDA_TRY(cudaMemcpyAsync(aux->hit, b, npx, cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux->ijk) CUDA_TRY(cudaMemcpyAsync(aux->ijk, b + offIjk, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux->t_index) CUDA_TRY(cudaMemcpyAsync(aux->t_index, b + offTi, npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux->t_world) CUDA_TRY(cudaMemcpyAsync(aux->t_world, b + offTw, npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux->xyz) CUDA_TRY(cudaMemcpyAsync(aux->xyz, b + offXyz, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux->nml) CUDA_TRY(cudaMemcpyAsync(aux->nml, b + offNml, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_ls_opts* opts, vdbrt_counters* out)
+{
+    if (!ctx || !grid || !cam || !opts || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (opts->spp == 0) return setError(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
+    if (int rc = checkLevelSet(grid, opts->iso)) return rc;
+    DeviceGuard guard(ctx->device);
+    const size_t npx = size_t(cam->width) * cam->height;
+    if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;      // scratch film, discarded
+    CUDA_TRY(cudaMemsetAsync(ctx->io, 0, npx * 16, ctx->stream));
+    unsigned long long* dC = reinterpret_cast<unsigned long long*>(ctx->scratch + 128);
+    CUDA_TRY(cudaMemsetAsync(dC, 0, 10 * sizeof(unsigned long long), ctx->stream));
+    vdbrt_film film = {}; film.width = cam->width; film.height = cam->height;
+    vdbrt_shader sh = {}; sh.kind = VDBRT_SHADER_DIFFUSE; sh.rgba[0] = sh.rgba[1] = sh.rgba[2] = sh.rgba[3] = 1.f;
+    AuxOut a = {};
+    if (int rc = launchLevelSet(ctx, grid, cam, &sh, opts, &film, static_cast<float4*>(ctx->io), a, false, dC)) return rc;
+    unsigned long long h[10];
+    CUDA_TRY(cudaMemcpyAsync(h, dC, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out->rays = h[0]; out->root_probes = h[1]; out->upper_probes = h[2]; out->lower_probes = h[3]; out->voxel_probes = h[4];
+    out->stencil_refills = h[5]; out->primary_samples = h[6]; out->shadow_samples = h[7]; out->shadow_rays = h[8]; out->hits = h[9];
+    return VDBRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VolumeRender::render
+// ---------------------------------------------------------------------------------------------------------------
+static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_vol_opts* opts,
+                        uint32_t width, uint32_t height, float4* dFilm, unsigned long long* dCounters)
+{
+    VolParams p; vol_params(opts, p);
+    const TileMap tm = makeTileMap(width, height, opts->part.tile_w, opts->part.tile_h, opts->part.rank, opts->part.count);
+    const DevCamera dc = toDev(*cam);
+    unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
+    CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (dCounters) {
+        const int blocks = persistentGrid(ctx, (const void*)k_render_volume<true>, tm.items);
+        k_render_volume<true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, dCounters);
+    } else {
+        const int blocks = persistentGrid(ctx, (const void*)k_render_volume<false>, tm.items);
+        k_render_volume<false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = 1;
+    return VDBRT_OK;
+}
+
+int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_vol_opts* opts, vdbrt_film* film)
+{
+    if (!ctx || !grid || !cam || !opts || !film || !film->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (film->width == 0 || film->height == 0) return setError(VDBRT_ERR_INVALID_ARG, "empty film");
+    if (cam->width != film->width || cam->height != film->height) return setError(VDBRT_ERR_INVALID_ARG, "camera was built for a different film size");
+    if (int rc = checkVolume(grid)) return rc;
+    DeviceGuard guard(ctx->device);
+    const size_t npx = size_t(film->width) * film->height;
+    const bool host = film->memspace == VDBRT_MEM_HOST;
+    float4* dFilm = reinterpret_cast<float4*>(film->pixels);
+    if (host) {
+        if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
+        dFilm = static_cast<float4*>(ctx->film);
+        // every owned pixel is overwritten (tools/RayTracer.h:1020); only a partitioned render needs the old film
+        if (opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (int rc = launchVolume(ctx, grid, cam, opts, film->width, film->height, dFilm, nullptr)) return rc;
+    if (host) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_vol_opts* opts, vdbrt_counters* out)
+{
+    if (!ctx || !grid || !cam || !opts || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (int rc = checkVolume(grid)) return rc;
+    DeviceGuard guard(ctx->device);
+    const size_t npx = size_t(cam->width) * cam->height;
+    if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;
+    unsigned long long* dC = reinterpret_cast<unsigned long long*>(ctx->scratch + 128);
+    CUDA_TRY(cudaMemsetAsync(dC, 0, 10 * sizeof(unsigned long long), ctx->stream));
+    if (int rc = launchVolume(ctx, grid, cam, opts, cam->width, cam->height, static_cast<float4*>(ctx->io), dC)) return rc;
+    unsigned long long h[10];
+    CUDA_TRY(cudaMemcpyAsync(h, dC, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out->rays = h[0]; out->root_probes = h[1]; out->upper_probes = h[2]; out->lower_probes = h[3]; out->voxel_probes = h[4];
+    out->stencil_refills = h[5]; out->primary_samples = h[6]; out->shadow_samples = h[7]; out->shadow_rays = h[8]; out->hits = h[9];
+    return VDBRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// arbitrary-ray batches
+// ---------------------------------------------------------------------------------------------------------------
+int vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso,
+                             vdbrt_hit* hits, uint32_t memspace)
+{
+    if (!ctx || !grid || (n && (!rays || !hits))) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (int rc = checkLevelSet(grid, iso)) return rc;
+    if (n == 0) return VDBRT_OK;
+    static_assert(sizeof(vdbrt_ray) == sizeof(RayIn) && sizeof(vdbrt_hit) == sizeof(HitOut), "POD mismatch");
+    DeviceGuard guard(ctx->device);
+    const RayIn* dR = reinterpret_cast<const RayIn*>(rays);
+    HitOut* dH = reinterpret_cast<HitOut*>(hits);
+    const size_t rb = n * sizeof(RayIn), hb = n * sizeof(HitOut);
+    if (memspace == VDBRT_MEM_HOST) {
+        if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, rb + hb + 256)) return rc;
+        uint8_t* b = static_cast<uint8_t*>(ctx->io);
+        CUDA_TRY(cudaMemcpyAsync(b, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
+        dR = reinterpret_cast<const RayIn*>(b);
+        dH = reinterpret_cast<HitOut*>(b + ((rb + 255) & ~size_t(255)));
+    }
+    const float vmin = iso - float(2 * grid->info.voxel_size[0]), vmax = iso + float(2 * grid->info.voxel_size[0]);
+    const unsigned blocks = unsigned(std::min<uint64_t>((n + kBlockThreads - 1) / kBlockThreads, uint64_t(ctx->sm_count) * 16));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    k_intersect_levelset<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = 1;
+    if (memspace == VDBRT_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(hits, dH, hb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_volume_spans(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space, uint32_t maxSpans,
+                       double* spans, int32_t* counts, uint32_t memspace)
+{
+    if (!ctx || !grid || (n && (!rays || !spans || !counts))) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (int rc = checkVolume(grid)) return rc;
+    if (n == 0) return VDBRT_OK;
+    DeviceGuard guard(ctx->device);
+    const RayIn* dR = reinterpret_cast<const RayIn*>(rays);
+    double* dS = spans; int32_t* dC = counts;
+    const size_t rb = (n * sizeof(RayIn) + 255) & ~size_t(255), sb = (n * maxSpans * 16 + 255) & ~size_t(255), cb = n * 4;
+    if (memspace == VDBRT_MEM_HOST) {
+        if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, rb + sb + cb)) return rc;
+        uint8_t* b = static_cast<uint8_t*>(ctx->io);
+        CUDA_TRY(cudaMemcpyAsync(b, rays, n * sizeof(RayIn), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(b + rb, 0, sb + cb, ctx->stream));
+        dR = reinterpret_cast<const RayIn*>(b); dS = reinterpret_cast<double*>(b + rb); dC = reinterpret_cast<int32_t*>(b + rb + sb);
+    }
+    const unsigned blocks = unsigned(std::min<uint64_t>((n + kBlockThreads - 1) / kBlockThreads, uint64_t(ctx->sm_count) * 16));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    k_volume_spans<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, maxSpans, dS, dC);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = 1;
+    if (memspace == VDBRT_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(spans, dS, n * maxSpans * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(counts, dC, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches)
+{
+    if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
+    DeviceGuard guard(ctx->device);
+    if (ms) { CUDA_TRY(cudaEventSynchronize(ctx->ev1)); CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1)); }
+    if (launches) *launches = ctx->last_launches;
+    return VDBRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,566 @@
+// vdbrt_device.cuh -- device-side building blocks of the sm_100a ray-tracing kernels.
+//
+// Data layout is NanoVDB's (NanoGrid<float>, nanovdb/nanovdb/NanoVDB.h:67-122); the ALGORITHM and PRECISION are
+// OpenVDB's CPU RayTracer: double rays / DDA / hit times, float voxel values and stencil maths,
+// no FMA contraction anywhere (this translation unit is compiled with --fmad=false; division and sqrt are IEEE).
+// Paths in comments are relative to the OpenVDB tree (openvdb/openvdb/...).
+//
+// Design (B200-first, not a translation of the reference's nested C++ templates):
+//   * TreeCursor  -- register-resident root/upper/lower/leaf path cache.  One cached coordinate + three 32-bit
+//                    node handles (byte offset >> 5, nodes are 32 B aligned); a probe XORs the query with the
+//                    cached coordinate and re-descends only from the first level that differs.  The root tile
+//                    table lives in shared memory.  All grid reads are ld.global.nc.
+//   * HDDA        -- the reference nests four fixed-stride DDAs as recursive template calls.  Here ONE DDA lives
+//                    in registers and the suspended parent levels are parked in explicit save slots, so every
+//                    lane of a warp executes the same "probe / step / descend / ascend" loop body whatever level
+//                    it is on (no per-level code replication, no dynamic register indexing).  Per-level deltas
+//                    are recomputed as double(+-DIM)*invDir, the reference's own expression, instead of stored.
+//   * the same cursor drives the fog path as a resumable span generator (VolumeHDDA::hits without the std::vector).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vdbrt {
+
+// ---- NanoVDB offsets (GridData :1944-2135, TreeData :2393-2423, RootData :2621-2695, InternalData :3181-3291,
+//      LeafData<float> :3671-3746)
+constexpr uint32_t kRootTableSize = 24, kRootBackground = 28, kRootTiles = 64, kTileSize = 32;
+constexpr uint32_t kUpperVMask = 32, kUpperCMask = 32 + 4096, kUpperTable = 8256;
+constexpr uint32_t kLowerVMask = 32, kLowerCMask = 32 + 512, kLowerTable = 1088;
+constexpr uint32_t kLeafVMask = 16, kLeafValues = 96;
+constexpr int kMaxSmemTiles = 96;
+
+struct DevGrid {
+    const uint8_t* base;      // device copy of the serialised grid (GridData at offset 0)
+    const uint8_t* tiles;     // RootData::Tile array (device)
+    uint64_t root_off;        // byte offset of RootData from base (root tile children are relative to it)
+    uint32_t table_size;
+    float    background;
+    double   scale[3], inv[3], trans[3];
+    int32_t  bbox_min[3], bbox_max[3];   // node-granular bbox, max as CoordBBox stores it (no +1)
+    uint32_t has_translation;
+    uint32_t grid_class;
+    double   voxel_size0;
+};
+
+struct RootSmem {
+    unsigned long long key[kMaxSmemTiles];
+    uint32_t child[kMaxSmemTiles];   // node handle (offset>>5 from base), 0 = value tile
+    uint32_t state[kMaxSmemTiles];
+    float    value[kMaxSmemTiles];
+    uint32_t count;                  // tiles staged; == table_size unless the table is too large
+    uint32_t staged;
+};
+
+__device__ __forceinline__ unsigned long long ldg64(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ long long ldgs64(const uint8_t* p) { return __ldg(reinterpret_cast<const long long*>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ float ldgf(const uint8_t* p) { return __ldg(reinterpret_cast<const float*>(p)); }
+__device__ __forceinline__ bool maskBit(const uint8_t* mask, uint32_t n) { return (ldg64(mask + 8u * (n >> 6)) >> (n & 63u)) & 1ull; }
+
+// RootData::CoordToKey with NANOVDB_USE_SINGLE_ROOT_KEY (NanoVDB.h:2630-2640)
+__device__ __forceinline__ unsigned long long rootKey(int x, int y, int z) {
+    return (unsigned long long)(uint32_t(z) >> 12) | ((unsigned long long)(uint32_t(y) >> 12) << 21) | ((unsigned long long)(uint32_t(x) >> 12) << 42);
+}
+__device__ __forceinline__ uint32_t upperOffset(int x, int y, int z) { return (((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7); }
+__device__ __forceinline__ uint32_t lowerOffset(int x, int y, int z) { return (((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3); }
+__device__ __forceinline__ uint32_t leafOffset(int x, int y, int z) { return ((x & 7) << 6) | ((y & 7) << 3) | (z & 7); }
+
+// cooperative staging of the root table into shared memory (call from all threads of the CTA, then __syncthreads)
+__device__ __forceinline__ void stageRoot(const DevGrid& g, RootSmem& s)
+{
+    const uint32_t n = g.table_size <= (uint32_t)kMaxSmemTiles ? g.table_size : 0u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint8_t* t = g.tiles + kTileSize * i;
+        s.key[i] = ldg64(t);
+        const long long child = ldgs64(t + 8);
+        s.child[i] = child ? uint32_t((g.root_off + (unsigned long long)child) >> 5) : 0u;
+        s.state[i] = ldg32(t + 16);
+        s.value[i] = ldgf(t + 20);
+    }
+    if (threadIdx.x == 0) { s.count = n; s.staged = (n == g.table_size); }
+}
+
+struct Counters {   // per-thread work counters of the instrumented (never timed) launches
+    uint32_t root, upper, lower, voxel, refills, psamples, ssamples, srays, hits, rays;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// TreeCursor: semantics of tree::ValueAccessor::probeConstNode / probeValue / getValue / isValueOn
+// (tree/ValueAccessor.h:455-510,805-830,937-953) on the NanoVDB node arrays.
+// ------------------------------------------------------------------------------------------------------------
+struct TreeCursor {
+    int kx, ky, kz;          // coordinate of the last descent
+    uint32_t n2, n1, n0;     // handles of the upper / lower / leaf node containing (kx,ky,kz); 0 = none
+
+    __device__ __forceinline__ void reset() { kx = ky = kz = 0; n2 = n1 = n0 = 0u; }
+    __device__ __forceinline__ static const uint8_t* node(const DevGrid& g, uint32_t h) { return g.base + ((unsigned long long)h << 5); }
+
+    // root table search (RootNode::probeChild / findTile, NanoVDB.h:2785-2799): index of the tile or -1
+    __device__ __forceinline__ static int findTile(const DevGrid& g, const RootSmem& s, int x, int y, int z)
+    {
+        const unsigned long long key = rootKey(x, y, z);
+        if (s.staged) {
+            for (uint32_t i = 0; i < s.count; ++i) if (s.key[i] == key) return int(i);
+            return -1;
+        }
+        for (uint32_t i = 0; i < g.table_size; ++i) if (ldg64(g.tiles + kTileSize * i) == key) return int(i);
+        return -1;
+    }
+    __device__ __forceinline__ static uint32_t tileChild(const DevGrid& g, const RootSmem& s, int i)
+    {
+        if (s.staged) return s.child[i];
+        const long long child = ldgs64(g.tiles + kTileSize * i + 8);
+        return child ? uint32_t((g.root_off + (unsigned long long)child) >> 5) : 0u;
+    }
+
+    // Re-descend from the first level whose node does not contain (x,y,z).  Returns the depth reached:
+    // 0 = leaf, 1 = lower node (no leaf), 2 = upper node (no lower), 3 = nothing below the root.
+    __device__ __forceinline__ int descend(const DevGrid& g, const RootSmem& s, int x, int y, int z)
+    {
+        const uint32_t d = uint32_t((x ^ kx) | (y ^ ky) | (z ^ kz));
+        if (n0 && !(d & ~7u)) return 0;
+        if (!(n1 && !(d & ~127u))) {
+            if (!(n2 && !(d & ~4095u))) {
+                const int t = findTile(g, s, x, y, z);
+                n2 = t >= 0 ? tileChild(g, s, t) : 0u;
+            }
+            n1 = 0u;
+            if (n2) {
+                const uint8_t* u = node(g, n2);
+                const uint32_t n = upperOffset(x, y, z);
+                if (maskBit(u + kUpperCMask, n))      // child offset is relative to this InternalData (:3190-3199)
+                    n1 = uint32_t((((unsigned long long)n2 << 5) + (unsigned long long)ldgs64(u + kUpperTable + 8u * n)) >> 5);
+            }
+        }
+        n0 = 0u;
+        if (n1) {
+            const uint8_t* l = node(g, n1);
+            const uint32_t n = lowerOffset(x, y, z);
+            if (maskBit(l + kLowerCMask, n))
+                n0 = uint32_t((((unsigned long long)n1 << 5) + (unsigned long long)ldgs64(l + kLowerTable + 8u * n)) >> 5);
+        }
+        kx = x; ky = y; kz = z;
+        return n0 ? 0 : (n1 ? 1 : (n2 ? 2 : 3));
+    }
+
+    // value and active state at the deepest node containing the coordinate (after descend())
+    __device__ __forceinline__ bool valueAt(const DevGrid& g, const RootSmem& s, int depth, int x, int y, int z, float& v) const
+    {
+        if (depth == 0) { const uint8_t* p = node(g, n0); const uint32_t n = leafOffset(x, y, z); v = ldgf(p + kLeafValues + 4u * n); return maskBit(p + kLeafVMask, n); }
+        if (depth == 1) { const uint8_t* p = node(g, n1); const uint32_t n = lowerOffset(x, y, z); v = ldgf(p + kLowerTable + 8u * n); return maskBit(p + kLowerVMask, n); }
+        if (depth == 2) { const uint8_t* p = node(g, n2); const uint32_t n = upperOffset(x, y, z); v = ldgf(p + kUpperTable + 8u * n); return maskBit(p + kUpperVMask, n); }
+        const int t = findTile(g, s, x, y, z);
+        if (t < 0) { v = g.background; return false; }
+        if (s.staged) { v = s.value[t]; return s.state[t] != 0u; }
+        v = ldgf(g.tiles + kTileSize * t + 20); return ldg32(g.tiles + kTileSize * t + 16) != 0u;
+    }
+    __device__ __forceinline__ bool activeAt(const DevGrid& g, const RootSmem& s, int depth, int x, int y, int z) const
+    {
+        if (depth == 0) return maskBit(node(g, n0) + kLeafVMask, leafOffset(x, y, z));
+        if (depth == 1) return maskBit(node(g, n1) + kLowerVMask, lowerOffset(x, y, z));
+        if (depth == 2) return maskBit(node(g, n2) + kUpperVMask, upperOffset(x, y, z));
+        const int t = findTile(g, s, x, y, z);
+        if (t < 0) return false;
+        return (s.staged ? s.state[t] : ldg32(g.tiles + kTileSize * t + 16)) != 0u;
+    }
+    __device__ __forceinline__ bool probeValue(const DevGrid& g, const RootSmem& s, int x, int y, int z, float& v)
+    {
+        const int depth = descend(g, s, x, y, z);
+        return valueAt(g, s, depth, x, y, z, v);
+    }
+    __device__ __forceinline__ float getValue(const DevGrid& g, const RootSmem& s, int x, int y, int z)
+    {
+        float v; probeValue(g, s, x, y, z, v); return v;
+    }
+
+    // the 8 corners of the cell (x..x+1, y..y+1, z..z+1) in BoxStencil slot order 000,001,011,010,100,101,111,110
+    // (math/Stencils.h:285-293,414-423; same order as BoxSampler::probeValues, tools/Interpolation.h:663-689).
+    // Fast path: the whole cell lies inside one leaf -> eight loads off one base pointer.
+    __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
+    {
+        const int depth = descend(g, s, x, y, z);
+        if (depth == 0 && (x & 7) < 7 && (y & 7) < 7 && (z & 7) < 7) {
+            const float* p = reinterpret_cast<const float*>(node(g, n0) + kLeafValues) + leafOffset(x, y, z);
+            v[0] = __ldg(p);      v[1] = __ldg(p + 1);  v[2] = __ldg(p + 9);  v[3] = __ldg(p + 8);
+            v[4] = __ldg(p + 64); v[5] = __ldg(p + 65); v[6] = __ldg(p + 73); v[7] = __ldg(p + 72);
+            return;
+        }
+        if (depth == 1 && (x & 7) < 7 && (y & 7) < 7 && (z & 7) < 7) {     // whole cell inside one lower-node tile
+            const float t = ldgf(node(g, n1) + kLowerTable + 8u * lowerOffset(x, y, z));
+            v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = t;
+            return;
+        }
+        valueAt(g, s, depth, x, y, z, v[0]);
+        v[1] = getValue(g, s, x, y, z + 1);
+        v[2] = getValue(g, s, x, y + 1, z + 1);
+        v[3] = getValue(g, s, x, y + 1, z);
+        v[4] = getValue(g, s, x + 1, y, z);
+        v[5] = getValue(g, s, x + 1, y, z + 1);
+        v[6] = getValue(g, s, x + 1, y + 1, z + 1);
+        v[7] = getValue(g, s, x + 1, y + 1, z);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// math::Ray<double> (math/Ray.h:26-295) and the grid's ScaleMap / ScaleTranslateMap (math/Maps.h:726-771,1255-1290)
+// ------------------------------------------------------------------------------------------------------------
+struct Ray {
+    double ex, ey, ez, dx, dy, dz, ix, iy, iz, t0, t1;
+    __device__ __forceinline__ void setDir(double x, double y, double z) { dx = x; dy = y; dz = z; ix = 1 / x; iy = 1 / y; iz = 1 / z; } // Ray.h:67-71
+};
+
+__device__ __forceinline__ double vlength(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }  // math/Vec3.h:201-207
+// Vec3::normalize (math/Vec3.h:363-371): isApproxEqual(d, 0, 1e-7) == !(|d-0| > 1e-7) (math/Math.h:428-431)
+__device__ __forceinline__ void vnormalize(double& x, double& y, double& z)
+{
+    const double d = vlength(x, y, z);
+    if (!(fabs(d - 0.0) > 1.0e-7)) return;
+    const double s = 1.0 / d;
+    x *= s; y *= s; z *= s;
+}
+
+// Ray::intersects(bbox,t0,t1) + clip (math/Ray.h:233-267).  pad = 0 for level sets (CoordBBox max as is),
+// pad = 1 for VolumeRayIntersector (mBBox.max().offset(1), tools/RayIntersector.h:318).
+__device__ __forceinline__ bool clipRay(Ray& r, const DevGrid& g, int pad)
+{
+    double a0 = r.t0, a1 = r.t1;
+    {
+        double a = (g.bbox_min[0] - r.ex) * r.ix, b = ((g.bbox_max[0] + pad) - r.ex) * r.ix;
+        if (a > b) { const double t = a; a = b; b = t; }
+        if (a > a0) a0 = a;
+        if (b < a1) a1 = b;
+        if (a0 > a1) return false;
+    }
+    {
+        double a = (g.bbox_min[1] - r.ey) * r.iy, b = ((g.bbox_max[1] + pad) - r.ey) * r.iy;
+        if (a > b) { const double t = a; a = b; b = t; }
+        if (a > a0) a0 = a;
+        if (b < a1) a1 = b;
+        if (a0 > a1) return false;
+    }
+    {
+        double a = (g.bbox_min[2] - r.ez) * r.iz, b = ((g.bbox_max[2] + pad) - r.ez) * r.iz;
+        if (a > b) { const double t = a; a = b; b = t; }
+        if (a > a0) a0 = a;
+        if (b < a1) a1 = b;
+        if (a0 > a1) return false;
+    }
+    r.t0 = a0; r.t1 = a1;
+    return true;
+}
+
+// Ray::worldToIndex == applyInverseMap (math/Ray.h:150-159)
+__device__ __forceinline__ void worldToIndex(const DevGrid& g, Ray& r)
+{
+    double x, y, z;
+    if (g.has_translation) { x = (r.ex - g.trans[0]) * g.inv[0]; y = (r.ey - g.trans[1]) * g.inv[1]; z = (r.ez - g.trans[2]) * g.inv[2]; }
+    else { x = r.ex * g.inv[0]; y = r.ey * g.inv[1]; z = r.ez * g.inv[2]; }
+    r.ex = x; r.ey = y; r.ez = z;
+    const double jx = r.dx * g.inv[0], jy = r.dy * g.inv[1], jz = r.dz * g.inv[2];
+    const double len = vlength(jx, jy, jz);
+    r.setDir(jx / len, jy / len, jz / len);
+    r.t0 = len * r.t0; r.t1 = len * r.t1;
+}
+__device__ __forceinline__ void indexToWorldPos(const DevGrid& g, double& x, double& y, double& z)
+{
+    if (g.has_translation) { x = x * g.scale[0] + g.trans[0]; y = y * g.scale[1] + g.trans[1]; z = z * g.scale[2] + g.trans[2]; }
+    else { x = x * g.scale[0]; y = y * g.scale[1]; z = z * g.scale[2]; }
+}
+__device__ __forceinline__ void worldToIndexPos(const DevGrid& g, double& x, double& y, double& z)
+{
+    if (g.has_translation) { x = (x - g.trans[0]) * g.inv[0]; y = (y - g.trans[1]) * g.inv[1]; z = (z - g.trans[2]) * g.inv[2]; }
+    else { x = x * g.inv[0]; y = y * g.inv[1]; z = z * g.inv[2]; }
+}
+
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // std::min
+
+// ------------------------------------------------------------------------------------------------------------
+// One math::DDA<Ray,Log2Dim> (math/DDA.h:34-127) with the stride as a run-time shift.
+// ------------------------------------------------------------------------------------------------------------
+struct Dda {
+    double t0, t1, nx, ny, nz;
+    int vx, vy, vz;
+
+    // DDA::init(ray, startTime, maxTime) (DDA.h:52-75)
+    __device__ __forceinline__ void init(const Ray& r, double start, double maxT, int shift)
+    {
+        const int dim = 1 << shift;
+        t0 = start; t1 = maxT;
+        const double px = r.ex + r.dx * t0, py = r.ey + r.dy * t0, pz = r.ez + r.dz * t0;
+        vx = int(floor(px)) & ~(dim - 1); vy = int(floor(py)) & ~(dim - 1); vz = int(floor(pz)) & ~(dim - 1);
+        nx = r.dx == 0.0 ? DBL_MAX : (r.ix > 0 ? t0 + ((vx + dim) - px) * r.ix : t0 + (vx - px) * r.ix);
+        ny = r.dy == 0.0 ? DBL_MAX : (r.iy > 0 ? t0 + ((vy + dim) - py) * r.iy : t0 + (vy - py) * r.iy);
+        nz = r.dz == 0.0 ? DBL_MAX : (r.iz > 0 ? t0 + ((vz + dim) - pz) * r.iz : t0 + (vz - pz) * r.iz);
+    }
+    // DDA::step (DDA.h:83-90); MinIndex ties go to the largest index (math/Math.h:999-1007).
+    // step/delta are rebuilt from the ray: step = 0/+DIM/-DIM, delta = DBL_MAX or double(step)*inv (DDA.h:61-73)
+    __device__ __forceinline__ bool step(const Ray& r, int shift)
+    {
+        const int dim = 1 << shift;
+        int axis = 0;
+        double m = nx;
+        if (ny <= m) { axis = 1; m = ny; }
+        if (nz <= m) { axis = 2; m = nz; }
+        t0 = m;
+        if (axis == 0) { const int st = r.dx == 0.0 ? 0 : (r.ix > 0 ? dim : -dim); nx += (r.dx == 0.0 ? DBL_MAX : st * r.ix); vx += st; }
+        else if (axis == 1) { const int st = r.dy == 0.0 ? 0 : (r.iy > 0 ? dim : -dim); ny += (r.dy == 0.0 ? DBL_MAX : st * r.iy); vy += st; }
+        else { const int st = r.dz == 0.0 ? 0 : (r.iz > 0 ? dim : -dim); nz += (r.dz == 0.0 ? DBL_MAX : st * r.iz); vz += st; }
+        return t0 <= t1;
+    }
+    // DDA::next = math::Min(mT1, mNext[0], mNext[1], mNext[2]) (DDA.h:112, Math.h:734-738)
+    __device__ __forceinline__ double next() const { return dmin(dmin(t1, nx), dmin(ny, nz)); }
+};
+
+struct DdaSave { double t1, nx, ny, nz; int vx, vy, vz; };   // a suspended parent level (its t0 is rewritten by step())
+__device__ __forceinline__ void park(DdaSave& s, const Dda& d) { s.t1 = d.t1; s.nx = d.nx; s.ny = d.ny; s.nz = d.nz; s.vx = d.vx; s.vy = d.vy; s.vz = d.vz; }
+__device__ __forceinline__ void unpark(Dda& d, const DdaSave& s) { d.t1 = s.t1; d.nx = s.nx; d.ny = s.ny; d.nz = s.nz; d.vx = s.vx; d.vy = s.vy; d.vz = s.vz; }
+
+// ------------------------------------------------------------------------------------------------------------
+// math::BoxStencil<FloatGrid> (math/Stencils.h:85-90,335-423)
+// ------------------------------------------------------------------------------------------------------------
+struct Stencil {
+    int cx, cy, cz;
+    float v[8];
+    __device__ __forceinline__ void reset() { cx = cy = cz = 0x7fffffff; }    // BaseStencil: mCenter(Coord::max()) (:212)
+
+    template<bool COUNT>
+    __device__ __forceinline__ void moveTo(const DevGrid& g, const RootSmem& s, TreeCursor& acc, double x, double y, double z, Counters& c)
+    {
+        const int i = int(floor(x)), j = int(floor(y)), k = int(floor(z));
+        if (i == cx && j == cy && k == cz) return;
+        cx = i; cy = j; cz = k;
+        if (COUNT) ++c.refills;
+        acc.fetchCell(g, s, i, j, k, v);
+    }
+    // interpolation(Vec3<float>) (:335-360): position converted to float first; every lerp in float
+    __device__ __forceinline__ float interpolation(double x, double y, double z) const
+    {
+        const float u = float(x) - float(cx), vv = float(y) - float(cy), w = float(z) - float(cz);
+        float V = v[0];
+        float A = V + (v[1] - V) * w;
+        V = v[3];
+        float B = V + (v[2] - V) * w;
+        const float C = A + (B - A) * vv;
+        V = v[4];
+        A = V + (v[5] - V) * w;
+        V = v[7];
+        B = V + (v[6] - V) * w;
+        const float D = A + (B - A) * vv;
+        return C + (D - C) * u;
+    }
+    // gradient(Vec3<float>) (:369-411) then applyIJT = * 1/scale in double, rounded back to float (Maps.h:767-771)
+    __device__ __forceinline__ void gradient(const DevGrid& g, double x, double y, double z, float& gx, float& gy, float& gz) const
+    {
+        const float u = float(x) - float(cx), vv = float(y) - float(cy), w = float(z) - float(cz);
+        float D0 = v[1] - v[0], D1 = v[2] - v[3], D2 = v[5] - v[4], D3 = v[6] - v[7];
+        float A = D0 + (D1 - D0) * vv;
+        float B = D2 + (D3 - D2) * vv;
+        const float z_ = A + (B - A) * u;
+        D0 = v[0] + D0 * w; D1 = v[3] + D1 * w; D2 = v[4] + D2 * w; D3 = v[7] + D3 * w;
+        A = D0 + (D1 - D0) * vv;
+        B = D2 + (D3 - D2) * vv;
+        const float x_ = B - A;
+        A = D1 - D0;
+        B = D3 - D2;
+        const float y_ = A + (B - A) * u;
+        gx = float(double(x_) * g.inv[0]); gy = float(double(y_) * g.inv[1]); gz = float(double(z_) * g.inv[2]);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// LevelSetRayIntersector::intersects* = LinearSearchImpl (tools/RayIntersector.h:514-668) driven by
+// LevelSetHDDA<Tree,2> (math/DDA.h:144-177), flattened into one loop over an explicit level variable.
+// shift 12: root-level DDA probing upper nodes; 7: inside an upper node probing lower nodes; 3: inside a lower node
+// probing leaves; 0: voxel DDA running the tester.
+// ------------------------------------------------------------------------------------------------------------
+struct LsHit { double time; int ix, iy, iz; };
+
+template<bool COUNT>
+__device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, Ray& ray,
+                                                  float iso, float vmin, float vmax, LsHit& out, Counters& c)
+{
+    // `ray` is the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
+    Dda cur; DdaSave s12, s7, s3;
+    int shift = 12;
+    cur.init(ray, ray.t0, ray.t1, 12);
+    double T0 = 0.0; float V0 = 0.f;      // LinearSearchImpl::mT[0], mV[0]
+    for (;;) {
+        if (shift != 0) {
+            // tester.hasNode<NodeT>(dda.voxel()) (:609-613)
+            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+            if (COUNT) { if (shift == 12) ++c.root; else if (shift == 7) ++c.upper; else ++c.lower; }
+            const bool exists = shift == 12 ? depth <= 2 : (shift == 7 ? depth <= 1 : depth == 0);
+            if (exists) {
+                // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
+                const double c0 = cur.t0, c1 = cur.next();
+                if (shift == 12) { park(s12, cur); shift = 7; } else if (shift == 7) { park(s7, cur); shift = 3; } else { park(s3, cur); shift = 0; }
+                cur.init(ray, c0, c1, shift);
+                if (shift == 0) {
+                    // tester.init(dda.time()) (:597-601): mT[0] = t0; mV[0] = float(interpValue(t0))
+                    T0 = c0;
+                    const double px = ray.ex + ray.dx * c0, py = ray.ey + ray.dy * c0, pz = ray.ez + ray.dz * c0;
+                    st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
+                    V0 = st.interpolation(px, py, pz) - iso;
+                }
+                continue;
+            }
+        } else {
+            // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
+            if (COUNT) ++c.voxel;
+            float V;
+            if (acc.probeValue(g, s, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) {
+                const double T1 = cur.next();
+                const double px = ray.ex + ray.dx * T1, py = ray.ey + ray.dy * T1, pz = ray.ez + ray.dz * T1;
+                st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
+                const float V1 = st.interpolation(px, py, pz) - iso;
+                if (V0 * V1 <= 0.0f) {                                     // math::ZeroCrossing (math/Math.h:821)
+                    out.time = T0 + (T1 - T0) * V0 / (V0 - V1);           // interpTime (:646-650): float diff promoted to double
+                    out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
+                    return true;
+                }
+                T0 = T1; V0 = V1;
+            }
+        }
+        // while (dda.step()) ... return false -> continue the parent's loop (DDA.h:158-159,174-175)
+        for (;;) {
+            if (cur.step(ray, shift)) break;
+            if (shift == 12) return false;
+            if (shift == 0) { unpark(cur, s3); shift = 3; } else if (shift == 3) { unpark(cur, s7); shift = 7; } else { unpark(cur, s12); shift = 12; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// VolumeRayIntersector::hits == VolumeHDDA<BoolTree,Ray,2>::hits (math/DDA.h:210-217,247-264,321-336) as a
+// resumable generator: next() returns the spans in the order the reference pushes them into its std::vector.
+// The bool topology copy the reference walks (tools/RayIntersector.h:299-319, dilation 0) has the float tree's
+// child topology and active states, so the float tree itself is probed.
+// ------------------------------------------------------------------------------------------------------------
+struct SpanWalker {
+    Dda cur; DdaSave s12, s7;
+    double ts0, topT1;     // open span start (<0: none), maxTime of the root-level DDA
+    int shift;             // 12 / 7 / 3; -1 = finished
+    bool needStep;
+
+    __device__ __forceinline__ void begin(const Ray& ray)
+    {
+        shift = 12; needStep = false; ts0 = -1.0; topT1 = ray.t1;
+        cur.init(ray, ray.t0, ray.t1, 12);
+    }
+    // Produces the next valid span; false when the walk is over.
+    template<bool COUNT>
+    __device__ __forceinline__ bool next(const DevGrid& g, const RootSmem& s, TreeCursor& acc, const Ray& ray, double& a, double& b, Counters& c)
+    {
+        if (shift < 0) return false;
+        for (;;) {
+            if (needStep) {
+                bool over = false;
+                for (;;) {
+                    if (cur.step(ray, shift)) break;
+                    // a level is exhausted: "if (t.t0>=0) t.t1 = mDDA.maxTime()" -- only the outermost assignment
+                    // survives because any later close overwrites t1 (DDA.h:263,335)
+                    if (shift == 12) { over = true; break; }
+                    if (shift == 3) { unpark(cur, s7); shift = 7; } else { unpark(cur, s12); shift = 12; }
+                }
+                if (over) {
+                    shift = -1;
+                    if (ts0 >= 0.0) { a = ts0; b = topT1; ts0 = -1.0; return (b - a) > 1e-9; }   // TimeSpan::valid (Ray.h:48)
+                    return false;
+                }
+            }
+            needStep = true;
+            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+            if (COUNT) { if (shift == 12) ++c.root; else if (shift == 7) ++c.upper; else ++c.lower; }
+            const bool child = shift == 12 ? depth <= 2 : (shift == 7 ? depth <= 1 : false);
+            if (child) {
+                const double c0 = cur.t0, c1 = cur.next();                 // ray.setTimes(time(), next()) (DDA.h:252,326)
+                if (shift == 12) { park(s12, cur); shift = 7; } else { park(s7, cur); shift = 3; }
+                cur.init(ray, c0, c1, shift);
+                needStep = false;
+                continue;
+            }
+            // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state
+            const bool active = (shift == 3 && depth == 0) ? true : acc.activeAt(g, s, depth, cur.vx, cur.vy, cur.vz);
+            if (active) {
+                if (ts0 < 0.0) ts0 = cur.t0;
+            } else if (ts0 >= 0.0) {
+                a = ts0; b = cur.t0; ts0 = -1.0;
+                if ((b - a) > 1e-9) return true;
+            }
+        }
+    }
+};
+
+// tools::BoxSampler::sample through GridSampler::wsSample (tools/Interpolation.h:420-425,712-762): corner values are
+// float, each lerp is a + float((b-a) * w) with a DOUBLE weight.
+__device__ __forceinline__ float lerpBox(float a, float b, double w) { const double t = (b - a) * w; return a + float(t); }
+__device__ __forceinline__ float boxSampleWorld(const DevGrid& g, const RootSmem& s, TreeCursor& acc, double wx, double wy, double wz)
+{
+    worldToIndexPos(g, wx, wy, wz);
+    const int i = int(floor(wx)), j = int(floor(wy)), k = int(floor(wz));
+    const double u = wx - i, v = wy - j, w = wz - k;
+    float d[8];   // 000,001,011,010,100,101,111,110
+    acc.fetchCell(g, s, i, j, k, d);
+    return lerpBox(lerpBox(lerpBox(d[0], d[1], w), lerpBox(d[3], d[2], w), v),
+                   lerpBox(lerpBox(d[4], d[5], w), lerpBox(d[7], d[6], w), v), u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cameras (tools/RayTracer.h:351-513) on the flattened POD, shaders (:565-753)
+// ------------------------------------------------------------------------------------------------------------
+struct DevCamera {
+    uint32_t kind, width, height, pad;
+    double m[16];
+    double eye[3], dir[3];
+    double scale_w, scale_h, t0, t1;
+};
+struct DevShader { uint32_t kind; float r, g, b, a; double bmin[3], inv[3]; };
+
+__device__ __forceinline__ void cameraRay(const DevCamera& c, uint32_t i, uint32_t j, double io, double jo, Ray& ray)
+{
+    ray.ex = c.eye[0]; ray.ey = c.eye[1]; ray.ez = c.eye[2];
+    ray.t0 = c.t0; ray.t1 = c.t1;
+    // rasterToScreen (:391-395)
+    const double sx = (2 * (double(i) + io) / double(c.width) - 1) * c.scale_w;
+    const double sy = (1 - 2 * (double(j) + jo) / double(c.height)) * c.scale_h;
+    if (c.kind == 0) {                                            // PerspectiveCamera::getRay (:452-462)
+        const double sz = -1.0;
+        double x = sx * c.m[0] + sy * c.m[4] + sz * c.m[8];       // Mat4::transform3x3 (math/Mat4.h:1070-1076)
+        double y = sx * c.m[1] + sy * c.m[5] + sz * c.m[9];
+        double z = sx * c.m[2] + sy * c.m[6] + sz * c.m[10];
+        vnormalize(x, y, z);
+        const double sc = 1.0 / (x * c.dir[0] + y * c.dir[1] + z * c.dir[2]);
+        ray.t0 *= sc; ray.t1 *= sc;                               // scaleTimes
+        ray.setDir(x, y, z);
+    } else {                                                      // OrthographicCamera::getRay (:505-512)
+        const double sz = 0.0;
+        ray.ex = sx * c.m[0] + sy * c.m[4] + sz * c.m[8] + c.m[12];   // Vec3 * Mat4 (math/Mat4.h:1180-1188)
+        ray.ey = sx * c.m[1] + sy * c.m[5] + sz * c.m[9] + c.m[13];
+        ray.ez = sx * c.m[2] + sy * c.m[6] + sz * c.m[10] + c.m[14];
+        ray.setDir(c.dir[0], c.dir[1], c.dir[2]);
+    }
+}
+
+__device__ __forceinline__ float4 shade(const DevShader& s, double wx, double wy, double wz, double nx, double ny, double nz,
+                                        double dx, double dy, double dz)
+{
+    switch (s.kind) {
+    case 0: return make_float4(s.r, s.g, s.b, s.a);                                              // MatteShader (:565-581)
+    case 1: {                                                                                    // NormalShader (:614-630)
+        const float r = s.r * 0.5f, g = s.g * 0.5f, b = s.b * 0.5f;
+        return make_float4(r * float(nx + 1.0), g * float(ny + 1.0), b * float(nz + 1.0), 1.0f);
+    }
+    case 2: {                                                                                    // PositionShader (:671-690)
+        const double rx = (wx - s.bmin[0]) * s.inv[0], ry = (wy - s.bmin[1]) * s.inv[1], rz = (wz - s.bmin[2]) * s.inv[2];
+        return make_float4(s.r * float(rx), s.g * float(ry), s.b * float(rz), 1.0f);
+    }
+    default: {                                                                                   // DiffuseShader (:728-753)
+        const float f = float(fabs(nx * dx + ny * dy + nz * dz));
+        return make_float4(s.r * f, s.g * f, s.b * f, 1.0f);
+    }
+    }
+}
+
+} // namespace vdbrt

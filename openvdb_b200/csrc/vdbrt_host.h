@@ -1,0 +1,32 @@
+// vdbrt_host.h -- host-side state shared by the translation units of libvdbrt.so
+#pragma once
+#include "../../include/vdbrt.h"
+#include "vdbrt_device.cuh"
+#include <cuda_runtime.h>
+#include <string>
+
+struct vdbrt_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the kernel(s) of the last call on `stream`
+    uint32_t last_launches = 0;
+    uint8_t* scratch = nullptr;                 // 4 KB: [0,64) bbox reduction, [64,128) work queue, [128,..) counters
+    void* film = nullptr;  size_t film_cap = 0; // device staging for host films
+    void* aux = nullptr;   size_t aux_cap = 0;  // device staging for per-pixel records
+    void* io = nullptr;    size_t io_cap = 0;   // device staging for ray batches / scratch films
+};
+
+struct vdbrt_grid {
+    uint8_t* dev = nullptr;                     // serialised NanoGrid<float> in device memory
+    uint64_t bytes = 0;
+    int device = 0;
+    vdbrt_grid_info info;
+    vdbrt::DevGrid dgrid;
+};
+
+namespace vdbrt {
+int setError(int code, const std::string& msg);
+int cudaFail(cudaError_t e, const char* what);
+// parse the header of grid->dev, validate it, fill info/dgrid and compute the node-granular bbox on the device
+int finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid);
+}

@@ -1,0 +1,346 @@
+// vdbrt_kernels.cuh -- the sm_100a kernels of the ray-tracing hot path (included once, by vdbrt.cu).
+//
+// Scheduling (subsystem (a) of the north star): persistent CTAs, one per SM x resident CTAs, whose warps pull
+// 8x4-pixel tiles from a global atomic work queue.  Tiles are numbered macro-tile major (default 64x64 pixels)
+// so that consecutive queue tickets touch neighbouring rays -> neighbouring tree nodes (L1/L2 reuse), and so that
+// a multi-GPU partition (vdbrt_partition) is a stride over macro tiles.
+#pragma once
+#include "vdbrt_device.cuh"
+
+namespace vdbrt {
+
+constexpr int kBlockThreads = 128;       // 4 warps per CTA
+constexpr int kSubW = 8, kSubH = 4;      // pixels per warp tile
+
+struct TileMap {
+    uint32_t width, height;
+    uint32_t tile_w, tile_h;             // macro tile
+    uint32_t macro_x, macro_count;       // macro tiles per row / total
+    uint32_t rank, count;                // partition
+    uint32_t sub_x, sub_per_macro;       // warp tiles per macro-tile row / per macro tile
+    uint32_t items;                      // work items (warp tiles) owned by this rank
+};
+
+__host__ inline TileMap makeTileMap(uint32_t width, uint32_t height, uint32_t tw, uint32_t th, uint32_t rank, uint32_t count)
+{
+    TileMap m;
+    m.width = width; m.height = height;
+    m.tile_w = tw ? tw : 64u; m.tile_h = th ? th : 64u;
+    m.count = count ? count : 1u; m.rank = count ? rank : 0u;
+    m.macro_x = (width + m.tile_w - 1) / m.tile_w;
+    const uint32_t macro_y = (height + m.tile_h - 1) / m.tile_h;
+    m.macro_count = m.macro_x * macro_y;
+    m.sub_x = (m.tile_w + kSubW - 1) / kSubW;
+    m.sub_per_macro = m.sub_x * ((m.tile_h + kSubH - 1) / kSubH);
+    const uint32_t owned = m.macro_count > m.rank ? (m.macro_count - m.rank + m.count - 1) / m.count : 0u;
+    m.items = owned * m.sub_per_macro;
+    return m;
+}
+
+// warp-level ticket: lane 0 takes the next work item, everyone gets the pixel of its lane (or false)
+__device__ __forceinline__ bool nextPixel(const TileMap& m, unsigned int* queue, uint32_t& px, uint32_t& py, bool& valid)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= m.items) return false;
+    const uint32_t macro = m.rank + (item / m.sub_per_macro) * m.count;
+    const uint32_t sub = item % m.sub_per_macro;
+    const uint32_t mx = macro % m.macro_x, my = macro / m.macro_x;
+    const uint32_t lx = (sub % m.sub_x) * kSubW + (lane & 7u), ly = (sub / m.sub_x) * kSubH + (lane >> 3);
+    px = mx * m.tile_w + lx; py = my * m.tile_h + ly;
+    valid = lx < m.tile_w && ly < m.tile_h && px < m.width && py < m.height;
+    return true;
+}
+
+struct AuxOut { uint8_t* hit; int32_t* ijk; double* t_index; double* t_world; double* xyz; double* nml; };
+struct LsParams { float iso, vmin, vmax, frac; uint32_t sub; uint32_t uniform_bg; float bg[4]; double jitter[16]; };
+
+__device__ __forceinline__ void flushCounters(const Counters& c, unsigned long long* out)
+{
+    // warp-reduce then one atomic per counter per warp
+    const uint32_t vals[10] = {c.rays, c.root, c.upper, c.lower, c.voxel, c.refills, c.psamples, c.ssamples, c.srays, c.hits};
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        uint32_t v = vals[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(out + k, (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LevelSetRayTracer::operator() (tools/RayTracer.h:899-918): primary ray + (spp-1) jittered rays per pixel.
+// Jitter index n(i,j) = 2*(spp-1)*(j*W+i): the reference's counter for render(threaded=false).
+// ------------------------------------------------------------------------------------------------------------
+template<bool AUX, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads)
+k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
+                  const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* __restrict__ film,
+                  AuxOut aux, unsigned int* queue, unsigned long long* counters)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+
+    TreeCursor acc; acc.reset();
+    Stencil st; st.reset();
+    Counters c = {};
+    uint32_t px, py; bool valid;
+    while (nextPixel(tm, queue, px, py, valid)) {
+        if (!valid) continue;
+        const size_t pix = size_t(py) * tm.width + px;
+        float4 bg;
+        if (p.uniform_bg) bg = make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]); else bg = film[pix];
+        float4 col = bg;
+        unsigned long long n = 2ull * p.sub * pix;
+        for (uint32_t k = 0; k <= p.sub; ++k) {
+            Ray ray;
+            if (k == 0) cameraRay(cam, px, py, 0.5, 0.5, ray);
+            else { cameraRay(cam, px, py, p.jitter[n & 15], p.jitter[(n + 1) & 15], ray); n += 2; }
+            const double wdx = ray.dx, wdy = ray.dy, wdz = ray.dz;       // world direction for the shader
+            if (COUNT) ++c.rays;
+            // intersectsWS(ray, xyz, nml): setWorldRay (worldToIndex + clip) -> HDDA -> getWorldPosAndNml
+            worldToIndex(g, ray);
+            LsHit h;
+            const bool hit = clipRay(ray, g, 0) && intersectLevelSet<COUNT>(g, root, acc, st, ray, p.iso, p.vmin, p.vmax, h, c);
+            float4 s = bg;
+            if (hit) {
+                if (COUNT) ++c.hits;
+                // getWorldPosAndNml (tools/RayIntersector.h:575-582)
+                double x = ray.ex + ray.dx * h.time, y = ray.ey + ray.dy * h.time, z = ray.ez + ray.dz * h.time;
+                st.template moveTo<COUNT>(g, root, acc, x, y, z, c);
+                float gx, gy, gz;
+                st.gradient(g, x, y, z, gx, gy, gz);
+                double nx = gx, ny = gy, nz = gz;
+                vnormalize(nx, ny, nz);
+                indexToWorldPos(g, x, y, z);
+                s = shade(sh, x, y, z, nx, ny, nz, wdx, wdy, wdz);
+                if (AUX && k == 0) {
+                    if (aux.ijk) { aux.ijk[3 * pix] = h.ix; aux.ijk[3 * pix + 1] = h.iy; aux.ijk[3 * pix + 2] = h.iz; }
+                    if (aux.t_index) aux.t_index[pix] = h.time;
+                    // getWorldTime (:588-591): mTime * |J dir|
+                    if (aux.t_world) aux.t_world[pix] = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
+                    if (aux.xyz) { aux.xyz[3 * pix] = x; aux.xyz[3 * pix + 1] = y; aux.xyz[3 * pix + 2] = z; }
+                    if (aux.nml) { aux.nml[3 * pix] = nx; aux.nml[3 * pix + 1] = ny; aux.nml[3 * pix + 2] = nz; }
+                }
+            }
+            if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
+            if (k == 0) col = s;
+            else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+        }
+        film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+    }
+    if (COUNT) flushCounters(c, counters);
+}
+
+// LevelSetRayIntersector::intersectsWS / intersectsIS on arbitrary rays (tools/RayIntersector.h:119-240)
+struct HitOut { int32_t hit; int32_t ijk[3]; double t_index, t_world; double xyz_index[3], xyz_world[3], nml[3]; };
+struct RayIn { double eye[3], dir[3], t0, t1; };
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays, unsigned long long n, uint32_t space,
+                     float iso, float vmin, float vmax, HitOut* __restrict__ hits)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+    TreeCursor acc; acc.reset();
+    Stencil st; st.reset();
+    Counters c = {};
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.ex = rays[k].eye[0]; ray.ey = rays[k].eye[1]; ray.ez = rays[k].eye[2];
+        ray.setDir(rays[k].dir[0], rays[k].dir[1], rays[k].dir[2]);
+        ray.t0 = rays[k].t0; ray.t1 = rays[k].t1;
+        if (space == 0) worldToIndex(g, ray);
+        HitOut o = {};
+        LsHit h;
+        if (clipRay(ray, g, 0) && intersectLevelSet<false>(g, root, acc, st, ray, iso, vmin, vmax, h, c)) {
+            double x = ray.ex + ray.dx * h.time, y = ray.ey + ray.dy * h.time, z = ray.ez + ray.dz * h.time;
+            st.template moveTo<false>(g, root, acc, x, y, z, c);
+            float gx, gy, gz;
+            st.gradient(g, x, y, z, gx, gy, gz);
+            double nx = gx, ny = gy, nz = gz;
+            vnormalize(nx, ny, nz);
+            o.hit = 1; o.ijk[0] = h.ix; o.ijk[1] = h.iy; o.ijk[2] = h.iz;
+            o.t_index = h.time;
+            o.t_world = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
+            o.xyz_index[0] = x; o.xyz_index[1] = y; o.xyz_index[2] = z;
+            indexToWorldPos(g, x, y, z);
+            o.xyz_world[0] = x; o.xyz_world[1] = y; o.xyz_world[2] = z;
+            o.nml[0] = nx; o.nml[1] = ny; o.nml[2] = nz;
+        }
+        hits[k] = o;
+    }
+}
+
+// VolumeRayIntersector::hits on arbitrary rays (tools/RayIntersector.h:368-432)
+__global__ void __launch_bounds__(kBlockThreads)
+k_volume_spans(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays, unsigned long long n, uint32_t space,
+               uint32_t maxSpans, double* __restrict__ spans, int32_t* __restrict__ counts)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+    TreeCursor acc; acc.reset();
+    Counters c = {};
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.ex = rays[k].eye[0]; ray.ey = rays[k].eye[1]; ray.ez = rays[k].eye[2];
+        ray.setDir(rays[k].dir[0], rays[k].dir[1], rays[k].dir[2]);
+        ray.t0 = rays[k].t0; ray.t1 = rays[k].t1;
+        if (space == 0) worldToIndex(g, ray);
+        if (!clipRay(ray, g, 1)) { counts[k] = -1; continue; }
+        SpanWalker w; w.begin(ray);
+        int cnt = 0; double a, b;
+        while (w.template next<false>(g, root, acc, ray, a, b, c)) {
+            if (uint32_t(cnt) < maxSpans) { spans[(k * maxSpans + cnt) * 2] = a; spans[(k * maxSpans + cnt) * 2 + 1] = b; }
+            ++cnt;
+        }
+        counts[k] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// VolumeRender<VolumeRayIntersector<FloatGrid>,BoxSampler>::operator() (tools/RayTracer.h:991-1070)
+// ------------------------------------------------------------------------------------------------------------
+struct VolParams {
+    double pstep, sstep, cutoff, gain;
+    double light[3];            // world-space unit light direction
+    double ext[3], albedo[3];   // extinction = -scattering-absorption; albedo = lightColor*scattering/(scattering+absorption)
+};
+
+template<bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads)
+k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
+                const __grid_constant__ TileMap tm, float4* __restrict__ film, unsigned int* queue, unsigned long long* counters)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+
+    TreeCursor accP, accS, accV;        // primary walker, shadow walker, sampler (the reference keeps three accessors too)
+    accP.reset(); accS.reset(); accV.reset();
+    Counters c = {};
+    // the shadow ray's direction is the same for every sample: sRay(Vec3R(0), mLightDir) through worldToIndex
+    Ray sBase;
+    sBase.ex = sBase.ey = sBase.ez = 0.0;
+    sBase.setDir(p.light[0], p.light[1], p.light[2]);
+    sBase.t0 = 1e-9; sBase.t1 = DBL_MAX;                 // Ray ctor defaults (math/Ray.h:57-63)
+    {
+        const double jx = sBase.dx * g.inv[0], jy = sBase.dy * g.inv[1], jz = sBase.dz * g.inv[2];
+        const double len = vlength(jx, jy, jz);
+        sBase.setDir(jx / len, jy / len, jz / len);
+        sBase.t0 = len * sBase.t0; sBase.t1 = len * sBase.t1;
+    }
+
+    uint32_t px, py; bool valid;
+    while (nextPixel(tm, queue, px, py, valid)) {
+        if (!valid) continue;
+        const size_t pix = size_t(py) * tm.width + px;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);                    // bg.a = bg.r = bg.g = bg.b = 0 (:1020)
+        Ray pRay;
+        cameraRay(cam, px, py, 0.5, 0.5, pRay);
+        if (COUNT) ++c.rays;
+        worldToIndex(g, pRay);
+        if (clipRay(pRay, g, 1)) {                                       // mPrimary->setWorldRay(pRay) (:1022)
+            double Tx = 1.0, Ty = 1.0, Tz = 1.0, Lx = 0.0, Ly = 0.0, Lz = 0.0;
+            SpanWalker pw; pw.begin(pRay);
+            double a, b;
+            bool done = false;
+            while (!done && pw.template next<COUNT>(g, root, accP, pRay, a, b, c)) {
+                for (double pT = p.pstep * ceil(a / p.pstep); pT <= b; pT += p.pstep) {
+                    // pPos = mPrimary->getWorldPos(pT); density = sampler.wsSample(pPos) (:1034-1035)
+                    double wx = pRay.ex + pRay.dx * pT, wy = pRay.ey + pRay.dy * pT, wz = pRay.ez + pRay.dz * pT;
+                    indexToWorldPos(g, wx, wy, wz);
+                    const double density = boxSampleWorld(g, root, accV, wx, wy, wz);
+                    if (COUNT) ++c.psamples;
+                    if (density < p.cutoff) continue;
+                    const double dTx = exp(p.ext[0] * density * p.pstep), dTy = exp(p.ext[1] * density * p.pstep), dTz = exp(p.ext[2] * density * p.pstep);
+                    double Sx = 1.0, Sy = 1.0, Sz = 1.0;
+                    // sRay.setEye(pPos); mShadow->setWorldRay(sRay) (:1039-1040)
+                    Ray sRay = sBase;
+                    sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
+                    worldToIndexPos(g, sRay.ex, sRay.ey, sRay.ez);
+                    if (COUNT) ++c.srays;
+                    if (!clipRay(sRay, g, 1)) continue;
+                    SpanWalker sw; sw.begin(sRay);
+                    double sa, sb;
+                    bool lit = false;
+                    while (!lit && sw.template next<COUNT>(g, root, accS, sRay, sa, sb, c)) {
+                        for (double sT = p.sstep * ceil(sa / p.sstep); sT <= sb; sT += p.sstep) {
+                            double qx = sRay.ex + sRay.dx * sT, qy = sRay.ey + sRay.dy * sT, qz = sRay.ez + sRay.dz * sT;
+                            indexToWorldPos(g, qx, qy, qz);
+                            const double d = boxSampleWorld(g, root, accV, qx, qy, qz);
+                            if (COUNT) ++c.ssamples;
+                            if (d < p.cutoff) continue;
+                            const double den = 1.0 + sT * p.gain;
+                            Sx *= exp(p.ext[0] * d * p.sstep / den); Sy *= exp(p.ext[1] * d * p.sstep / den); Sz *= exp(p.ext[2] * d * p.sstep / den);
+                            if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) { lit = true; break; }          // goto Luminance
+                        }
+                    }
+                    Lx += p.albedo[0] * Sx * Tx * (1.0 - dTx); Ly += p.albedo[1] * Sy * Ty * (1.0 - dTy); Lz += p.albedo[2] * Sz * Tz * (1.0 - dTz);
+                    Tx *= dTx; Ty *= dTy; Tz *= dTz;
+                    if (Tx * Tx + Ty * Ty + Tz * Tz < p.cutoff) { done = true; break; }                 // goto Pixel
+                }
+            }
+            out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
+            if (COUNT && out.w > 0.f) ++c.hits;
+        }
+        film[pix] = out;
+    }
+    if (COUNT) flushCounters(c, counters);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RootNode::evalActiveBoundingBox(bbox, /*visitVoxels=*/false) (tree/RootNode.h:1532-1541, InternalNode.h:1246-1256,
+// LeafNode.h:1505-1517) over the NanoVDB node arrays: one thread per (root tile, upper slot).
+// out[0..2] = min, out[3..5] = max (initialised to INT_MAX / INT_MIN by the host)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void expandBox(int* out, int x, int y, int z, int dim)
+{
+    atomicMin(out + 0, x); atomicMin(out + 1, y); atomicMin(out + 2, z);
+    atomicMax(out + 3, x + dim - 1); atomicMax(out + 4, y + dim - 1); atomicMax(out + 5, z + dim - 1);
+}
+
+__global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long rootOff, uint32_t tableSize, int* out)
+{
+    const unsigned long long gid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const uint32_t tile = uint32_t(gid >> 15), n = uint32_t(gid & 32767u);
+    if (tile >= tableSize) return;
+    const uint8_t* t = base + rootOff + kRootTiles + kTileSize * tile;
+    const unsigned long long key = ldg64(t);
+    const int ox = int(uint32_t((key >> 42) & 0x1FFFFFull) << 12), oy = int(uint32_t((key >> 21) & 0x1FFFFFull) << 12), oz = int(uint32_t(key & 0x1FFFFFull) << 12);
+    const long long child = ldgs64(t + 8);
+    if (child == 0) { if (n == 0 && ldg32(t + 16)) expandBox(out, ox, oy, oz, 4096); return; }
+    const uint8_t* u = base + rootOff + child;
+    const int ux = ox + int((n >> 10) << 7), uy = oy + int(((n >> 5) & 31u) << 7), uz = oz + int((n & 31u) << 7);
+    if (!maskBit(u + kUpperCMask, n)) { if (maskBit(u + kUpperVMask, n)) expandBox(out, ux, uy, uz, 128); return; }
+    const uint8_t* l = u + ldgs64(u + kUpperTable + 8u * n);
+    int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {int(0x80000000), int(0x80000000), int(0x80000000)};
+    for (uint32_t w = 0; w < 64; ++w) {
+        const unsigned long long cm = ldg64(l + kLowerCMask + 8u * w), vm = ldg64(l + kLowerVMask + 8u * w);
+        unsigned long long tiles = vm & ~cm, kids = cm;
+        while (tiles) {
+            const uint32_t m = w * 64u + uint32_t(__ffsll((long long)tiles) - 1); tiles &= tiles - 1;
+            const int x = ux + int((m >> 8) << 3), y = uy + int(((m >> 4) & 15u) << 3), z = uz + int((m & 15u) << 3);
+            mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z); mx[0] = max(mx[0], x + 7); mx[1] = max(mx[1], y + 7); mx[2] = max(mx[2], z + 7);
+        }
+        while (kids) {
+            const uint32_t m = w * 64u + uint32_t(__ffsll((long long)kids) - 1); kids &= kids - 1;
+            const uint8_t* lf = l + ldgs64(l + kLowerTable + 8u * m);
+            unsigned long long any = 0;
+            for (int q = 0; q < 8; ++q) any |= ldg64(lf + kLeafVMask + 8 * q);
+            if (!any) continue;
+            const int x = ux + int((m >> 8) << 3), y = uy + int(((m >> 4) & 15u) << 3), z = uz + int((m & 15u) << 3);
+            mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z); mx[0] = max(mx[0], x + 7); mx[1] = max(mx[1], y + 7); mx[2] = max(mx[2], z + 7);
+        }
+    }
+    if (mn[0] <= mx[0]) {
+        atomicMin(out + 0, mn[0]); atomicMin(out + 1, mn[1]); atomicMin(out + 2, mn[2]);
+        atomicMax(out + 3, mx[0]); atomicMax(out + 4, mx[1]); atomicMax(out + 5, mx[2]);
+    }
+}
+
+} // namespace vdbrt
