@@ -177,29 +177,27 @@ struct TreeCursor {
 
     // the 8 corners of the cell (x..x+1, y..y+1, z..z+1) in BoxStencil slot order 000,001,011,010,100,101,111,110
     // (math/Stencils.h:285-293,414-423; same order as BoxSampler::probeValues, tools/Interpolation.h:663-689).
-    // Fast path: the whole cell lies inside one leaf -> eight loads off one base pointer.
+    // A cell touches 2^(number of axes on which it straddles a leaf face) leaves: one rolled loop visits each of those
+    // leaves once (1.4 on average) and pulls all corners that live in it with predicated loads off one base pointer.
     __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
     {
-        const int depth = descend(g, s, x, y, z);
-        if (depth == 0 && (x & 7) < 7 && (y & 7) < 7 && (z & 7) < 7) {
-            const float* p = reinterpret_cast<const float*>(node(g, n0) + kLeafValues) + leafOffset(x, y, z);
-            v[0] = __ldg(p);      v[1] = __ldg(p + 1);  v[2] = __ldg(p + 9);  v[3] = __ldg(p + 8);
-            v[4] = __ldg(p + 64); v[5] = __ldg(p + 65); v[6] = __ldg(p + 73); v[7] = __ldg(p + 72);
-            return;
+        const int fmask = (((x & 7) == 7) ? 4 : 0) | (((y & 7) == 7) ? 2 : 0) | (((z & 7) == 7) ? 1 : 0);
+#pragma unroll 1
+        for (int cmb = 0; cmb < 8; ++cmb) {
+            if (cmb & ~fmask) continue;                     // this neighbour leaf is not touched
+            const int rx = x + (cmb >> 2), ry = y + ((cmb >> 1) & 1), rz = z + (cmb & 1);   // a corner inside that leaf
+            const int depth = descend(g, s, rx, ry, rz);
+            float tile = 0.f;
+            const float* lv = nullptr;
+            if (depth == 0) lv = reinterpret_cast<const float*>(node(g, n0) + kLeafValues);
+            else valueAt(g, s, depth, rx, ry, rz, tile);     // one tile (or the background) covers the whole 8^3 block
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dx = q >> 2, dy = (q >> 1) & 1, dz = (q ^ (q >> 1)) & 1;            // slot q -> corner offset
+                if ((((dx << 2) | (dy << 1) | dz) & fmask) == cmb)
+                    v[q] = lv ? __ldg(lv + leafOffset(x + dx, y + dy, z + dz)) : tile;
+            }
         }
-        if (depth == 1 && (x & 7) < 7 && (y & 7) < 7 && (z & 7) < 7) {     // whole cell inside one lower-node tile
-            const float t = ldgf(node(g, n1) + kLowerTable + 8u * lowerOffset(x, y, z));
-            v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = t;
-            return;
-        }
-        valueAt(g, s, depth, x, y, z, v[0]);
-        v[1] = getValue(g, s, x, y, z + 1);
-        v[2] = getValue(g, s, x, y + 1, z + 1);
-        v[3] = getValue(g, s, x, y + 1, z);
-        v[4] = getValue(g, s, x + 1, y, z);
-        v[5] = getValue(g, s, x + 1, y, z + 1);
-        v[6] = getValue(g, s, x + 1, y + 1, z + 1);
-        v[7] = getValue(g, s, x + 1, y + 1, z);
     }
 };
 
@@ -375,60 +373,121 @@ struct Stencil {
 // shift 12: root-level DDA probing upper nodes; 7: inside an upper node probing lower nodes; 3: inside a lower node
 // probing leaves; 0: voxel DDA running the tester.
 // ------------------------------------------------------------------------------------------------------------
-struct LsHit { double time; int ix, iy, iz; };
+struct LsHit { double time; int ix, iy, iz; double px, py, pz; float gx, gy, gz; };
 
-template<bool COUNT>
-__device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, Ray& ray,
-                                                  float iso, float vmin, float vmax, LsHit& out, Counters& c)
-{
-    // `ray` is the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
+// Traversal state of one ray.  step() performs at most ONE level set-up, ONE cell probe, ONE stencil evaluation and
+// ONE DDA step, each of which exists exactly once in the instruction stream: all lanes of a warp run the same short
+// loop body whatever level they are on (the warp-synchronous render loop reconverges after every call), and the hot
+// loop stays inside the instruction cache.
+struct LsWalk {
     Dda cur; DdaSave s12, s7, s3;
-    int shift = 12;
-    cur.init(ray, ray.t0, ray.t1, 12);
-    double T0 = 0.0; float V0 = 0.f;      // LinearSearchImpl::mT[0], mV[0]
-    for (;;) {
-        if (shift != 0) {
+    double T0;            // LinearSearchImpl::mT[0]
+    double c0, c1;        // pending child range: tester.setRange(dda.time(), dda.next())
+    float V0;             // LinearSearchImpl::mV[0]
+    int shift;            // 12 / 7 / 3 / 0
+    bool skip;            // the current cell was already handled (we just came back up): only step
+    bool pendLevel;       // a DDA must be initialised over [c0,c1] at `shift`
+    bool pendFinal;       // a zero crossing was found: evaluate position + gradient at the hit time
+
+    // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
+    __device__ __forceinline__ void begin(const Ray& ray)
+    {
+        shift = 12; skip = false; pendLevel = true; pendFinal = false; T0 = 0.0; V0 = 0.f; c0 = ray.t0; c1 = ray.t1;
+    }
+};
+
+enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
+
+// SYNC = true: the caller runs a warp-synchronous loop in which ALL 32 lanes call lsAdvance every iteration (lanes
+// without a ray pass active = false).  __syncwarp() between the phases makes the warp reconverge after each phase and
+// stops the compiler from cloning the later phases per control-flow path (which would keep lanes apart until the end
+// of the iteration).  SYNC = false: plain per-thread use.
+template<bool COUNT, bool SYNC>
+__device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, const Ray& ray,
+                                         float iso, float vmin, float vmax, LsWalk& w, LsHit& out, Counters& c)
+{
+    Dda& cur = w.cur;
+    int status = kWalkContinue;
+    int purpose = 0;            // 1: tester.init, 2: tester(ijk,t), 3: getWorldPosAndNml
+    double tq = 0.0;
+    bool doStep = false, probe = false;
+    // ---- phase A: level set-up
+    if (active) {
+        probe = !w.skip;
+        if (w.skip) { w.skip = false; doStep = true; }
+        if (w.pendLevel) {
+            // math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
+            cur.init(ray, w.c0, w.c1, w.shift);
+            w.pendLevel = false;
+            if (w.shift == 0) { purpose = 1; tq = w.c0; probe = false; }     // tester.init(dda.time()) (:597-601)
+        } else if (w.pendFinal) {
+            w.pendFinal = false; purpose = 3; tq = out.time; probe = false;
+        }
+    }
+    if (SYNC) __syncwarp();
+    // ---- phase B: probe the current cell
+    if (probe) {
+        const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+        if (w.shift != 0) {
             // tester.hasNode<NodeT>(dda.voxel()) (:609-613)
-            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
-            if (COUNT) { if (shift == 12) ++c.root; else if (shift == 7) ++c.upper; else ++c.lower; }
-            const bool exists = shift == 12 ? depth <= 2 : (shift == 7 ? depth <= 1 : depth == 0);
+            if (COUNT) { if (w.shift == 12) ++c.root; else if (w.shift == 7) ++c.upper; else ++c.lower; }
+            const bool exists = w.shift == 12 ? depth <= 2 : (w.shift == 7 ? depth <= 1 : depth == 0);
             if (exists) {
                 // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
-                const double c0 = cur.t0, c1 = cur.next();
-                if (shift == 12) { park(s12, cur); shift = 7; } else if (shift == 7) { park(s7, cur); shift = 3; } else { park(s3, cur); shift = 0; }
-                cur.init(ray, c0, c1, shift);
-                if (shift == 0) {
-                    // tester.init(dda.time()) (:597-601): mT[0] = t0; mV[0] = float(interpValue(t0))
-                    T0 = c0;
-                    const double px = ray.ex + ray.dx * c0, py = ray.ey + ray.dy * c0, pz = ray.ez + ray.dz * c0;
-                    st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
-                    V0 = st.interpolation(px, py, pz) - iso;
-                }
-                continue;
-            }
+                w.c0 = cur.t0; w.c1 = cur.next();
+                if (w.shift == 12) { park(w.s12, cur); w.shift = 7; } else if (w.shift == 7) { park(w.s7, cur); w.shift = 3; } else { park(w.s3, cur); w.shift = 0; }
+                w.pendLevel = true;
+            } else doStep = true;
         } else {
             // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
             if (COUNT) ++c.voxel;
             float V;
-            if (acc.probeValue(g, s, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) {
-                const double T1 = cur.next();
-                const double px = ray.ex + ray.dx * T1, py = ray.ey + ray.dy * T1, pz = ray.ez + ray.dz * T1;
-                st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
-                const float V1 = st.interpolation(px, py, pz) - iso;
-                if (V0 * V1 <= 0.0f) {                                     // math::ZeroCrossing (math/Math.h:821)
-                    out.time = T0 + (T1 - T0) * V0 / (V0 - V1);           // interpTime (:646-650): float diff promoted to double
-                    out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
-                    return true;
-                }
-                T0 = T1; V0 = V1;
-            }
+            if (acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) { purpose = 2; tq = cur.next(); }
+            doStep = true;
         }
-        // while (dda.step()) ... return false -> continue the parent's loop (DDA.h:158-159,174-175)
-        for (;;) {
-            if (cur.step(ray, shift)) break;
-            if (shift == 12) return false;
-            if (shift == 0) { unpark(cur, s3); shift = 3; } else if (shift == 3) { unpark(cur, s7); shift = 7; } else { unpark(cur, s12); shift = 12; }
+    }
+    if (SYNC) __syncwarp();
+    // ---- phase C: stencil evaluation
+    if (purpose) {
+        // interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
+        const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
+        st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
+        if (purpose == 3) {
+            // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
+            out.px = px; out.py = py; out.pz = pz;
+            st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
+            status = kWalkHit; doStep = false;
+        } else {
+            const float V1 = st.interpolation(px, py, pz) - iso;
+            if (purpose == 2 && w.V0 * V1 <= 0.0f) {                         // math::ZeroCrossing (math/Math.h:821)
+                out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
+                out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
+                w.pendFinal = true; doStep = false;
+            } else { w.T0 = tq; w.V0 = V1; }                                  // init: mT[0],mV[0]; no crossing: slide
         }
+    }
+    if (SYNC) __syncwarp();
+    // ---- phase D: while (dda.step()) ... ; an exhausted level returns false to its parent (DDA.h:158-159,174-175)
+    if (doStep && !cur.step(ray, w.shift)) {
+        if (w.shift == 12) status = kWalkMiss;
+        else {
+            if (w.shift == 0) { unpark(cur, w.s3); w.shift = 3; } else if (w.shift == 3) { unpark(cur, w.s7); w.shift = 7; } else { unpark(cur, w.s12); w.shift = 12; }
+            w.skip = true;
+        }
+    }
+    return status;
+}
+
+// plain per-thread form (arbitrary-ray batches)
+template<bool COUNT>
+__device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, Ray& ray,
+                                                  float iso, float vmin, float vmax, LsHit& out, Counters& c)
+{
+    LsWalk w; w.begin(ray);
+#pragma unroll 1
+    for (;;) {
+        const int r = lsAdvance<COUNT, false>(true, g, s, acc, st, ray, iso, vmin, vmax, w, out, c);
+        if (r != kWalkContinue) return r == kWalkHit;
     }
 }
 

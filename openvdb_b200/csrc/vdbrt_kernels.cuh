@@ -72,7 +72,25 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 // ------------------------------------------------------------------------------------------------------------
 // LevelSetRayTracer::operator() (tools/RayTracer.h:899-918): primary ray + (spp-1) jittered rays per pixel.
 // Jitter index n(i,j) = 2*(spp-1)*(j*W+i): the reference's counter for render(threaded=false).
+//
+// Warp-synchronous persistent loop: every lane owns one pixel at a time and advances its ray by ONE traversal step
+// per iteration (lsAdvance); the warp reconverges at the top of every iteration.  Lanes whose pixel is finished
+// are re-fed from the atomic queue in batches (one atomicAdd per refill, tickets numbered in tile order so a warp's
+// lanes stay spatially coherent), instead of idling until the slowest ray of a fixed tile is done.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kRefillThreshold = 8;      // refill when at least this many lanes are idle (or the whole warp is)
+
+__device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket, uint32_t& px, uint32_t& py)
+{
+    const unsigned item = ticket >> 5, slot = ticket & 31u;
+    const uint32_t macro = m.rank + (item / m.sub_per_macro) * m.count;
+    const uint32_t sub = item % m.sub_per_macro;
+    const uint32_t mx = macro % m.macro_x, my = macro / m.macro_x;
+    const uint32_t lx = (sub % m.sub_x) * kSubW + (slot & 7u), ly = (sub / m.sub_x) * kSubH + (slot >> 3);
+    px = mx * m.tile_w + lx; py = my * m.tile_h + ly;
+    return lx < m.tile_w && ly < m.tile_h && px < m.width && py < m.height;
+}
+
 template<bool AUX, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
@@ -83,36 +101,74 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     stageRoot(g, root);
     __syncthreads();
 
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned total = tm.items * 32u;            // tickets: 32 pixel slots per warp tile
     TreeCursor acc; acc.reset();
     Stencil st; st.reset();
     Counters c = {};
-    uint32_t px, py; bool valid;
-    while (nextPixel(tm, queue, px, py, valid)) {
-        if (!valid) continue;
-        const size_t pix = size_t(py) * tm.width + px;
-        float4 bg;
-        if (p.uniform_bg) bg = make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]); else bg = film[pix];
-        float4 col = bg;
-        unsigned long long n = 2ull * p.sub * pix;
-        for (uint32_t k = 0; k <= p.sub; ++k) {
-            Ray ray;
-            if (k == 0) cameraRay(cam, px, py, 0.5, 0.5, ray);
-            else { cameraRay(cam, px, py, p.jitter[n & 15], p.jitter[(n + 1) & 15], ray); n += 2; }
-            const double wdx = ray.dx, wdy = ray.dy, wdz = ray.dz;       // world direction for the shader
+    // per-lane pixel / ray state
+    bool hasPix = false, rayOn = false, drained = false;
+    uint32_t px = 0, py = 0, k = 0;
+    size_t pix = 0;
+    unsigned long long n = 0;
+    float4 bg = make_float4(0.f, 0.f, 0.f, 1.f), col = bg;
+    Ray ray; double wdx = 0.0, wdy = 0.0, wdz = 0.0;
+    LsWalk walk; LsHit h;
+    ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray);
+    h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
+    walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
+
+    for (;;) {
+        __syncwarp();
+        // (1) refill idle lanes from the queue
+        const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
+        if (idle == 0xffffffffu && drained) break;
+        if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillThreshold)) {
+            const unsigned want = __popc(idle);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(queue, want);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + want >= total) drained = true;
+            if (!hasPix) {
+                const unsigned ticket = base + __popc(idle & ((1u << lane) - 1u));
+                if (ticket < total && ticketToPixel(tm, ticket, px, py)) {
+                    hasPix = true; rayOn = false; k = 0;
+                    pix = size_t(py) * tm.width + px;
+                    bg = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
+                    col = bg;
+                    n = 2ull * p.sub * pix;
+                }
+            }
+        }
+        // (2) start the next ray of the lane's pixel
+        int status = kWalkContinue;
+        if (hasPix && !rayOn) {
+            const bool first = k == 0;
+            cameraRay(cam, px, py, first ? 0.5 : p.jitter[n & 15], first ? 0.5 : p.jitter[(n + 1) & 15], ray);
+            if (!first) n += 2;
+            wdx = ray.dx; wdy = ray.dy; wdz = ray.dz;               // world direction for the shader
             if (COUNT) ++c.rays;
-            // intersectsWS(ray, xyz, nml): setWorldRay (worldToIndex + clip) -> HDDA -> getWorldPosAndNml
+            // intersectsWS: setWorldRay = worldToIndex + clip (tools/RayIntersector.h:558-562)
             worldToIndex(g, ray);
-            LsHit h;
-            const bool hit = clipRay(ray, g, 0) && intersectLevelSet<COUNT>(g, root, acc, st, ray, p.iso, p.vmin, p.vmax, h, c);
+            if (clipRay(ray, g, 0)) { walk.begin(ray); rayOn = true; }
+            else status = kWalkMiss;
+        }
+        __syncwarp();
+        // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases)
+        {
+            const int r = lsAdvance<COUNT, true>(rayOn, g, root, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
+            if (rayOn) status = r;
+        }
+        __syncwarp();
+        // (4) a ray ended: shade / composite, then next sample or write the pixel
+        if (status != kWalkContinue) {
             float4 s = bg;
+            const bool hit = status == kWalkHit;
             if (hit) {
                 if (COUNT) ++c.hits;
-                // getWorldPosAndNml (tools/RayIntersector.h:575-582)
-                double x = ray.ex + ray.dx * h.time, y = ray.ey + ray.dy * h.time, z = ray.ez + ray.dz * h.time;
-                st.template moveTo<COUNT>(g, root, acc, x, y, z, c);
-                float gx, gy, gz;
-                st.gradient(g, x, y, z, gx, gy, gz);
-                double nx = gx, ny = gy, nz = gz;
+                // getWorldPosAndNml (tools/RayIntersector.h:575-582): normalise the gradient in double, map the position
+                double x = h.px, y = h.py, z = h.pz;
+                double nx = h.gx, ny = h.gy, nz = h.gz;
                 vnormalize(nx, ny, nz);
                 indexToWorldPos(g, x, y, z);
                 s = shade(sh, x, y, z, nx, ny, nz, wdx, wdy, wdz);
@@ -128,8 +184,12 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
             if (k == 0) col = s;
             else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+            rayOn = false;
+            if (++k > p.sub) {
+                film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+                hasPix = false;
+            }
         }
-        film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
     }
     if (COUNT) flushCounters(c, counters);
 }
@@ -157,11 +217,8 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
         HitOut o = {};
         LsHit h;
         if (clipRay(ray, g, 0) && intersectLevelSet<false>(g, root, acc, st, ray, iso, vmin, vmax, h, c)) {
-            double x = ray.ex + ray.dx * h.time, y = ray.ey + ray.dy * h.time, z = ray.ez + ray.dz * h.time;
-            st.template moveTo<false>(g, root, acc, x, y, z, c);
-            float gx, gy, gz;
-            st.gradient(g, x, y, z, gx, gy, gz);
-            double nx = gx, ny = gy, nz = gz;
+            double x = h.px, y = h.py, z = h.pz;
+            double nx = h.gx, ny = h.gy, nz = h.gz;
             vnormalize(nx, ny, nz);
             o.hit = 1; o.ijk[0] = h.ix; o.ijk[1] = h.iy; o.ijk[2] = h.iz;
             o.t_index = h.time;
