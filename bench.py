@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- primary Mrays/s of the level-set ray tracer on the BASELINE.json configuration.
+
+Workload ("c2"): nanovdb createLevelSetTorus(R=650, r=325, voxel 1, half-width 3) ~ 50 M active voxels (0.58 GB NanoVDB
+grid, built on the GPU by the library's own builder), 1920x1080, 1 spp, DiffuseShader, vdb_render's perspective camera
+at (0, 1.5R, 3(R+r)) looking at the origin.
+
+  value    whole-frame primary rays / device time, grid and film resident in HBM (CUDA events, max over ranks)
+  e2e      the same metric through the C ABI with a pinned HOST film: H2D of the film + kernel + D2H inside the timing
+  roofline algorithmic bytes per ray (counted by an instrumented launch, SURVEY 8d formula) x rays / kernel time
+  cpu_baseline  the reference's own CPU path (oracle/_ref, all host threads) on a bounded sample of the same workload
+
+N > 1 (torchrun, one rank per GPU): the grid is replicated, the film is split into 64x60-pixel tiles interleaved over
+the ranks (vdbrt_partition), and every step ends with an NCCL gather of the owned tiles to rank 0 ("strong" scaling:
+the frame is fixed).  `--impl reference` times the reference CPU implementation alone (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (major, minor, width, height)
+    "c2": (650.0, 325.0, 1920, 1080),
+    "c2-small": (160.0, 80.0, 640, 360),     # quick functional check, not a bench line
+}
+TILE_W, TILE_H = 64, 60
+
+
+def camera_args(R, r):
+    return (0.0, 1.5 * R, 3.0 * (R + r)), (0.0, 0.0, 0.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bytes_per_ray(c):
+    """B_LS = 32 n_R + 16 n_U + 16 n_L + 12 n_V + 32 n_S + 16"""
+    n = float(c["rays"])
+    return (32 * c["root_probes"] + 16 * c["upper_probes"] + 16 * c["lower_probes"] + 12 * c["voxel_probes"]
+            + 32 * c["stencil_refills"]) / n + 16.0
+
+
+def cpu_reference(R, r, W, H, steps, warmup, sample_div=4):
+    """the reference's own CPU implementation (oracle/_ref: unmodified OpenVDB LevelSetRayTracer, threaded) on a bounded
+    sample of the workload: the same grid and camera at (W/div) x (H/div) pixels.  Falls back to the oracle port."""
+    from tests import refapi
+    from openvdb_b200 import _abi as abi
+    w, h = max(W // sample_div, 1), max(H // sample_div, 1)
+    tr, look = camera_args(R, r)
+    cores = os.cpu_count() or 1
+    if os.path.exists(refapi.REF_SO):
+        ref = refapi.Ref()
+        ref.set_threads(cores)
+        g = ref.torus(R, r)
+        d = refapi.camera_desc(w, h, translation=tr, lookat=look)
+        sh = refapi.shader(abi.SHADER_DIFFUSE)
+        film = refapi.new_film(w, h)
+        times = []
+        for it in range(warmup + steps):
+            film[...] = (0, 0, 0, 1)
+            t = ref.render_levelset(g, d, sh, film, threaded=True)
+            if it >= warmup:
+                times.append(t)
+        kind = "reference"
+        hits = int((film[..., :3].sum(axis=2) > 0).sum())
+    else:
+        from openvdb_b200 import api
+        oracle = refapi.Oracle()
+        ctx = api.Context(0)
+        grid = ctx.build_torus(R, r)
+        og = oracle.open(grid.download())
+        cam = api.vdb_render_camera(w, h, tr, look)
+        sh = api.make_shader(abi.SHADER_DIFFUSE)
+        film = refapi.new_film(w, h)
+        times = []
+        for it in range(warmup + steps):
+            film[...] = (0, 0, 0, 1)
+            t0 = time.perf_counter()
+            oracle.render_levelset(og, cam, sh, film, threads=cores)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
+        hits = int((film[..., :3].sum(axis=2) > 0).sum())
+    t = float(np.median(times))
+    return {"value": w * h / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": "%dx%d pixels of the same torus/camera (1/%d of the frame's rays), median of %d runs after %d warm-up, %d hit pixels"
+                      % (w, h, sample_div * sample_div, steps, warmup, hits),
+            "ms_per_sample": t * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R, r, W, H = WORKLOADS[args.workload]
+    cb = cpu_reference(R, r, W, H, max(args.steps, 1), max(min(args.warmup, 2), 1))
+    line = {"impl": "reference", "metric": "primary Mrays/s, level-set ray tracer", "value": cb["value"], "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": level-set torus R=%g r=%g, %dx%d, 1 spp, diffuse (bounded sample)" % (R, r, W, H)},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vdbrt", choices=["vdbrt", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from openvdb_b200 import api, _abi as abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvdbrt.so has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+    R, r, W, H = WORKLOADS[args.workload]
+    tr, look = camera_args(R, r)
+
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    grid = ctx.build_torus(R, r)                       # replicated on every GPU
+    build_s = time.perf_counter() - t0
+    cam = api.vdb_render_camera(W, H, tr, look)
+    sh = api.make_shader(abi.SHADER_DIFFUSE)
+    part = api.partition(rank, world, TILE_W, TILE_H) if world > 1 else None
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    bg = (0.0, 0.0, 0.0, 1.0)                           # a fresh tools::Film (RayTracer.h:235)
+    opts = ctx.ls_opts(part=part, uniform_bg=True)
+    opts.flags |= abi.ASYNC
+
+    # multi-GPU frame assembly: tiles [ty, tx] of TILE_H x TILE_W pixels; rank r owns flat tile ids r, r+world, ...
+    tiles_y, tiles_x = H // TILE_H, W // TILE_W
+    assert tiles_y * TILE_H == H and tiles_x * TILE_W == W
+    ntiles = tiles_y * tiles_x
+    per_rank = (ntiles + world - 1) // world
+    send = torch.zeros((per_rank, TILE_H, TILE_W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    recv = [torch.zeros_like(send) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def tile_view(t):
+        return t.view(tiles_y, TILE_H, tiles_x, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(ntiles, TILE_H, TILE_W, 4)
+
+    def step():
+        ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
+        if world > 1:
+            mine = tile_view(film)[rank::world]
+            send[:mine.shape[0]].copy_(mine)
+            dist.gather(send, recv, dst=0)
+            if rank == 0:
+                tv = tile_view(film)          # a copy (permute + reshape); scatter the received tiles back
+                for q in range(1, world):
+                    n = tv[q::world].shape[0]
+                    tv[q::world] = recv[q][:n]
+                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
+        ev[k][1].record(stream)
+        if world > 1:
+            mine = tile_view(film)[rank::world]
+            send[:mine.shape[0]].copy_(mine)
+            dist.gather(send, recv, dst=0)
+            if rank == 0:
+                tv = tile_view(film)
+                for q in range(1, world):
+                    n = tv[q::world].shape[0]
+                    tv[q::world] = recv[q][:n]
+                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
+        ev[k][2].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
+    tt = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms_max = float(tt[0]), float(tt[1])
+    rays = W * H
+    value = rays * args.steps / (total_ms * 1e-3) / 1e6
+    hits = int((film[..., :3].sum(dim=2) > 0).sum().item()) if rank == 0 else 0
+
+    # ---- e2e: the call a user makes, host film in pinned memory, copies inside the timed region
+    opts_sync = ctx.ls_opts(part=part)
+    host = api.PinnedArray((H, W, 4), np.float32)
+    host.array[...] = bg
+    film_bytes = H * W * 16
+
+    def e2e_step():
+        if world == 1:
+            ctx.render_levelset(grid, cam, sh, host.array, opts=opts_sync)       # H2D film + kernel + D2H film
+        else:
+            film.copy_(torch.from_numpy(host.array), non_blocking=True)          # H2D of this step's film
+            step_opts = ctx.ls_opts(part=part)
+            step_opts.flags |= abi.ASYNC
+            ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, opts=step_opts)
+            mine = tile_view(film)[rank::world]
+            send[:mine.shape[0]].copy_(mine)
+            dist.gather(send, recv, dst=0)
+            if rank == 0:
+                tv = tile_view(film)
+                for q in range(1, world):
+                    n = tv[q::world].shape[0]
+                    tv[q::world] = recv[q][:n]
+                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
+                torch.from_numpy(host.array).copy_(film)                         # D2H of the finished frame
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = rays * args.steps / float(te[0]) / 1e6
+
+    if rank == 0:
+        counters = ctx.count_levelset(grid, cam).as_dict()      # separate instrumented launch, not timed
+        bpr = bytes_per_ray(counters)
+        peak, peak_src = measured_peak()
+        # bytes the dominant kernel moves per launch on THIS rank: its share of the frame's rays
+        rays_per_launch = rays / world
+        achieved = bpr * rays_per_launch / (kernel_ms_max * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_levelset_c2_dram_bytes.json")
+        if os.path.exists(tpath) and world == 1 and args.workload == "c2":
+            try:
+                traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "primary Mrays/s, level-set ray tracer", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": level-set torus R=%g r=%g voxel 1 hw 3 (%d active voxels, %.2f GB grid, GPU-built in %.2f s), "
+                                   "%dx%d, 1 spp, DiffuseShader, perspective camera" % (R, r, grid.info.active_voxels, grid.info.bytes / 1e9, build_s, W, H),
+                       "partition": "%d GPU(s), %dx%d tiles interleaved, NCCL gather to rank 0" % (world, TILE_W, TILE_H) if world > 1 else "single GPU",
+                       "l2": "grid (%.2f GB) is larger than the 126 MB L2; no explicit flush" % (grid.info.bytes / 1e9),
+                       "hit_pixels": hits},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": film_bytes, "d2h_bytes_per_step": film_bytes,
+                    "ms_per_step": float(te[0]) * 1e3 / args.steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "k_render_levelset", "kernel_ms": kernel_ms_max,
+                         "algorithmic_bytes_per_ray": bpr, "rays_per_launch": rays_per_launch, "counters": counters},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_reference(R, r, W, H, 3, 1)
+            except Exception as e:  # the checker is optional for the product arm
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,7 @@ typedef struct vdbrt_ls_opts {
     uint32_t reserved;
 } vdbrt_ls_opts;
 #define VDBRT_LS_UNIFORM_BG 1u /* every film pixel currently equals bg_rgba: skip the host->device film copy    */
+#define VDBRT_ASYNC         2u /* device-memory film only: enqueue on the context's stream and return at once   */
 
 /* VolumeRender parameters (tools/RayTracer.h:162-207; defaults :929-936).                                      */
 typedef struct vdbrt_vol_opts {
@@ -114,6 +115,8 @@ typedef struct vdbrt_vol_opts {
     double absorption[3];
     double scattering[3];
     vdbrt_partition part;
+    uint32_t flags;           /* VDBRT_ASYNC                                                                    */
+    uint32_t reserved;
 } vdbrt_vol_opts;
 
 /* tools::Film (tools/RayTracer.h:226-345): row-major RGBA float4, pixel (w,h) at [w + h*width].               */

@@ -1,7 +1,6 @@
 """ctypes mirrors of the POD structs in include/vdbrt.h (the C ABI of libvdbrt.so).
 
-Shared by the product binding (openvdb_b200/api.py) and by the test-side bindings of the two checkers
-(tests/refapi.py: oracle/_ref/libvdbref.so and oracle/libvdbrt_oracle.so), which use the same PODs.
+Used by the product binding (openvdb_b200/api.py); the test-side bindings of the checkers reuse the same PODs.
 """
 import ctypes as C
 
@@ -11,6 +10,7 @@ SHADER_MATTE, SHADER_NORMAL, SHADER_POSITION, SHADER_DIFFUSE = 0, 1, 2, 3
 SPACE_WORLD, SPACE_INDEX = 0, 1
 GRID_CLASS_UNKNOWN, GRID_CLASS_LEVEL_SET, GRID_CLASS_FOG_VOLUME = 0, 1, 2
 LS_UNIFORM_BG = 1
+ASYNC = 2
 
 ERR_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "BAD_GRID", 3: "NOT_FLOAT", 4: "NOT_LEVELSET", 5: "NONUNIFORM",
@@ -45,7 +45,8 @@ class LsOpts(C.Structure):
 class VolOpts(C.Structure):
     _fields_ = [("primary_step", C.c_double), ("shadow_step", C.c_double), ("cutoff", C.c_double),
                 ("light_gain", C.c_double), ("light_dir", C.c_double * 3), ("light_color", C.c_double * 3),
-                ("absorption", C.c_double * 3), ("scattering", C.c_double * 3), ("part", Partition)]
+                ("absorption", C.c_double * 3), ("scattering", C.c_double * 3), ("part", Partition),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Film(C.Structure):

@@ -123,13 +123,14 @@ namespace {
 int checkLevelSet(const vdbrt_grid* g, float iso)
 {
     const vdbrt_grid_info& i = g->info;
-    if (std::fabs(i.voxel_size[0] - i.voxel_size[1]) > 5e-7 || std::fabs(i.voxel_size[0] - i.voxel_size[2]) > 5e-7)
-        return setError(VDBRT_ERR_NONUNIFORM, "LevelSetRayIntersector only supports uniform voxels!");          // RayIntersector.h:101-104
-    if (i.grid_class != VDBRT_GRID_CLASS_LEVEL_SET)
-        return setError(VDBRT_ERR_NOT_LEVELSET, "LevelSetRayIntersector only supports level sets!");           // :105-109
+    // the member LinearSearchImpl is constructed before the intersector's own checks run (tools/RayIntersector.h:98,533-539)
     if (i.root_tiles == 0) return setError(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids"); // :533-535
     if (iso <= -i.background || iso >= i.background)
         return setError(VDBRT_ERR_ISO_RANGE, "The iso-value must be inside the narrow-band!");                 // :536-539
+    if (std::fabs(i.voxel_size[0] - i.voxel_size[1]) > 5e-7 || std::fabs(i.voxel_size[0] - i.voxel_size[2]) > 5e-7)
+        return setError(VDBRT_ERR_NONUNIFORM, "LevelSetRayIntersector only supports uniform voxels!");          // :101-104
+    if (i.grid_class != VDBRT_GRID_CLASS_LEVEL_SET)
+        return setError(VDBRT_ERR_NOT_LEVELSET, "LevelSetRayIntersector only supports level sets!");           // :105-109
     return VDBRT_OK;
 }
 int checkVolume(const vdbrt_grid* g)
@@ -387,7 +388,7 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
             if (aux->nml) CUDA_TRY(cudaMemcpyAsync(aux->nml, b + offNml, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (host || !(opts->flags & VDBRT_ASYNC)) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VDBRT_OK;
 }
 
@@ -457,7 +458,7 @@ int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     }
     if (int rc = launchVolume(ctx, grid, cam, opts, film->width, film->height, dFilm, nullptr)) return rc;
     if (host) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (host || !(opts->flags & VDBRT_ASYNC)) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VDBRT_OK;
 }
 

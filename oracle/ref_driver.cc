@@ -206,6 +206,29 @@ void* vdbref_grid_spheres_union(const double* spheres, uint32_t n, double voxel,
     } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
 
+// hand-made grid for the known-answer tests: setValue(ijk, v) for n voxels, then Grid::fill(bbox, value, active) for
+// nb boxes {min xyz, max xyz} (a node-aligned active box becomes an active tile)
+void* vdbref_grid_custom(float background, uint32_t gridClass, double voxelSize, const double* translation,
+                         const int32_t* ijk, const float* values, uint64_t n,
+                         const int32_t* boxes, const float* boxValues, const uint8_t* boxActive, uint64_t nb)
+{
+    try {
+        ensureInit();
+        auto* g = new RefGrid;
+        g->grid = FloatGrid::create(background);
+        auto xf = math::Transform::createLinearTransform(voxelSize);
+        if (translation && (translation[0] != 0 || translation[1] != 0 || translation[2] != 0))
+            xf->postTranslate(Vec3d(translation[0], translation[1], translation[2]));
+        g->grid->setTransform(xf);
+        g->grid->setGridClass(gridClass == VDBRT_GRID_CLASS_LEVEL_SET ? GRID_LEVEL_SET : (gridClass == VDBRT_GRID_CLASS_FOG_VOLUME ? GRID_FOG_VOLUME : GRID_UNKNOWN));
+        for (uint64_t i = 0; i < n; ++i) g->grid->tree().setValue(Coord(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]), values[i]);
+        for (uint64_t b = 0; b < nb; ++b)
+            g->grid->fill(CoordBBox(Coord(boxes[6 * b], boxes[6 * b + 1], boxes[6 * b + 2]), Coord(boxes[6 * b + 3], boxes[6 * b + 4], boxes[6 * b + 5])),
+                          boxValues[b], boxActive[b] != 0);
+        return g;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
 // any NanoGrid<float> buffer (e.g. one produced by the product's GPU builder) -> OpenVDB grid
 void* vdbref_grid_from_nanovdb(const void* buf, uint64_t bytes)
 {

@@ -615,12 +615,13 @@ int oracle_grid_probe(const oracle_grid* g, const int32_t* ijk, uint64_t n, floa
 // Validation performed by the reference at construction (RayIntersector.h:100-112,527-541)
 static int checkLevelSet(const oracle_grid* g, float iso)
 {
+    // member mTester (LinearSearchImpl) is constructed first: empty / iso checks precede the intersector's own checks
+    if (g->tableSize == 0) return fail(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids");
+    if (iso <= -g->background || iso >= g->background) return fail(VDBRT_ERR_ISO_RANGE, "The iso-value must be inside the narrow-band!");
     const double s0 = std::fabs(g->scale[0]);
     if (std::fabs(s0 - std::fabs(g->scale[1])) > 5e-7 || std::fabs(s0 - std::fabs(g->scale[2])) > 5e-7)
         return fail(VDBRT_ERR_NONUNIFORM, "LevelSetRayIntersector only supports uniform voxels!");
     if (g->gridClass != VDBRT_GRID_CLASS_LEVEL_SET) return fail(VDBRT_ERR_NOT_LEVELSET, "LevelSetRayIntersector only supports level sets!");
-    if (g->tableSize == 0) return fail(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids");
-    if (iso <= -g->background || iso >= g->background) return fail(VDBRT_ERR_ISO_RANGE, "The iso-value must be inside the narrow-band!");
     return VDBRT_OK;
 }
 static int checkVolume(const oracle_grid* g)

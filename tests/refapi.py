@@ -119,6 +119,8 @@ class Ref:
         L.vdbref_grid_fog_from_levelset.argtypes = [vp]
         L.vdbref_grid_spheres_union.restype = vp
         L.vdbref_grid_spheres_union.argtypes = [vp, C.c_uint32, C.c_double, C.c_double]
+        L.vdbref_grid_custom.restype = vp
+        L.vdbref_grid_custom.argtypes = [C.c_float, C.c_uint32, C.c_double, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64]
         L.vdbref_grid_from_nanovdb.restype = vp
         L.vdbref_grid_from_nanovdb.argtypes = [vp, C.c_uint64]
         L.vdbref_grid_free.argtypes = [vp]
@@ -167,6 +169,17 @@ class Ref:
     def spheres_union(self, spheres, voxel=1.0, half_width=3.0):
         s = np.ascontiguousarray(spheres, np.float64).reshape(-1, 4)
         return self._chk(self.L.vdbref_grid_spheres_union(s.ctypes.data, len(s), voxel, half_width))
+
+    def custom(self, background=0.0, grid_class=abi.GRID_CLASS_FOG_VOLUME, voxel=1.0, translation=(0, 0, 0), voxels=(), boxes=()):
+        """voxels: [((i,j,k), value)], boxes: [((min xyz),(max xyz), value, active)]"""
+        ijk = np.ascontiguousarray([v[0] for v in voxels], np.int32).reshape(-1, 3)
+        val = np.ascontiguousarray([v[1] for v in voxels], np.float32)
+        bx = np.ascontiguousarray([list(b[0]) + list(b[1]) for b in boxes], np.int32).reshape(-1, 6)
+        bv = np.ascontiguousarray([b[2] for b in boxes], np.float32)
+        ba = np.ascontiguousarray([1 if b[3] else 0 for b in boxes], np.uint8)
+        t = np.ascontiguousarray(translation, np.float64)
+        return self._chk(self.L.vdbref_grid_custom(background, grid_class, voxel, t.ctypes.data, ijk.ctypes.data, val.ctypes.data, len(ijk),
+                                                   bx.ctypes.data, bv.ctypes.data, ba.ctypes.data, len(bx)))
 
     def from_nanovdb(self, buf):
         buf = np.ascontiguousarray(buf, np.uint8)
