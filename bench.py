@@ -194,7 +194,10 @@ def main():
     tr, look = camera_args(R, r)
 
     ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
+    # one non-default torch stream carries the library's kernels, torch's copies, NCCL and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     grid = ctx.build_torus(R, r)                       # replicated on every GPU
