@@ -375,118 +375,136 @@ struct Stencil {
 // ------------------------------------------------------------------------------------------------------------
 struct LsHit { double time; int ix, iy, iz; double px, py, pz; float gx, gy, gz; };
 
-// Traversal state of one ray.  step() performs at most ONE level set-up, ONE cell probe, ONE stencil evaluation and
+// Suspended parent DDAs live in shared memory (structure of arrays, one column per thread): parking / resuming a level
+// is a handful of ST.S / LD.S indexed by the level, instead of a three-way branch over 33 registers.
+template<int THREADS>
+struct WalkSmem {
+    double t1[3][THREADS], nx[3][THREADS], ny[3][THREADS], nz[3][THREADS];
+    int vx[3][THREADS], vy[3][THREADS], vz[3][THREADS];
+    __device__ __forceinline__ void park(int lvl, const Dda& d)
+    {
+        const int t = threadIdx.x;
+        t1[lvl][t] = d.t1; nx[lvl][t] = d.nx; ny[lvl][t] = d.ny; nz[lvl][t] = d.nz; vx[lvl][t] = d.vx; vy[lvl][t] = d.vy; vz[lvl][t] = d.vz;
+    }
+    __device__ __forceinline__ void unpark(int lvl, Dda& d) const
+    {
+        const int t = threadIdx.x;
+        d.t1 = t1[lvl][t]; d.nx = nx[lvl][t]; d.ny = ny[lvl][t]; d.nz = nz[lvl][t]; d.vx = vx[lvl][t]; d.vy = vy[lvl][t]; d.vz = vz[lvl][t];
+    }
+};
+
+// Traversal state of one ray.  lsAdvance() performs at most ONE level set-up, ONE cell probe, ONE stencil evaluation and
 // ONE DDA step, each of which exists exactly once in the instruction stream: all lanes of a warp run the same short
-// loop body whatever level they are on (the warp-synchronous render loop reconverges after every call), and the hot
-// loop stays inside the instruction cache.
+// loop body whatever level they are on (the warp-synchronous render loop reconverges after every phase), and the hot
+// loop stays inside the instruction cache.  The rare, expensive phases (level set-up, stencil evaluation) are
+// deferred: a lane that needs one parks itself until enough lanes of its warp need the same phase (runA / runC).
 struct LsWalk {
-    Dda cur; DdaSave s12, s7, s3;
+    Dda cur;
     double T0;            // LinearSearchImpl::mT[0]
     double c0, c1;        // pending child range: tester.setRange(dda.time(), dda.next())
+    double tq;            // time of the pending stencil evaluation
     float V0;             // LinearSearchImpl::mV[0]
-    int shift;            // 12 / 7 / 3 / 0
+    int lvl;              // 0: root-level DDA (4096^3 cells) 1: inside an upper node (128^3) 2: inside a lower node (8^3) 3: voxels
+    int pendInterp;       // 0 none, 1: tester.init, 2: tester(ijk,t), 3: getWorldPosAndNml
     bool skip;            // the current cell was already handled (we just came back up): only step
-    bool pendLevel;       // a DDA must be initialised over [c0,c1] at `shift`
-    bool pendFinal;       // a zero crossing was found: evaluate position + gradient at the hit time
+    bool pendLevel;       // a DDA must be initialised over [c0,c1] at `lvl`
+    bool pendStep;        // the current cell is done: step
 
+    __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }   // 12, 7, 3, 0
     // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
     __device__ __forceinline__ void begin(const Ray& ray)
     {
-        shift = 12; skip = false; pendLevel = true; pendFinal = false; T0 = 0.0; V0 = 0.f; c0 = ray.t0; c1 = ray.t1;
+        lvl = 0; skip = false; pendLevel = true; pendStep = false; pendInterp = 0; T0 = 0.0; V0 = 0.f; c0 = ray.t0; c1 = ray.t1; tq = 0.0;
     }
+    __device__ __forceinline__ bool runnable() const { return !pendLevel && !pendInterp; }
 };
 
 enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 
 // SYNC = true: the caller runs a warp-synchronous loop in which ALL 32 lanes call lsAdvance every iteration (lanes
 // without a ray pass active = false).  __syncwarp() between the phases makes the warp reconverge after each phase and
-// stops the compiler from cloning the later phases per control-flow path (which would keep lanes apart until the end
-// of the iteration).  SYNC = false: plain per-thread use.
-template<bool COUNT, bool SYNC>
-__device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, const Ray& ray,
-                                         float iso, float vmin, float vmax, LsWalk& w, LsHit& out, Counters& c)
+// stops the compiler from cloning the later phases per control-flow path.  SYNC = false: plain per-thread use.
+template<bool COUNT, bool SYNC, int THREADS>
+__device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
+                                         TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
+                                         LsWalk& w, LsHit& out, Counters& c)
 {
     Dda& cur = w.cur;
     int status = kWalkContinue;
-    int purpose = 0;            // 1: tester.init, 2: tester(ijk,t), 3: getWorldPosAndNml
-    double tq = 0.0;
-    bool doStep = false, probe = false;
-    // ---- phase A: level set-up
-    if (active) {
-        probe = !w.skip;
-        if (w.skip) { w.skip = false; doStep = true; }
-        if (w.pendLevel) {
-            // math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
-            cur.init(ray, w.c0, w.c1, w.shift);
-            w.pendLevel = false;
-            if (w.shift == 0) { purpose = 1; tq = w.c0; probe = false; }     // tester.init(dda.time()) (:597-601)
-        } else if (w.pendFinal) {
-            w.pendFinal = false; purpose = 3; tq = out.time; probe = false;
-        }
+    // ---- phase A: level set-up: math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
+    if (active && w.pendLevel && runA) {
+        cur.init(ray, w.c0, w.c1, LsWalk::shiftOf(w.lvl));
+        w.pendLevel = false;
+        if (w.lvl == 3) { w.pendInterp = 1; w.tq = w.c0; }               // tester.init(dda.time()) (:597-601)
     }
     if (SYNC) __syncwarp();
     // ---- phase B: probe the current cell
-    if (probe) {
-        const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
-        if (w.shift != 0) {
-            // tester.hasNode<NodeT>(dda.voxel()) (:609-613)
-            if (COUNT) { if (w.shift == 12) ++c.root; else if (w.shift == 7) ++c.upper; else ++c.lower; }
-            const bool exists = w.shift == 12 ? depth <= 2 : (w.shift == 7 ? depth <= 1 : depth == 0);
-            if (exists) {
-                // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
-                w.c0 = cur.t0; w.c1 = cur.next();
-                if (w.shift == 12) { park(w.s12, cur); w.shift = 7; } else if (w.shift == 7) { park(w.s7, cur); w.shift = 3; } else { park(w.s3, cur); w.shift = 0; }
-                w.pendLevel = true;
-            } else doStep = true;
-        } else {
-            // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
-            if (COUNT) ++c.voxel;
-            float V;
-            if (acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) { purpose = 2; tq = cur.next(); }
-            doStep = true;
+    if (active && !w.pendLevel && !w.pendInterp && !w.pendStep) {
+        if (w.skip) { w.skip = false; w.pendStep = true; }
+        else {
+            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+            if (w.lvl != 3) {
+                // tester.hasNode<NodeT>(dda.voxel()) (:609-613): level 0 wants an upper node (depth <= 2), 1 a lower, 2 a leaf
+                if (COUNT) { if (w.lvl == 0) ++c.root; else if (w.lvl == 1) ++c.upper; else ++c.lower; }
+                if (depth <= 2 - w.lvl) {
+                    // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
+                    w.c0 = cur.t0; w.c1 = cur.next();
+                    sm.park(w.lvl, cur);
+                    ++w.lvl;
+                    w.pendLevel = true;
+                } else w.pendStep = true;
+            } else {
+                // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
+                if (COUNT) ++c.voxel;
+                float V;
+                if (acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) { w.pendInterp = 2; w.tq = cur.next(); }
+                w.pendStep = true;
+            }
         }
     }
     if (SYNC) __syncwarp();
-    // ---- phase C: stencil evaluation
-    if (purpose) {
-        // interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
+    // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
+    if (active && w.pendInterp && runC) {
+        const int purpose = w.pendInterp;
+        const double tq = w.tq;
+        w.pendInterp = 0;
         const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
         st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
         if (purpose == 3) {
             // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
             out.px = px; out.py = py; out.pz = pz;
             st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
-            status = kWalkHit; doStep = false;
+            status = kWalkHit;
         } else {
             const float V1 = st.interpolation(px, py, pz) - iso;
             if (purpose == 2 && w.V0 * V1 <= 0.0f) {                         // math::ZeroCrossing (math/Math.h:821)
                 out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
                 out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
-                w.pendFinal = true; doStep = false;
+                w.pendInterp = 3; w.tq = out.time; w.pendStep = false;
             } else { w.T0 = tq; w.V0 = V1; }                                  // init: mT[0],mV[0]; no crossing: slide
         }
     }
     if (SYNC) __syncwarp();
     // ---- phase D: while (dda.step()) ... ; an exhausted level returns false to its parent (DDA.h:158-159,174-175)
-    if (doStep && !cur.step(ray, w.shift)) {
-        if (w.shift == 12) status = kWalkMiss;
-        else {
-            if (w.shift == 0) { unpark(cur, w.s3); w.shift = 3; } else if (w.shift == 3) { unpark(cur, w.s7); w.shift = 7; } else { unpark(cur, w.s12); w.shift = 12; }
-            w.skip = true;
+    if (active && w.pendStep && !w.pendInterp) {
+        w.pendStep = false;
+        if (!cur.step(ray, LsWalk::shiftOf(w.lvl))) {
+            if (w.lvl == 0) status = kWalkMiss;
+            else { --w.lvl; sm.unpark(w.lvl, cur); w.skip = true; }
         }
     }
     return status;
 }
 
 // plain per-thread form (arbitrary-ray batches)
-template<bool COUNT>
-__device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, Ray& ray,
+template<bool COUNT, int THREADS>
+__device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm, TreeCursor& acc, Stencil& st, Ray& ray,
                                                   float iso, float vmin, float vmax, LsHit& out, Counters& c)
 {
     LsWalk w; w.begin(ray);
 #pragma unroll 1
     for (;;) {
-        const int r = lsAdvance<COUNT, false>(true, g, s, acc, st, ray, iso, vmin, vmax, w, out, c);
+        const int r = lsAdvance<COUNT, false, THREADS>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c);
         if (r != kWalkContinue) return r == kWalkHit;
     }
 }

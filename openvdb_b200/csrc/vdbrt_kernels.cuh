@@ -78,7 +78,18 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 // are re-fed from the atomic queue in batches (one atomicAdd per refill, tickets numbered in tile order so a warp's
 // lanes stay spatially coherent), instead of idling until the slowest ray of a fixed tile is done.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kRefillThreshold = 8;      // refill when at least this many lanes are idle (or the whole warp is)
+#ifndef VDBRT_REFILL
+#define VDBRT_REFILL 32
+#endif
+#ifndef VDBRT_MINBLOCKS
+#define VDBRT_MINBLOCKS 3
+#endif
+// measured on the B200 (C2 workload): re-feeding single lanes costs more (ray set-up for a few lanes at a time, lost
+// coherence) than it gains; a warp takes a fresh 8x4 tile when all its lanes are done (profiles/r01_tuning.md)
+constexpr int kRefillThreshold = VDBRT_REFILL;   // refill when at least this many lanes are idle
+constexpr int kBatchLevel = 4;           // run the level set-up phase when this many lanes wait for it ...
+constexpr int kBatchInterp = 4;          // ... the stencil phase when this many lanes wait for it ...
+constexpr int kBatchRunnable = 8;        // ... or when fewer lanes than this could probe / step instead
 
 __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket, uint32_t& px, uint32_t& py)
 {
@@ -92,12 +103,13 @@ __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket,
 }
 
 template<bool AUX, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* __restrict__ film,
                   AuxOut aux, unsigned int* queue, unsigned long long* counters)
 {
     __shared__ RootSmem root;
+    __shared__ WalkSmem<kBlockThreads> wsm;
     stageRoot(g, root);
     __syncthreads();
 
@@ -154,9 +166,14 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             else status = kWalkMiss;
         }
         __syncwarp();
-        // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases)
+        // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
+        // The rare phases run when enough lanes wait for them, or when too few lanes could do anything else.
         {
-            const int r = lsAdvance<COUNT, true>(rayOn, g, root, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
+            const int nA = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendLevel));
+            const int nC = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendInterp != 0));
+            const int nRun = __popc(__ballot_sync(0xffffffffu, rayOn && walk.runnable()));
+            const bool runA = nA >= kBatchLevel || nRun < kBatchRunnable, runC = nC >= kBatchInterp || nRun < kBatchRunnable;
+            const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, runA, runC, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
             if (rayOn) status = r;
         }
         __syncwarp();
@@ -203,6 +220,7 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
                      float iso, float vmin, float vmax, HitOut* __restrict__ hits)
 {
     __shared__ RootSmem root;
+    __shared__ WalkSmem<kBlockThreads> wsm;
     stageRoot(g, root);
     __syncthreads();
     TreeCursor acc; acc.reset();
@@ -216,7 +234,7 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
         if (space == 0) worldToIndex(g, ray);
         HitOut o = {};
         LsHit h;
-        if (clipRay(ray, g, 0) && intersectLevelSet<false>(g, root, acc, st, ray, iso, vmin, vmax, h, c)) {
+        if (clipRay(ray, g, 0) && intersectLevelSet<false, kBlockThreads>(g, root, wsm, acc, st, ray, iso, vmin, vmax, h, c)) {
             double x = h.px, y = h.py, z = h.pz;
             double nx = h.gx, ny = h.gy, nz = h.gz;
             vnormalize(nx, ny, nz);
