@@ -490,7 +490,14 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
         w.pendStep = false;
         if (!cur.step(ray, LsWalk::shiftOf(w.lvl))) {
             if (w.lvl == 0) status = kWalkMiss;
-            else { --w.lvl; sm.unpark(w.lvl, cur); w.skip = true; }
+            else {
+                // the parent steps right away (one level per call; a second exhausted level waits for the next call)
+                --w.lvl; sm.unpark(w.lvl, cur);
+                if (!cur.step(ray, LsWalk::shiftOf(w.lvl))) {
+                    if (w.lvl == 0) status = kWalkMiss;
+                    else { --w.lvl; sm.unpark(w.lvl, cur); w.skip = true; }
+                }
+            }
         }
     }
     return status;
