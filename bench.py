@@ -210,29 +210,14 @@ def main():
     opts = ctx.ls_opts(part=part, uniform_bg=True)
     opts.flags |= abi.ASYNC
 
-    # multi-GPU frame assembly: tiles [ty, tx] of TILE_H x TILE_W pixels; rank r owns flat tile ids r, r+world, ...
-    tiles_y, tiles_x = H // TILE_H, W // TILE_W
-    assert tiles_y * TILE_H == H and tiles_x * TILE_W == W
-    ntiles = tiles_y * tiles_x
-    per_rank = (ntiles + world - 1) // world
-    send = torch.zeros((per_rank, TILE_H, TILE_W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
-    recv = [torch.zeros_like(send) for _ in range(world)] if (world > 1 and rank == 0) else None
-
-    def tile_view(t):
-        return t.view(tiles_y, TILE_H, tiles_x, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(ntiles, TILE_H, TILE_W, 4)
+    # multi-GPU frame assembly (openvdb_b200/frame.py): rank r owns tiles r, r+world, ...; one gather per frame
+    from openvdb_b200.frame import TileGather
+    gather = TileGather(H, W, TILE_H, TILE_W, rank, world, "cuda") if world > 1 else None
 
     def step():
         ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
-        if world > 1:
-            mine = tile_view(film)[rank::world]
-            send[:mine.shape[0]].copy_(mine)
-            dist.gather(send, recv, dst=0)
-            if rank == 0:
-                tv = tile_view(film)          # a copy (permute + reshape); scatter the received tiles back
-                for q in range(1, world):
-                    n = tv[q::world].shape[0]
-                    tv[q::world] = recv[q][:n]
-                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
+        if gather:
+            gather.gather(film)
 
     def barrier():
         torch.cuda.synchronize()
@@ -252,16 +237,8 @@ def main():
         ev[k][0].record(stream)
         ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
         ev[k][1].record(stream)
-        if world > 1:
-            mine = tile_view(film)[rank::world]
-            send[:mine.shape[0]].copy_(mine)
-            dist.gather(send, recv, dst=0)
-            if rank == 0:
-                tv = tile_view(film)
-                for q in range(1, world):
-                    n = tv[q::world].shape[0]
-                    tv[q::world] = recv[q][:n]
-                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
+        if gather:
+            gather.gather(film)
         ev[k][2].record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -289,15 +266,8 @@ def main():
             step_opts = ctx.ls_opts(part=part)
             step_opts.flags |= abi.ASYNC
             ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, opts=step_opts)
-            mine = tile_view(film)[rank::world]
-            send[:mine.shape[0]].copy_(mine)
-            dist.gather(send, recv, dst=0)
+            gather.gather(film)
             if rank == 0:
-                tv = tile_view(film)
-                for q in range(1, world):
-                    n = tv[q::world].shape[0]
-                    tv[q::world] = recv[q][:n]
-                film.copy_(tv.view(tiles_y, tiles_x, TILE_H, TILE_W, 4).permute(0, 2, 1, 3, 4).reshape(H, W, 4))
                 torch.from_numpy(host.array).copy_(film)                         # D2H of the finished frame
             torch.cuda.synchronize()
 
