@@ -1,0 +1,382 @@
+// vdbrt/RayTracer.h -- C++ facade over the C ABI (include/vdbrt.h) with the reference's class names and call shapes.
+//
+// Mirrors openvdb/openvdb/tools/RayTracer.h and tools/RayIntersector.h for the one path this library accelerates:
+//   tools::Film, BaseCamera / PerspectiveCamera / OrthographicCamera, BaseShader + the four constant-colour shaders,
+//   LevelSetRayIntersector, VolumeRayIntersector, LevelSetRayTracer, VolumeRender, rayTrace().
+// Host code written against the reference changes its grid type (a NanoVDB-serialised grid uploaded to the GPU) and its
+// namespace; the per-pixel loops (RayTracer.h:899-918, 991-1070) run in the CUDA kernels of libvdbrt.so.
+//
+// What cannot be a drop-in: user subclasses of BaseCamera / BaseShader (virtual getRay / operator()) cannot run on the
+// device, so only the two cameras and the four const-colour shaders are accepted; anything else throws RuntimeError
+// (there is no CPU fallback, by design).  Errors the reference throws at construction are thrown here at the same
+// points (intersector / tracer construction), with the same exception kinds.
+#pragma once
+#include "../vdbrt.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace vdbrt {
+
+struct RuntimeError : std::runtime_error { using std::runtime_error::runtime_error; };   // openvdb::RuntimeError
+struct ValueError : std::runtime_error { using std::runtime_error::runtime_error; };     // openvdb::ValueError
+
+inline void check(int code)
+{
+    if (code == VDBRT_OK) return;
+    const std::string msg = vdbrt_last_error();
+    if (code == VDBRT_ERR_ISO_RANGE || code == VDBRT_ERR_SPP_ZERO) throw ValueError(msg);
+    throw RuntimeError(msg);
+}
+
+struct Vec3R { double x = 0, y = 0, z = 0; Vec3R() = default; Vec3R(double a, double b, double c) : x(a), y(b), z(c) {} explicit Vec3R(double v) : x(v), y(v), z(v) {} };
+
+/// one GPU
+class Context
+{
+public:
+    explicit Context(int device = 0) { check(vdbrt_create(device, &mCtx)); }
+    ~Context() { vdbrt_destroy(mCtx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    vdbrt_ctx* get() const { return mCtx; }
+private:
+    vdbrt_ctx* mCtx = nullptr;
+};
+
+/// A NanoGrid<float> resident on the GPU (replaces the openvdb::FloatGrid argument of the reference's classes).
+class FloatGrid
+{
+public:
+    using Ptr = std::shared_ptr<FloatGrid>;
+    /// upload a serialised grid (nanovdb::GridHandle<HostBuffer>::data(), size())
+    static Ptr upload(Context& ctx, const void* nanovdbBuffer, uint64_t bytes)
+    {
+        vdbrt_grid* g = nullptr;
+        check(vdbrt_upload_grid(ctx.get(), nanovdbBuffer, bytes, VDBRT_MEM_HOST, &g));
+        return Ptr(new FloatGrid(ctx, g));
+    }
+    static Ptr createLevelSetSphere(Context& ctx, double radius, const Vec3R& center, double voxelSize, double halfWidth = 3.0)
+    {
+        vdbrt_grid* g = nullptr;
+        const double c[3] = {center.x, center.y, center.z};
+        check(vdbrt_build_levelset_sphere(ctx.get(), radius, c, voxelSize, halfWidth, &g));
+        return Ptr(new FloatGrid(ctx, g));
+    }
+    static Ptr createLevelSetTorus(Context& ctx, double majorRadius, double minorRadius, const Vec3R& center, double voxelSize, double halfWidth = 3.0)
+    {
+        vdbrt_grid* g = nullptr;
+        const double c[3] = {center.x, center.y, center.z};
+        check(vdbrt_build_levelset_torus(ctx.get(), majorRadius, minorRadius, c, voxelSize, halfWidth, &g));
+        return Ptr(new FloatGrid(ctx, g));
+    }
+    /// openvdb::tools::sdfToFogVolume
+    Ptr sdfToFogVolume() const
+    {
+        vdbrt_grid* g = nullptr;
+        check(vdbrt_build_fog_from_levelset(mCtx->get(), mGrid, &g));
+        return Ptr(new FloatGrid(*mCtx, g));
+    }
+    ~FloatGrid() { vdbrt_free_grid(mCtx->get(), mGrid); }
+    vdbrt_grid_info info() const { vdbrt_grid_info i; check(vdbrt_grid_get_info(mGrid, &i)); return i; }
+    Context& context() const { return *mCtx; }
+    const vdbrt_grid* get() const { return mGrid; }
+private:
+    FloatGrid(Context& ctx, vdbrt_grid* g) : mCtx(&ctx), mGrid(g) {}
+    Context* mCtx; vdbrt_grid* mGrid;
+};
+
+namespace tools {
+
+/// tools::Film (RayTracer.h:226-345): pixels live in pinned host memory so the copies to/from the GPU run at full speed.
+class Film
+{
+public:
+    struct RGBA {
+        using ValueT = float;
+        RGBA() : r(0), g(0), b(0), a(1) {}
+        explicit RGBA(ValueT i) : r(i), g(i), b(i), a(1) {}
+        RGBA(ValueT _r, ValueT _g, ValueT _b, ValueT _a = 1.0f) : r(_r), g(_g), b(_b), a(_a) {}
+        RGBA(double _r, double _g, double _b, double _a = 1.0) : r(ValueT(_r)), g(ValueT(_g)), b(ValueT(_b)), a(ValueT(_a)) {}
+        RGBA operator*(ValueT s) const { return RGBA(r * s, g * s, b * s); }
+        RGBA operator+(const RGBA& o) const { return RGBA(r + o.r, g + o.g, b + o.b); }
+        RGBA operator*(const RGBA& o) const { return RGBA(r * o.r, g * o.g, b * o.b); }
+        RGBA& operator+=(const RGBA& o) { r += o.r; g += o.g; b += o.b; a += o.a; return *this; }
+        void over(const RGBA& rhs) { const float s = rhs.a * (1.0f - a); r = a * r + s * rhs.r; g = a * g + s * rhs.g; b = a * b + s * rhs.b; a = a + s; }
+        ValueT r, g, b, a;
+    };
+    Film(size_t width, size_t height) : mWidth(width), mHeight(height), mSize(width * height) { alloc(); fill(RGBA()); }
+    Film(size_t width, size_t height, const RGBA& bg) : mWidth(width), mHeight(height), mSize(width * height) { alloc(); fill(bg); }
+    ~Film() { vdbrt_host_free(mPixels); }
+    Film(const Film&) = delete;
+    Film& operator=(const Film&) = delete;
+    const RGBA& pixel(size_t w, size_t h) const { return mPixels[w + h * mWidth]; }
+    RGBA& pixel(size_t w, size_t h) { mUniform = false; return mPixels[w + h * mWidth]; }
+    void fill(const RGBA& rgb = RGBA(0)) { for (size_t i = 0; i < mSize; ++i) mPixels[i] = rgb; mUniform = true; mFill = rgb; }
+    void checkerboard(const RGBA& c1 = RGBA(0.3f), const RGBA& c2 = RGBA(0.6f), size_t size = 32)
+    {
+        RGBA* p = mPixels;
+        for (size_t j = 0; j < mHeight; ++j) for (size_t i = 0; i < mWidth; ++i, ++p) *p = ((i & size) ^ (j & size)) ? c1 : c2;
+        mUniform = false;
+    }
+    template<typename Type = unsigned char>
+    std::unique_ptr<Type[]> convertToBitBuffer(const bool alpha = true) const
+    {
+        const size_t totalSize = mSize * (alpha ? 4 : 3);
+        std::unique_ptr<Type[]> buffer(new Type[totalSize]);
+        Type* q = buffer.get();
+        const RGBA* p = mPixels;
+        size_t n = mSize;
+        while (n--) { *q++ = Type(255.0f * p->r); *q++ = Type(255.0f * p->g); *q++ = Type(255.0f * p->b); if (alpha) *q++ = Type(255.0f * p->a); ++p; }
+        return buffer;
+    }
+    void savePPM(const std::string& fileName);   // defined below (same P6 layout as the reference, RayTracer.h:319-335)
+    size_t width() const { return mWidth; }
+    size_t height() const { return mHeight; }
+    size_t numPixels() const { return mSize; }
+    const RGBA* pixels() const { return mPixels; }
+    // facade internals: a film that was only ever fill()ed lets the library skip the host->device copy
+    bool uniform(RGBA& c) const { c = mFill; return mUniform; }
+    RGBA* data() { return mPixels; }
+    void markRendered() { mUniform = false; }
+private:
+    void alloc() { void* p = nullptr; check(vdbrt_host_alloc(mSize * sizeof(RGBA) + 16, &p)); mPixels = static_cast<RGBA*>(p); }
+    size_t mWidth, mHeight, mSize;
+    RGBA* mPixels = nullptr;
+    bool mUniform = true;
+    RGBA mFill;
+};
+
+class BaseCamera
+{
+public:
+    virtual ~BaseCamera() = default;
+    Film::RGBA& pixel(size_t i, size_t j) { return mFilm->pixel(i, j); }
+    size_t width() const { return mFilm->width(); }
+    size_t height() const { return mFilm->height(); }
+    /// BaseCamera::lookAt (RayTracer.h:379-389)
+    void lookAt(const Vec3R& xyz, const Vec3R& up = Vec3R(0.0, 1.0, 0.0))
+    {
+        const double t[3] = {xyz.x, xyz.y, xyz.z}, u[3] = {up.x, up.y, up.z};
+        check(vdbrt_camera_look_at(&mPod, t, u));
+    }
+    const vdbrt_camera& pod() const { return mPod; }
+    Film& film() const { return *mFilm; }
+protected:
+    explicit BaseCamera(Film& film) : mFilm(&film) {}
+    Film* mFilm;
+    vdbrt_camera mPod;
+};
+
+class PerspectiveCamera : public BaseCamera
+{
+public:
+    PerspectiveCamera(Film& film, const Vec3R& rotation = Vec3R(0.0), const Vec3R& translation = Vec3R(0.0), double focalLength = 50.0,
+                      double aperture = 41.2136, double nearPlane = 1e-3, double farPlane = std::numeric_limits<double>::max())
+        : BaseCamera(film)
+    {
+        const double r[3] = {rotation.x, rotation.y, rotation.z}, t[3] = {translation.x, translation.y, translation.z};
+        check(vdbrt_camera_perspective(&mPod, uint32_t(film.width()), uint32_t(film.height()), r, t, focalLength, aperture, nearPlane, farPlane));
+    }
+};
+
+class OrthographicCamera : public BaseCamera
+{
+public:
+    OrthographicCamera(Film& film, const Vec3R& rotation = Vec3R(0.0), const Vec3R& translation = Vec3R(0.0), double frameWidth = 1.0,
+                       double nearPlane = 1e-3, double farPlane = std::numeric_limits<double>::max())
+        : BaseCamera(film)
+    {
+        const double r[3] = {rotation.x, rotation.y, rotation.z}, t[3] = {translation.x, translation.y, translation.z};
+        check(vdbrt_camera_orthographic(&mPod, uint32_t(film.width()), uint32_t(film.height()), r, t, frameWidth, nearPlane, farPlane));
+    }
+};
+
+/// BaseShader: the device runs the four constant-colour shaders; the object only carries their parameters.
+class BaseShader
+{
+public:
+    virtual ~BaseShader() = default;
+    virtual BaseShader* copy() const = 0;
+    const vdbrt_shader& pod() const { return mPod; }
+protected:
+    BaseShader(uint32_t kind, const Film::RGBA& c) { std::memset(&mPod, 0, sizeof(mPod)); mPod.kind = kind; mPod.rgba[0] = c.r; mPod.rgba[1] = c.g; mPod.rgba[2] = c.b; mPod.rgba[3] = c.a; }
+    vdbrt_shader mPod;
+};
+// the reference's default template argument GridT = Film::RGBA selects the constant-colour specialisation (RayTracer.h:565,614,671,728)
+template<typename GridT = Film::RGBA> class MatteShader;
+template<typename GridT = Film::RGBA> class NormalShader;
+template<typename GridT = Film::RGBA> class PositionShader;
+template<typename GridT = Film::RGBA> class DiffuseShader;
+template<> class MatteShader<Film::RGBA> : public BaseShader { public:
+    MatteShader(const Film::RGBA& c = Film::RGBA(1.0f)) : BaseShader(VDBRT_SHADER_MATTE, c) {}
+    BaseShader* copy() const override { return new MatteShader(*this); } };
+template<> class NormalShader<Film::RGBA> : public BaseShader { public:
+    NormalShader(const Film::RGBA& c = Film::RGBA(1.0f)) : BaseShader(VDBRT_SHADER_NORMAL, c) {}
+    BaseShader* copy() const override { return new NormalShader(*this); } };
+template<> class PositionShader<Film::RGBA> : public BaseShader { public:
+    /// bbox in world space: min and max corners (math::BBox<Vec3R>)
+    PositionShader(const Vec3R& bboxMin, const Vec3R& bboxMax, const Film::RGBA& c = Film::RGBA(1.0f)) : BaseShader(VDBRT_SHADER_POSITION, c)
+    {
+        mPod.bbox_min[0] = bboxMin.x; mPod.bbox_min[1] = bboxMin.y; mPod.bbox_min[2] = bboxMin.z;
+        mPod.inv_dim[0] = 1.0 / (bboxMax.x - bboxMin.x); mPod.inv_dim[1] = 1.0 / (bboxMax.y - bboxMin.y); mPod.inv_dim[2] = 1.0 / (bboxMax.z - bboxMin.z);
+    }
+    BaseShader* copy() const override { return new PositionShader(*this); } };
+template<> class DiffuseShader<Film::RGBA> : public BaseShader { public:
+    DiffuseShader(const Film::RGBA& d = Film::RGBA(1.0f)) : BaseShader(VDBRT_SHADER_DIFFUSE, d) {}
+    BaseShader* copy() const override { return new DiffuseShader(*this); } };
+
+/// tools::LevelSetRayIntersector (RayIntersector.h:79-246): validates at construction, batches of rays on the device
+template<typename GridT = FloatGrid>
+class LevelSetRayIntersector
+{
+public:
+    LevelSetRayIntersector(const GridT& grid, float isoValue = 0.0f) : mGrid(&grid), mIso(isoValue)
+    {
+        // same construction-time checks as the reference, evaluated by the library (empty batch = validation only)
+        check(vdbrt_intersect_levelset(grid.context().get(), grid.get(), nullptr, 0, VDBRT_SPACE_WORLD, isoValue, nullptr, VDBRT_MEM_HOST));
+    }
+    const float& getIsoValue() const { return mIso; }
+    /// intersectsWS / intersectsIS for n rays at once; hits[i].hit == 0 leaves the record zeroed (outputs untouched)
+    void intersectsWS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const
+    { check(vdbrt_intersect_levelset(mGrid->context().get(), mGrid->get(), rays, n, VDBRT_SPACE_WORLD, mIso, hits, VDBRT_MEM_HOST)); }
+    void intersectsIS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const
+    { check(vdbrt_intersect_levelset(mGrid->context().get(), mGrid->get(), rays, n, VDBRT_SPACE_INDEX, mIso, hits, VDBRT_MEM_HOST)); }
+    bool intersectsWS(const vdbrt_ray& ray, Vec3R& world, Vec3R& normal, double& wTime) const
+    {
+        vdbrt_hit h; intersectsWS(&ray, 1, &h);
+        if (!h.hit) return false;
+        world = Vec3R(h.xyz_world[0], h.xyz_world[1], h.xyz_world[2]); normal = Vec3R(h.nml[0], h.nml[1], h.nml[2]); wTime = h.t_world;
+        return true;
+    }
+    const GridT& grid() const { return *mGrid; }
+private:
+    const GridT* mGrid; float mIso;
+};
+
+/// tools::VolumeRayIntersector (RayIntersector.h:277-485): hits() for batches of rays
+template<typename GridT = FloatGrid>
+class VolumeRayIntersector
+{
+public:
+    explicit VolumeRayIntersector(const GridT& grid) : mGrid(&grid)
+    { check(vdbrt_volume_spans(grid.context().get(), grid.get(), nullptr, 0, VDBRT_SPACE_WORLD, 0, nullptr, nullptr, VDBRT_MEM_HOST)); }
+    /// spans[i*maxSpans + k] = {t0,t1}; counts[i] = -1 when the ray misses the bbox
+    void hits(const vdbrt_ray* rays, size_t n, bool indexSpace, uint32_t maxSpans, double* spans, int32_t* counts) const
+    { check(vdbrt_volume_spans(mGrid->context().get(), mGrid->get(), rays, n, indexSpace ? VDBRT_SPACE_INDEX : VDBRT_SPACE_WORLD, maxSpans, spans, counts, VDBRT_MEM_HOST)); }
+    const GridT& grid() const { return *mGrid; }
+private:
+    const GridT* mGrid;
+};
+
+/// tools::LevelSetRayTracer (RayTracer.h:72-140,789-918)
+template<typename GridT = FloatGrid, typename IntersectorT = LevelSetRayIntersector<GridT>>
+class LevelSetRayTracer
+{
+public:
+    LevelSetRayTracer(const GridT& grid, const BaseShader& shader, BaseCamera& camera, size_t pixelSamples = 1, unsigned int seed = 0)
+        : mInter(grid), mShader(shader.copy()), mCamera(&camera) { setPixelSamples(pixelSamples, seed); }
+    LevelSetRayTracer(const IntersectorT& inter, const BaseShader& shader, BaseCamera& camera, size_t pixelSamples = 1, unsigned int seed = 0)
+        : mInter(inter), mShader(shader.copy()), mCamera(&camera) { setPixelSamples(pixelSamples, seed); }
+    void setGrid(const GridT& grid) { mInter = IntersectorT(grid); }
+    void setIntersector(const IntersectorT& inter) { mInter = inter; }
+    void setShader(const BaseShader& shader) { mShader.reset(shader.copy()); }
+    void setCamera(BaseCamera& camera) { mCamera = &camera; }
+    void setPixelSamples(size_t pixelSamples, unsigned int seed = 0)
+    {
+        if (pixelSamples == 0) throw ValueError("pixelSamples must be larger than zero!");       // RayTracer.h:877-879
+        std::memset(&mOpts, 0, sizeof(mOpts));
+        mOpts.spp = uint32_t(pixelSamples);
+        if (pixelSamples > 1) check(vdbrt_jitter_table(seed, mOpts.jitter));
+    }
+    /// the `threaded` flag of the reference is accepted and ignored: the frame is rendered by the GPU either way
+    void render(bool /*threaded*/ = true) const
+    {
+        Film& film = mCamera->film();
+        vdbrt_ls_opts o = mOpts;
+        o.iso = mInter.getIsoValue();
+        vdbrt_film f; std::memset(&f, 0, sizeof(f));
+        f.pixels = reinterpret_cast<float*>(film.data()); f.width = uint32_t(film.width()); f.height = uint32_t(film.height()); f.memspace = VDBRT_MEM_HOST;
+        Film::RGBA bg;
+        if (film.uniform(bg)) { o.flags |= VDBRT_LS_UNIFORM_BG; f.bg_rgba[0] = bg.r; f.bg_rgba[1] = bg.g; f.bg_rgba[2] = bg.b; f.bg_rgba[3] = bg.a; }
+        check(vdbrt_render_levelset(mInter.grid().context().get(), mInter.grid().get(), &mCamera->pod(), &mShader->pod(), &o, &f, nullptr));
+        film.markRendered();
+    }
+private:
+    IntersectorT mInter;
+    std::unique_ptr<const BaseShader> mShader;
+    BaseCamera* mCamera;
+    vdbrt_ls_opts mOpts;
+};
+
+/// tools::rayTrace (RayTracer.h:48-64,758-783)
+template<typename GridT>
+inline void rayTrace(const GridT& grid, const BaseShader& shader, BaseCamera& camera, size_t pixelSamples = 1, unsigned int seed = 0, bool threaded = true)
+{
+    LevelSetRayTracer<GridT, LevelSetRayIntersector<GridT>> tracer(grid, shader, camera, pixelSamples, seed);
+    tracer.render(threaded);
+}
+template<typename GridT, typename IntersectorT>
+inline void rayTrace(const GridT&, const IntersectorT& inter, const BaseShader& shader, BaseCamera& camera, size_t pixelSamples = 1, unsigned int seed = 0, bool threaded = true)
+{
+    LevelSetRayTracer<GridT, IntersectorT> tracer(inter, shader, camera, pixelSamples, seed);
+    tracer.render(threaded);
+}
+
+/// tools::VolumeRender (RayTracer.h:148-220,922-1070)
+template<typename IntersectorT = VolumeRayIntersector<FloatGrid>>
+class VolumeRender
+{
+public:
+    VolumeRender(const IntersectorT& inter, BaseCamera& camera) : mInter(inter), mCamera(&camera) { check(vdbrt_vol_opts_default(&mOpts)); }
+    void setCamera(BaseCamera& camera) { mCamera = &camera; }
+    void setIntersector(const IntersectorT& inter) { mInter = inter; }
+    /// throws (like Vec3::unit) if the vector is null
+    void setLightDir(double x, double y, double z)
+    {
+        const double len = std::sqrt(x * x + y * y + z * z);
+        if (!(len > 0.0)) throw RuntimeError("Normalizing null 3-vector");
+        mOpts.light_dir[0] = x / len; mOpts.light_dir[1] = y / len; mOpts.light_dir[2] = z / len;
+    }
+    void setLightColor(double r, double g, double b) { mOpts.light_color[0] = r; mOpts.light_color[1] = g; mOpts.light_color[2] = b; }
+    void setPrimaryStep(double s) { mOpts.primary_step = s; }
+    void setShadowStep(double s) { mOpts.shadow_step = s; }
+    void setScattering(double x, double y, double z) { mOpts.scattering[0] = x; mOpts.scattering[1] = y; mOpts.scattering[2] = z; }
+    void setAbsorption(double x, double y, double z) { mOpts.absorption[0] = x; mOpts.absorption[1] = y; mOpts.absorption[2] = z; }
+    void setLightGain(double g) { mOpts.light_gain = g; }
+    void setCutOff(double c) { mOpts.cutoff = c; }
+    void render(bool /*threaded*/ = true) const
+    {
+        Film& film = mCamera->film();
+        vdbrt_film f; std::memset(&f, 0, sizeof(f));
+        f.pixels = reinterpret_cast<float*>(film.data()); f.width = uint32_t(film.width()); f.height = uint32_t(film.height()); f.memspace = VDBRT_MEM_HOST;
+        check(vdbrt_render_volume(mInter.grid().context().get(), mInter.grid().get(), &mCamera->pod(), &mOpts, &f));
+        film.markRendered();
+    }
+private:
+    IntersectorT mInter;
+    BaseCamera* mCamera;
+    vdbrt_vol_opts mOpts;
+};
+
+} // namespace tools
+} // namespace vdbrt
+
+#include <cmath>
+#include <fstream>
+#include <iostream>
+inline void vdbrt::tools::Film::savePPM(const std::string& fileName)
+{
+    std::string name(fileName);
+    if (name.find_last_of(".") == std::string::npos) name.append(".ppm");
+    std::ofstream os(name.c_str(), std::ios_base::binary);
+    if (!os.is_open()) { std::cerr << "Error opening PPM file \"" << name << "\"" << std::endl; return; }
+    auto buf = this->convertToBitBuffer<unsigned char>(/*alpha=*/false);
+    os << "P6\n" << mWidth << " " << mHeight << "\n255\n";
+    os.write(reinterpret_cast<const char*>(buf.get()), 3 * mSize * sizeof(unsigned char));
+}
