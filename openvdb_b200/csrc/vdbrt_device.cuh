@@ -522,58 +522,84 @@ __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSm
 // The bool topology copy the reference walks (tools/RayIntersector.h:299-319, dilation 0) has the float tree's
 // child topology and active states, so the float tree itself is probed.
 // ------------------------------------------------------------------------------------------------------------
-struct SpanWalker {
-    Dda cur; DdaSave s12, s7;
-    double ts0, topT1;     // open span start (<0: none), maxTime of the root-level DDA
-    int shift;             // 12 / 7 / 3; -1 = finished
-    bool needStep;
+// Parking area of the fog kernel (structure of arrays, one column per thread): slots 0,1 = suspended parents of the
+// primary walk, 2,3 = suspended parents of the shadow walk, 4 = the primary walk's current DDA while a shadow ray runs.
+template<int THREADS>
+struct FogSmem {
+    double t1[5][THREADS], nx[5][THREADS], ny[5][THREADS], nz[5][THREADS];
+    int vx[5][THREADS], vy[5][THREADS], vz[5][THREADS];
+    double ray[11][THREADS];          // the primary index-space ray while a shadow ray is active
+    double dt0[THREADS];              // primary Dda::t0
+    double ts0[THREADS], topT1[THREADS], tcur[THREADS], tend[THREADS];
+    int misc[THREADS];                // primary walk: lvl | needStep << 8
+    double sbase[8];                  // shadow ray constants shared by the CTA: dir xyz, inv xyz, t0, t1 (index space)
+    __device__ __forceinline__ void park(int slot, const Dda& d)
+    {
+        const int t = threadIdx.x;
+        t1[slot][t] = d.t1; nx[slot][t] = d.nx; ny[slot][t] = d.ny; nz[slot][t] = d.nz; vx[slot][t] = d.vx; vy[slot][t] = d.vy; vz[slot][t] = d.vz;
+    }
+    __device__ __forceinline__ void unpark(int slot, Dda& d) const
+    {
+        const int t = threadIdx.x;
+        d.t1 = t1[slot][t]; d.nx = nx[slot][t]; d.ny = ny[slot][t]; d.nz = nz[slot][t]; d.vx = vx[slot][t]; d.vy = vy[slot][t]; d.vz = vz[slot][t];
+    }
+};
 
+enum { kSpanContinue = 0, kSpanEmit = 1, kSpanDone = 2 };
+
+// One unit of VolumeHDDA::hits per call (at most one DDA set-up or step and one cell probe, each a single site).
+struct SpanWalk {
+    Dda cur;
+    double ts0, topT1;     // open span start (<0: none), maxTime of the root-level DDA
+    double c0, c1;         // pending child range: ray.setTimes(time(), next()) (DDA.h:252,326)
+    int lvl;               // 0 root-level DDA (4096^3), 1 inside an upper node (128^3), 2 inside a lower node (8^3); -1 = finished
+    bool needStep, pendLevel;
+
+    __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }
     __device__ __forceinline__ void begin(const Ray& ray)
     {
-        shift = 12; needStep = false; ts0 = -1.0; topT1 = ray.t1;
-        cur.init(ray, ray.t0, ray.t1, 12);
+        lvl = 0; needStep = false; pendLevel = true; ts0 = -1.0; topT1 = ray.t1; c0 = ray.t0; c1 = ray.t1;
     }
-    // Produces the next valid span; false when the walk is over.
-    template<bool COUNT>
-    __device__ __forceinline__ bool next(const DevGrid& g, const RootSmem& s, TreeCursor& acc, const Ray& ray, double& a, double& b, Counters& c)
+    // slotBase: first parking slot of this walk's parents (0 primary, 2 shadow)
+    template<bool COUNT, class SM>
+    __device__ __forceinline__ int advance(const DevGrid& g, const RootSmem& s, SM& sm, int slotBase, TreeCursor& acc, const Ray& ray,
+                                           double& a, double& b, Counters& c)
     {
-        if (shift < 0) return false;
-        for (;;) {
-            if (needStep) {
-                bool over = false;
-                for (;;) {
-                    if (cur.step(ray, shift)) break;
-                    // a level is exhausted: "if (t.t0>=0) t.t1 = mDDA.maxTime()" -- only the outermost assignment
-                    // survives because any later close overwrites t1 (DDA.h:263,335)
-                    if (shift == 12) { over = true; break; }
-                    if (shift == 3) { unpark(cur, s7); shift = 7; } else { unpark(cur, s12); shift = 12; }
+        if (lvl < 0) return kSpanDone;
+        if (pendLevel) {
+            cur.init(ray, c0, c1, shiftOf(lvl));
+            pendLevel = false;
+        } else if (needStep) {
+            if (!cur.step(ray, shiftOf(lvl))) {
+                // a level is exhausted: "if (t.t0>=0) t.t1 = mDDA.maxTime()" -- only the outermost assignment survives
+                // because any later close overwrites t1 (DDA.h:263,335)
+                if (lvl == 0) {
+                    lvl = -1;
+                    if (ts0 >= 0.0) { a = ts0; b = topT1; ts0 = -1.0; return (b - a) > 1e-9 ? kSpanEmit : kSpanDone; }   // TimeSpan::valid (Ray.h:48)
+                    return kSpanDone;
                 }
-                if (over) {
-                    shift = -1;
-                    if (ts0 >= 0.0) { a = ts0; b = topT1; ts0 = -1.0; return (b - a) > 1e-9; }   // TimeSpan::valid (Ray.h:48)
-                    return false;
-                }
-            }
-            needStep = true;
-            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
-            if (COUNT) { if (shift == 12) ++c.root; else if (shift == 7) ++c.upper; else ++c.lower; }
-            const bool child = shift == 12 ? depth <= 2 : (shift == 7 ? depth <= 1 : false);
-            if (child) {
-                const double c0 = cur.t0, c1 = cur.next();                 // ray.setTimes(time(), next()) (DDA.h:252,326)
-                if (shift == 12) { park(s12, cur); shift = 7; } else { park(s7, cur); shift = 3; }
-                cur.init(ray, c0, c1, shift);
-                needStep = false;
-                continue;
-            }
-            // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state
-            const bool active = (shift == 3 && depth == 0) ? true : acc.activeAt(g, s, depth, cur.vx, cur.vy, cur.vz);
-            if (active) {
-                if (ts0 < 0.0) ts0 = cur.t0;
-            } else if (ts0 >= 0.0) {
-                a = ts0; b = cur.t0; ts0 = -1.0;
-                if ((b - a) > 1e-9) return true;
+                --lvl; sm.unpark(slotBase + lvl, cur);
+                return kSpanContinue;                   // the parent steps on the next call
             }
         }
+        needStep = true;
+        const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+        if (COUNT) { if (lvl == 0) ++c.root; else if (lvl == 1) ++c.upper; else ++c.lower; }
+        if (lvl < 2 && depth <= 2 - lvl) {              // child node: walk it
+            c0 = cur.t0; c1 = cur.next();
+            sm.park(slotBase + lvl, cur);
+            ++lvl; pendLevel = true; needStep = false;
+            return kSpanContinue;
+        }
+        // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state
+        const bool active = (lvl == 2 && depth == 0) ? true : acc.activeAt(g, s, depth, cur.vx, cur.vy, cur.vz);
+        if (active) {
+            if (ts0 < 0.0) ts0 = cur.t0;
+        } else if (ts0 >= 0.0) {
+            a = ts0; b = cur.t0; ts0 = -1.0;
+            if ((b - a) > 1e-9) return kSpanEmit;
+        }
+        return kSpanContinue;
     }
 };
 

@@ -256,6 +256,7 @@ k_volume_spans(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays
                uint32_t maxSpans, double* __restrict__ spans, int32_t* __restrict__ counts)
 {
     __shared__ RootSmem root;
+    __shared__ FogSmem<kBlockThreads> fsm;
     stageRoot(g, root);
     __syncthreads();
     TreeCursor acc; acc.reset();
@@ -267,11 +268,16 @@ k_volume_spans(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays
         ray.t0 = rays[k].t0; ray.t1 = rays[k].t1;
         if (space == 0) worldToIndex(g, ray);
         if (!clipRay(ray, g, 1)) { counts[k] = -1; continue; }
-        SpanWalker w; w.begin(ray);
+        SpanWalk w; w.begin(ray);
         int cnt = 0; double a, b;
-        while (w.template next<false>(g, root, acc, ray, a, b, c)) {
-            if (uint32_t(cnt) < maxSpans) { spans[(k * maxSpans + cnt) * 2] = a; spans[(k * maxSpans + cnt) * 2 + 1] = b; }
-            ++cnt;
+#pragma unroll 1
+        for (;;) {
+            const int r = w.template advance<false>(g, root, fsm, 0, acc, ray, a, b, c);
+            if (r == kSpanDone) break;
+            if (r == kSpanEmit) {
+                if (uint32_t(cnt) < maxSpans) { spans[(k * maxSpans + cnt) * 2] = a; spans[(k * maxSpans + cnt) * 2 + 1] = b; }
+                ++cnt;
+            }
         }
         counts[k] = cnt;
     }
@@ -286,84 +292,171 @@ struct VolParams {
     double ext[3], albedo[3];   // extinction = -scattering-absorption; albedo = lightColor*scattering/(scattering+absorption)
 };
 
+// Per-lane state machine, warp-synchronous like the level-set kernel.  A lane is in one of four modes -- walking the
+// primary HDDA for the next span, marching samples inside a primary span, walking the shadow HDDA, marching shadow
+// samples -- and only ONE walker and ONE ray live in its registers: the suspended primary walk / ray sit in shared memory
+// while a shadow ray runs.  Each iteration runs the phases  walk | sample | exp  once, each a single site in the code.
+enum { kFogIdle = 0, kFogPWalk = 1, kFogPMarch = 2, kFogSWalk = 3, kFogSMarch = 4 };
+constexpr int kFogBatch = 8;             // a phase runs when this many lanes want it, or when the other phases are starved
+
 template<bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, 3)
 k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
                 const __grid_constant__ TileMap tm, float4* __restrict__ film, unsigned int* queue, unsigned long long* counters)
 {
     __shared__ RootSmem root;
+    __shared__ FogSmem<kBlockThreads> sm;
     stageRoot(g, root);
+    if (threadIdx.x == 0) {
+        // the shadow ray's direction is the same for every sample: sRay(Vec3R(0), mLightDir) through worldToIndex
+        // (tools/RayTracer.h:1017,1039-1040; Ray ctor defaults t0 = 1e-9, t1 = max, math/Ray.h:57-63)
+        const double jx = p.light[0] * g.inv[0], jy = p.light[1] * g.inv[1], jz = p.light[2] * g.inv[2];
+        const double len = vlength(jx, jy, jz);
+        const double dx = jx / len, dy = jy / len, dz = jz / len;
+        sm.sbase[0] = dx; sm.sbase[1] = dy; sm.sbase[2] = dz;
+        sm.sbase[3] = 1 / dx; sm.sbase[4] = 1 / dy; sm.sbase[5] = 1 / dz;
+        sm.sbase[6] = len * 1e-9; sm.sbase[7] = len * DBL_MAX;
+    }
     __syncthreads();
 
-    TreeCursor accP, accS, accV;        // primary walker, shadow walker, sampler (the reference keeps three accessors too)
-    accP.reset(); accS.reset(); accV.reset();
+    const unsigned lane = threadIdx.x & 31u;
+    const int tid = threadIdx.x;
+    TreeCursor accW, accV;               // walker cursor, sampler cursor (the reference keeps separate accessors too)
+    accW.reset(); accV.reset();
     Counters c = {};
-    // the shadow ray's direction is the same for every sample: sRay(Vec3R(0), mLightDir) through worldToIndex
-    Ray sBase;
-    sBase.ex = sBase.ey = sBase.ez = 0.0;
-    sBase.setDir(p.light[0], p.light[1], p.light[2]);
-    sBase.t0 = 1e-9; sBase.t1 = DBL_MAX;                 // Ray ctor defaults (math/Ray.h:57-63)
-    {
-        const double jx = sBase.dx * g.inv[0], jy = sBase.dy * g.inv[1], jz = sBase.dz * g.inv[2];
-        const double len = vlength(jx, jy, jz);
-        sBase.setDir(jx / len, jy / len, jz / len);
-        sBase.t0 = len * sBase.t0; sBase.t1 = len * sBase.t1;
-    }
+    int mode = kFogIdle, pendExp = 0;
+    bool drained = false;
+    size_t pix = 0;
+    Ray ray; SpanWalk walk;
+    ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0;
+    walk.begin(ray); walk.lvl = -1;
+    walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
+    double tcur = 0.0, tend = 0.0;       // march time / end of the current span of the ACTIVE ray
+    double dens = 0.0;                   // density of the sample waiting for its exp
+    double Tx = 1.0, Ty = 1.0, Tz = 1.0, Lx = 0.0, Ly = 0.0, Lz = 0.0;      // pTrans, pLumi
+    double Sx = 1.0, Sy = 1.0, Sz = 1.0, dTx = 1.0, dTy = 1.0, dTz = 1.0;  // sTrans, dT of the primary sample being lit
 
-    uint32_t px, py; bool valid;
-    while (nextPixel(tm, queue, px, py, valid)) {
-        if (!valid) continue;
-        const size_t pix = size_t(py) * tm.width + px;
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);                    // bg.a = bg.r = bg.g = bg.b = 0 (:1020)
-        Ray pRay;
-        cameraRay(cam, px, py, 0.5, 0.5, pRay);
-        if (COUNT) ++c.rays;
-        worldToIndex(g, pRay);
-        if (clipRay(pRay, g, 1)) {                                       // mPrimary->setWorldRay(pRay) (:1022)
-            double Tx = 1.0, Ty = 1.0, Tz = 1.0, Lx = 0.0, Ly = 0.0, Lz = 0.0;
-            SpanWalker pw; pw.begin(pRay);
-            double a, b;
-            bool done = false;
-            while (!done && pw.template next<COUNT>(g, root, accP, pRay, a, b, c)) {
-                for (double pT = p.pstep * ceil(a / p.pstep); pT <= b; pT += p.pstep) {
-                    // pPos = mPrimary->getWorldPos(pT); density = sampler.wsSample(pPos) (:1034-1035)
-                    double wx = pRay.ex + pRay.dx * pT, wy = pRay.ey + pRay.dy * pT, wz = pRay.ez + pRay.dz * pT;
-                    indexToWorldPos(g, wx, wy, wz);
-                    const double density = boxSampleWorld(g, root, accV, wx, wy, wz);
-                    if (COUNT) ++c.psamples;
-                    if (density < p.cutoff) continue;
-                    const double dTx = exp(p.ext[0] * density * p.pstep), dTy = exp(p.ext[1] * density * p.pstep), dTz = exp(p.ext[2] * density * p.pstep);
-                    double Sx = 1.0, Sy = 1.0, Sz = 1.0;
-                    // sRay.setEye(pPos); mShadow->setWorldRay(sRay) (:1039-1040)
-                    Ray sRay = sBase;
-                    sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
-                    worldToIndexPos(g, sRay.ex, sRay.ey, sRay.ez);
-                    if (COUNT) ++c.srays;
-                    if (!clipRay(sRay, g, 1)) continue;
-                    SpanWalker sw; sw.begin(sRay);
-                    double sa, sb;
-                    bool lit = false;
-                    while (!lit && sw.template next<COUNT>(g, root, accS, sRay, sa, sb, c)) {
-                        for (double sT = p.sstep * ceil(sa / p.sstep); sT <= sb; sT += p.sstep) {
-                            double qx = sRay.ex + sRay.dx * sT, qy = sRay.ey + sRay.dy * sT, qz = sRay.ez + sRay.dz * sT;
-                            indexToWorldPos(g, qx, qy, qz);
-                            const double d = boxSampleWorld(g, root, accV, qx, qy, qz);
-                            if (COUNT) ++c.ssamples;
-                            if (d < p.cutoff) continue;
-                            const double den = 1.0 + sT * p.gain;
-                            Sx *= exp(p.ext[0] * d * p.sstep / den); Sy *= exp(p.ext[1] * d * p.sstep / den); Sz *= exp(p.ext[2] * d * p.sstep / den);
-                            if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) { lit = true; break; }          // goto Luminance
-                        }
-                    }
-                    Lx += p.albedo[0] * Sx * Tx * (1.0 - dTx); Ly += p.albedo[1] * Sy * Ty * (1.0 - dTy); Lz += p.albedo[2] * Sz * Tz * (1.0 - dTz);
-                    Tx *= dTx; Ty *= dTy; Tz *= dTz;
-                    if (Tx * Tx + Ty * Ty + Tz * Tz < p.cutoff) { done = true; break; }                 // goto Pixel
-                }
+    for (;;) {
+        __syncwarp();
+        // (1) a warp takes a fresh 8x4 tile when all its lanes are done
+        const unsigned idle = __ballot_sync(0xffffffffu, mode == kFogIdle);
+        if (idle == 0xffffffffu) {
+            if (drained) break;
+            unsigned item = 0;
+            if (lane == 0) item = atomicAdd(queue, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= tm.items) { drained = true; continue; }
+            uint32_t px, py;
+            if (ticketToPixel(tm, item * 32u + lane, px, py)) {
+                pix = size_t(py) * tm.width + px;
+                cameraRay(cam, px, py, 0.5, 0.5, ray);
+                if (COUNT) ++c.rays;
+                worldToIndex(g, ray);
+                if (clipRay(ray, g, 1)) {                                // mPrimary->setWorldRay(pRay) (:1022)
+                    Tx = Ty = Tz = 1.0; Lx = Ly = Lz = 0.0;
+                    walk.begin(ray); mode = kFogPWalk; pendExp = 0;
+                } else film[pix] = make_float4(0.f, 0.f, 0.f, 0.f);      // bg.a = bg.r = bg.g = bg.b = 0 (:1020), continue
             }
-            out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
-            if (COUNT && out.w > 0.f) ++c.hits;
         }
-        film[pix] = out;
+        __syncwarp();
+        const bool walking = (mode == kFogPWalk || mode == kFogSWalk) && !pendExp;
+        const bool marching = (mode == kFogPMarch || mode == kFogSMarch) && !pendExp;
+        const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
+        const int nE = __popc(__ballot_sync(0xffffffffu, pendExp != 0));
+        const bool runW = nW >= kFogBatch || (nM < kFogBatch && nE < kFogBatch);
+        const bool runM = nM >= kFogBatch || (nW < kFogBatch && nE < kFogBatch);
+        const bool runE = nE >= kFogBatch || (nW < kFogBatch && nM < kFogBatch);
+        bool lum = false, fin = false;
+        // (2) walk: one unit of VolumeHDDA::hits for the active ray
+        if (walking && runW) {
+            double a, b;
+            const int r = walk.template advance<COUNT>(g, root, sm, mode == kFogPWalk ? 0 : 2, accW, ray, a, b, c);
+            if (r == kSpanEmit) {
+                // for (Real pT = pStep*ceil(pTS[k].t0/pStep); pT <= pT1; pT += pStep) (:1030-1032, :1045-1047)
+                const double st = mode == kFogPWalk ? p.pstep : p.sstep;
+                tcur = st * ceil(a / st); tend = b;
+                mode = mode == kFogPWalk ? kFogPMarch : kFogSMarch;
+            } else if (r == kSpanDone) {
+                if (mode == kFogPWalk) fin = true; else lum = true;     // shadow spans exhausted: fall into Luminance
+            }
+        }
+        __syncwarp();
+        // (3) sample: density at the current march time of the active ray
+        if (marching && runM) {
+            if (!(tcur <= tend)) mode = mode == kFogPMarch ? kFogPWalk : kFogSWalk;
+            else {
+                // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
+                double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
+                indexToWorldPos(g, wx, wy, wz);
+                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
+                if (COUNT) { if (mode == kFogPMarch) ++c.psamples; else ++c.ssamples; }
+                if (d < p.cutoff) tcur += mode == kFogPMarch ? p.pstep : p.sstep;      // continue
+                else { dens = d; pendExp = mode == kFogPMarch ? 1 : 2; }
+            }
+        }
+        __syncwarp();
+        // (4) exp: dT = Exp(extinction*density*pStep) (:1037) or sTrans *= Exp(extinction*d*sStep/(1+sT*sGain)) (:1053)
+        if (pendExp && runE) {
+            const bool prim = pendExp == 1;
+            pendExp = 0;
+            const double den = 1.0 + tcur * p.gain;
+            const double ax = prim ? p.ext[0] * dens * p.pstep : p.ext[0] * dens * p.sstep / den;
+            const double ay = prim ? p.ext[1] * dens * p.pstep : p.ext[1] * dens * p.sstep / den;
+            const double az = prim ? p.ext[2] * dens * p.pstep : p.ext[2] * dens * p.sstep / den;
+            const double ex = exp(ax), ey = exp(ay), ez = exp(az);
+            if (prim) {
+                dTx = ex; dTy = ey; dTz = ez;
+                Sx = Sy = Sz = 1.0;
+                // sRay.setEye(pPos); mShadow->setWorldRay(sRay) (:1039-1040)
+                double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
+                indexToWorldPos(g, wx, wy, wz);
+                worldToIndexPos(g, wx, wy, wz);
+                Ray sRay;
+                sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
+                sRay.dx = sm.sbase[0]; sRay.dy = sm.sbase[1]; sRay.dz = sm.sbase[2];
+                sRay.ix = sm.sbase[3]; sRay.iy = sm.sbase[4]; sRay.iz = sm.sbase[5];
+                sRay.t0 = sm.sbase[6]; sRay.t1 = sm.sbase[7];
+                if (COUNT) ++c.srays;
+                if (!clipRay(sRay, g, 1)) tcur += p.pstep;              // `continue`: no luminance for this sample
+                else {
+                    // suspend the primary walk and ray, switch the lane to the shadow ray
+                    sm.park(4, walk.cur);
+                    sm.dt0[tid] = walk.cur.t0; sm.ts0[tid] = walk.ts0; sm.topT1[tid] = walk.topT1; sm.tcur[tid] = tcur; sm.tend[tid] = tend;
+                    sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0);
+                    sm.ray[0][tid] = ray.ex; sm.ray[1][tid] = ray.ey; sm.ray[2][tid] = ray.ez; sm.ray[3][tid] = ray.dx; sm.ray[4][tid] = ray.dy;
+                    sm.ray[5][tid] = ray.dz; sm.ray[6][tid] = ray.ix; sm.ray[7][tid] = ray.iy; sm.ray[8][tid] = ray.iz; sm.ray[9][tid] = ray.t0; sm.ray[10][tid] = ray.t1;
+                    ray = sRay;
+                    walk.begin(ray);
+                    mode = kFogSWalk;
+                }
+            } else {
+                Sx *= ex; Sy *= ey; Sz *= ez;
+                if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) lum = true;                      // goto Luminance (:1054)
+                else tcur += p.sstep;
+            }
+        }
+        // (5) Luminance (:1057-1060): back to the primary ray
+        if (lum) {
+            Lx += p.albedo[0] * Sx * Tx * (1.0 - dTx); Ly += p.albedo[1] * Sy * Ty * (1.0 - dTy); Lz += p.albedo[2] * Sz * Tz * (1.0 - dTz);
+            Tx *= dTx; Ty *= dTy; Tz *= dTz;
+            if (Tx * Tx + Ty * Ty + Tz * Tz < p.cutoff) fin = true;                         // goto Pixel
+            else {
+                sm.unpark(4, walk.cur);
+                walk.cur.t0 = sm.dt0[tid]; walk.ts0 = sm.ts0[tid]; walk.topT1 = sm.topT1[tid]; tend = sm.tend[tid];
+                tcur = sm.tcur[tid] + p.pstep;
+                walk.lvl = (sm.misc[tid] & 255) - 1; walk.needStep = (sm.misc[tid] & 256) != 0; walk.pendLevel = false;
+                ray.ex = sm.ray[0][tid]; ray.ey = sm.ray[1][tid]; ray.ez = sm.ray[2][tid]; ray.dx = sm.ray[3][tid]; ray.dy = sm.ray[4][tid];
+                ray.dz = sm.ray[5][tid]; ray.ix = sm.ray[6][tid]; ray.iy = sm.ray[7][tid]; ray.iz = sm.ray[8][tid]; ray.t0 = sm.ray[9][tid]; ray.t1 = sm.ray[10][tid];
+                mode = kFogPMarch;
+            }
+        }
+        // (6) Pixel (:1063-1067)
+        if (fin) {
+            const float4 out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
+            if (COUNT && out.w > 0.f) ++c.hits;
+            film[pix] = out;
+            mode = kFogIdle; pendExp = 0;
+        }
     }
     if (COUNT) flushCounters(c, counters);
 }
