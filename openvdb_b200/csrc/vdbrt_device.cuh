@@ -528,9 +528,9 @@ template<int THREADS>
 struct FogSmem {
     double t1[5][THREADS], nx[5][THREADS], ny[5][THREADS], nz[5][THREADS];
     int vx[5][THREADS], vy[5][THREADS], vz[5][THREADS];
-    double ray[11][THREADS];          // the primary index-space ray while a shadow ray is active
+    double ray[6][THREADS];           // eye, dir of the primary index-space ray while a shadow ray is active (1/dir is recomputed)
     double dt0[THREADS];              // primary Dda::t0
-    double ts0[THREADS], topT1[THREADS], tcur[THREADS], tend[THREADS];
+    double ts0[THREADS], topT1[THREADS], tcur[THREADS], tend[THREADS], bound[THREADS], c0[THREADS], c1[THREADS];
     int misc[THREADS];                // primary walk: lvl | needStep << 8
     double sbase[8];                  // shadow ray constants shared by the CTA: dir xyz, inv xyz, t0, t1 (index space)
     __device__ __forceinline__ void park(int slot, const Dda& d)
@@ -552,13 +552,14 @@ struct SpanWalk {
     Dda cur;
     double ts0, topT1;     // open span start (<0: none), maxTime of the root-level DDA
     double c0, c1;         // pending child range: ray.setTimes(time(), next()) (DDA.h:252,326)
+    double bound;          // entry time of the last probed cell: while a span is open its end cannot be earlier than this
     int lvl;               // 0 root-level DDA (4096^3), 1 inside an upper node (128^3), 2 inside a lower node (8^3); -1 = finished
     bool needStep, pendLevel;
 
     __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }
     __device__ __forceinline__ void begin(const Ray& ray)
     {
-        lvl = 0; needStep = false; pendLevel = true; ts0 = -1.0; topT1 = ray.t1; c0 = ray.t0; c1 = ray.t1;
+        lvl = 0; needStep = false; pendLevel = true; ts0 = -1.0; topT1 = ray.t1; c0 = ray.t0; c1 = ray.t1; bound = ray.t0;
     }
     // slotBase: first parking slot of this walk's parents (0 primary, 2 shadow)
     template<bool COUNT, class SM>
@@ -583,6 +584,7 @@ struct SpanWalk {
             }
         }
         needStep = true;
+        bound = cur.t0;
         const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
         if (COUNT) { if (lvl == 0) ++c.root; else if (lvl == 1) ++c.upper; else ++c.lower; }
         if (lvl < 2 && depth <= 2 - lvl) {              // child node: walk it

@@ -292,11 +292,16 @@ struct VolParams {
     double ext[3], albedo[3];   // extinction = -scattering-absorption; albedo = lightColor*scattering/(scattering+absorption)
 };
 
-// Per-lane state machine, warp-synchronous like the level-set kernel.  A lane is in one of four modes -- walking the
-// primary HDDA for the next span, marching samples inside a primary span, walking the shadow HDDA, marching shadow
-// samples -- and only ONE walker and ONE ray live in its registers: the suspended primary walk / ray sit in shared memory
+// Per-lane state machine, warp-synchronous like the level-set kernel.  A lane works on its primary ray or on a shadow
+// ray, and only ONE walker and ONE ray live in its registers: the suspended primary walk / ray sit in shared memory
 // while a shadow ray runs.  Each iteration runs the phases  walk | sample | exp  once, each a single site in the code.
-enum { kFogIdle = 0, kFogPWalk = 1, kFogPMarch = 2, kFogSWalk = 3, kFogSMarch = 4 };
+//
+// Lazy spans: the reference first collects every span of the whole chord (VolumeRayIntersector::hits) and then marches
+// them.  Here the walk and the march are interleaved: while a span is still OPEN its end cannot lie before the entry
+// time of the last probed cell (`bound`), so every sample time <= bound is certain to be inside the final span and is
+// taken right away -- same samples, same order, same arithmetic.  A ray that saturates (|T|^2 < cutoff) after a few
+// samples never walks the rest of its chord (for shadow rays inside the fog that is > 90 % of the node probes).
+enum { kFogIdle = 0, kFogPrimary = 1, kFogShadow = 2 };
 constexpr int kFogBatch = 8;             // a phase runs when this many lanes want it, or when the other phases are starved
 
 template<bool COUNT>
@@ -325,13 +330,14 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
     accW.reset(); accV.reset();
     Counters c = {};
     int mode = kFogIdle, pendExp = 0;
+    int span = 0;                        // 0: looking for a span, 1: inside an open span (end >= walk.bound), 2: span closed at tend
     bool drained = false;
     size_t pix = 0;
     Ray ray; SpanWalk walk;
     ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0;
     walk.begin(ray); walk.lvl = -1;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
-    double tcur = 0.0, tend = 0.0;       // march time / end of the current span of the ACTIVE ray
+    double tcur = 0.0, tend = 0.0;       // march time / end of the closed span of the ACTIVE ray
     double dens = 0.0;                   // density of the sample waiting for its exp
     double Tx = 1.0, Ty = 1.0, Tz = 1.0, Lx = 0.0, Ly = 0.0, Lz = 0.0;      // pTrans, pLumi
     double Sx = 1.0, Sy = 1.0, Sz = 1.0, dTx = 1.0, dTy = 1.0, dTz = 1.0;  // sTrans, dT of the primary sample being lit
@@ -354,13 +360,16 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                 worldToIndex(g, ray);
                 if (clipRay(ray, g, 1)) {                                // mPrimary->setWorldRay(pRay) (:1022)
                     Tx = Ty = Tz = 1.0; Lx = Ly = Lz = 0.0;
-                    walk.begin(ray); mode = kFogPWalk; pendExp = 0;
+                    walk.begin(ray); mode = kFogPrimary; pendExp = 0; span = 0;
                 } else film[pix] = make_float4(0.f, 0.f, 0.f, 0.f);      // bg.a = bg.r = bg.g = bg.b = 0 (:1020), continue
             }
         }
         __syncwarp();
-        const bool walking = (mode == kFogPWalk || mode == kFogSWalk) && !pendExp;
-        const bool marching = (mode == kFogPMarch || mode == kFogSMarch) && !pendExp;
+        // for (pT = pStep*ceil(t0/pStep); pT <= pT1; pT += pStep): past the end of a closed span -> look for the next one
+        if (span == 2 && !(tcur <= tend)) span = 0;
+        const bool busy = mode != kFogIdle && !pendExp;
+        const bool marching = busy && (span == 2 || (span == 1 && tcur <= walk.bound && (walk.bound - walk.ts0) > 1e-9));
+        const bool walking = busy && !marching;
         const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
         const int nE = __popc(__ballot_sync(0xffffffffu, pendExp != 0));
         const bool runW = nW >= kFogBatch || (nM < kFogBatch && nE < kFogBatch);
@@ -370,34 +379,33 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
         // (2) walk: one unit of VolumeHDDA::hits for the active ray
         if (walking && runW) {
             double a, b;
-            const int r = walk.template advance<COUNT>(g, root, sm, mode == kFogPWalk ? 0 : 2, accW, ray, a, b, c);
-            if (r == kSpanEmit) {
-                // for (Real pT = pStep*ceil(pTS[k].t0/pStep); pT <= pT1; pT += pStep) (:1030-1032, :1045-1047)
-                const double st = mode == kFogPWalk ? p.pstep : p.sstep;
-                tcur = st * ceil(a / st); tend = b;
-                mode = mode == kFogPWalk ? kFogPMarch : kFogSMarch;
-            } else if (r == kSpanDone) {
-                if (mode == kFogPWalk) fin = true; else lum = true;     // shadow spans exhausted: fall into Luminance
+            const int r = walk.template advance<COUNT>(g, root, sm, mode == kFogPrimary ? 0 : 2, accW, ray, a, b, c);
+            if (r == kSpanEmit) { tend = b; span = 2; }                  // the open span closed at b (valid: b - a > 1e-9)
+            else if (r == kSpanDone) { if (mode == kFogPrimary) fin = true; else lum = true; }   // shadow spans exhausted: Luminance
+            else if (span == 1 && walk.ts0 < 0.0) span = 0;              // it closed, but too short to count (TimeSpan::valid)
+            if (span == 0 && r != kSpanDone && (walk.ts0 >= 0.0 || r == kSpanEmit)) {
+                // a span opened at a: first sample time pStep*ceil(t0/pStep) (:1030-1032, :1045-1047)
+                const double st = mode == kFogPrimary ? p.pstep : p.sstep;
+                const double t0s = r == kSpanEmit ? a : walk.ts0;
+                tcur = st * ceil(t0s / st);
+                span = r == kSpanEmit ? 2 : 1;
             }
         }
         __syncwarp();
         // (3) sample: density at the current march time of the active ray
         if (marching && runM) {
-            if (!(tcur <= tend)) mode = mode == kFogPMarch ? kFogPWalk : kFogSWalk;
-            else {
-                // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
-                double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
-                indexToWorldPos(g, wx, wy, wz);
-                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
-                if (COUNT) { if (mode == kFogPMarch) ++c.psamples; else ++c.ssamples; }
-                if (d < p.cutoff) tcur += mode == kFogPMarch ? p.pstep : p.sstep;      // continue
-                else { dens = d; pendExp = mode == kFogPMarch ? 1 : 2; }
-            }
+            // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
+            double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
+            indexToWorldPos(g, wx, wy, wz);
+            const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
+            if (COUNT) { if (mode == kFogPrimary) ++c.psamples; else ++c.ssamples; }
+            if (d < p.cutoff) tcur += mode == kFogPrimary ? p.pstep : p.sstep;        // continue
+            else { dens = d; pendExp = mode; }
         }
         __syncwarp();
         // (4) exp: dT = Exp(extinction*density*pStep) (:1037) or sTrans *= Exp(extinction*d*sStep/(1+sT*sGain)) (:1053)
         if (pendExp && runE) {
-            const bool prim = pendExp == 1;
+            const bool prim = pendExp == kFogPrimary;
             pendExp = 0;
             const double den = 1.0 + tcur * p.gain;
             const double ax = prim ? p.ext[0] * dens * p.pstep : p.ext[0] * dens * p.sstep / den;
@@ -422,12 +430,13 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                     // suspend the primary walk and ray, switch the lane to the shadow ray
                     sm.park(4, walk.cur);
                     sm.dt0[tid] = walk.cur.t0; sm.ts0[tid] = walk.ts0; sm.topT1[tid] = walk.topT1; sm.tcur[tid] = tcur; sm.tend[tid] = tend;
-                    sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0);
+                    sm.bound[tid] = walk.bound; sm.c0[tid] = walk.c0; sm.c1[tid] = walk.c1;
+                    sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0) | (walk.pendLevel ? 512 : 0) | (span << 12);
                     sm.ray[0][tid] = ray.ex; sm.ray[1][tid] = ray.ey; sm.ray[2][tid] = ray.ez; sm.ray[3][tid] = ray.dx; sm.ray[4][tid] = ray.dy;
-                    sm.ray[5][tid] = ray.dz; sm.ray[6][tid] = ray.ix; sm.ray[7][tid] = ray.iy; sm.ray[8][tid] = ray.iz; sm.ray[9][tid] = ray.t0; sm.ray[10][tid] = ray.t1;
+                    sm.ray[5][tid] = ray.dz;
                     ray = sRay;
                     walk.begin(ray);
-                    mode = kFogSWalk;
+                    mode = kFogShadow; span = 0;
                 }
             } else {
                 Sx *= ex; Sy *= ey; Sz *= ez;
@@ -443,11 +452,13 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
             else {
                 sm.unpark(4, walk.cur);
                 walk.cur.t0 = sm.dt0[tid]; walk.ts0 = sm.ts0[tid]; walk.topT1 = sm.topT1[tid]; tend = sm.tend[tid];
+                walk.bound = sm.bound[tid]; walk.c0 = sm.c0[tid]; walk.c1 = sm.c1[tid];
                 tcur = sm.tcur[tid] + p.pstep;
-                walk.lvl = (sm.misc[tid] & 255) - 1; walk.needStep = (sm.misc[tid] & 256) != 0; walk.pendLevel = false;
+                const int m = sm.misc[tid];
+                walk.lvl = (m & 255) - 1; walk.needStep = (m & 256) != 0; walk.pendLevel = (m & 512) != 0; span = m >> 12;
                 ray.ex = sm.ray[0][tid]; ray.ey = sm.ray[1][tid]; ray.ez = sm.ray[2][tid]; ray.dx = sm.ray[3][tid]; ray.dy = sm.ray[4][tid];
-                ray.dz = sm.ray[5][tid]; ray.ix = sm.ray[6][tid]; ray.iy = sm.ray[7][tid]; ray.iz = sm.ray[8][tid]; ray.t0 = sm.ray[9][tid]; ray.t1 = sm.ray[10][tid];
-                mode = kFogPMarch;
+                ray.setDir(ray.dx, ray.dy, sm.ray[5][tid]);          // invDir = 1/dir, the same division as at ray set-up
+                mode = kFogPrimary;
             }
         }
         // (6) Pixel (:1063-1067)
