@@ -403,16 +403,18 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;      // scratch film, discarded
     CUDA_TRY(cudaMemsetAsync(ctx->io, 0, npx * 16, ctx->stream));
     unsigned long long* dC = reinterpret_cast<unsigned long long*>(ctx->scratch + 128);
-    CUDA_TRY(cudaMemsetAsync(dC, 0, 10 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dC, 0, 16 * sizeof(unsigned long long), ctx->stream));
     vdbrt_film film = {}; film.width = cam->width; film.height = cam->height;
     vdbrt_shader sh = {}; sh.kind = VDBRT_SHADER_DIFFUSE; sh.rgba[0] = sh.rgba[1] = sh.rgba[2] = sh.rgba[3] = 1.f;
     AuxOut a = {};
     if (int rc = launchLevelSet(ctx, grid, cam, &sh, opts, &film, static_cast<float4*>(ctx->io), a, false, dC)) return rc;
-    unsigned long long h[10];
+    unsigned long long h[16];
     CUDA_TRY(cudaMemcpyAsync(h, dC, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     out->rays = h[0]; out->root_probes = h[1]; out->upper_probes = h[2]; out->lower_probes = h[3]; out->voxel_probes = h[4];
     out->stencil_refills = h[5]; out->primary_samples = h[6]; out->shadow_samples = h[7]; out->shadow_rays = h[8]; out->hits = h[9];
+    if (std::getenv("VDBRT_DEBUG_TILES"))
+        std::fprintf(stderr, "[vdbrt] tiles %llu: max cycles %llu, max iterations %llu, mean cycles %.0f\n", h[13], h[10], h[11], h[13] ? double(h[12]) / double(h[13]) : 0.0);
     return VDBRT_OK;
 }
 

@@ -128,18 +128,22 @@ struct TreeCursor {
             }
             n1 = 0u;
             if (n2) {
+                // the child-mask word and the table entry are fetched together (two independent loads, one latency); the
+                // entry is only a child offset -- relative to this InternalData (:3190-3199) -- when the mask bit is set
                 const uint8_t* u = node(g, n2);
                 const uint32_t n = upperOffset(x, y, z);
-                if (maskBit(u + kUpperCMask, n))      // child offset is relative to this InternalData (:3190-3199)
-                    n1 = uint32_t((((unsigned long long)n2 << 5) + (unsigned long long)ldgs64(u + kUpperTable + 8u * n)) >> 5);
+                const unsigned long long word = ldg64(u + kUpperCMask + 8u * (n >> 6));
+                const long long ent = ldgs64(u + kUpperTable + 8u * n);
+                if ((word >> (n & 63u)) & 1ull) n1 = uint32_t((((unsigned long long)n2 << 5) + (unsigned long long)ent) >> 5);
             }
         }
         n0 = 0u;
         if (n1) {
             const uint8_t* l = node(g, n1);
             const uint32_t n = lowerOffset(x, y, z);
-            if (maskBit(l + kLowerCMask, n))
-                n0 = uint32_t((((unsigned long long)n1 << 5) + (unsigned long long)ldgs64(l + kLowerTable + 8u * n)) >> 5);
+            const unsigned long long word = ldg64(l + kLowerCMask + 8u * (n >> 6));
+            const long long ent = ldgs64(l + kLowerTable + 8u * n);
+            if ((word >> (n & 63u)) & 1ull) n0 = uint32_t((((unsigned long long)n1 << 5) + (unsigned long long)ent) >> 5);
         }
         kx = x; ky = y; kz = z;
         return n0 ? 0 : (n1 ? 1 : (n2 ? 2 : 3));
