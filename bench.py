@@ -30,15 +30,28 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (major, minor, width, height)
+    # name: (major, minor, width, height)  -- level-set torus
     "c2": (650.0, 325.0, 1920, 1080),
     "c2-small": (160.0, 80.0, 640, 360),     # quick functional check, not a bench line
+    # BASELINE config 4: union of 10 000 random spheres (~1 B active voxels, ~12 GB grid replicated per GPU), 3840x2160;
+    # (n spheres, extent) in place of the radii; camera at (0, 0, 3*2048)
+    "c4": (10000, 1988.0, 3840, 2160),
+    "c4-small": (300, 600.0, 1280, 720),
 }
 TILE_W, TILE_H = 64, 60
 
 
-def camera_args(R, r):
+def camera_args(R, r, workload="c2"):
+    if workload.startswith("c4"):
+        return (0.0, 0.0, 3.0 * (r + 60.0)), (0.0, 0.0, 0.0)     # r = extent of the sphere centres; 3*2048 for the full set
     return (0.0, 1.5 * R, 3.0 * (R + r)), (0.0, 0.0, 0.0)
+
+
+def build_grid(ctx, api, workload):
+    R, r, _, _ = WORKLOADS[workload]
+    if workload.startswith("c4"):
+        return ctx.build_spheres(api.random_spheres(int(R), 20240607, r, 10.0, 60.0))
+    return ctx.build_torus(R, r)
 
 
 class ClockSampler:
@@ -149,6 +162,41 @@ def cpu_reference(R, r, W, H, steps, warmup, sample_div=4):
             "ms_per_sample": t * 1e3}
 
 
+def extras(ctx, api, abi, torch):
+    """informational timings of the other BASELINE configs (device-resident film, CUDA-event kernel time, 3 frames each):
+    C3 fog sphere (1024^3 bbox, step 0.5, 1920x1080) and C4 union of 10 000 spheres at 3840x2160 ('ms per 4K frame')"""
+    out = {}
+    ls = ctx.build_sphere(509.0)
+    fog = ctx.build_fog(ls)
+    ls.free()
+    W, H = 1920, 1080
+    cam = api.vdb_render_camera(W, H, (0.0, 0.0, 3 * 509.0), (0.0, 0.0, 0.0))
+    vo = api.vol_opts_default()
+    vo.primary_step = 0.5
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    ms = []
+    for _ in range(4):
+        ctx.render_volume(fog, cam, vo, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE)
+        ms.append(ctx.last_kernel_ms()[0])
+    out["c3_fog_1080p"] = {"ms_per_frame": float(np.median(ms[1:])), "Mrays_per_s": W * H / float(np.median(ms[1:])) / 1e3,
+                           "grid_gb": fog.info.bytes / 1e9, "alpha_sum": float(film[..., 3].sum().item())}
+    fog.free()
+    g = ctx.build_spheres(api.random_spheres(10000, 20240607, 1988.0, 10.0, 60.0))
+    W, H = 3840, 2160
+    cam = api.vdb_render_camera(W, H, (0.0, 0.0, 3 * 2048.0), (0.0, 0.0, 0.0))
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    opts = ctx.ls_opts(uniform_bg=True)
+    ms = []
+    for _ in range(4):
+        ctx.render_levelset(g, cam, api.make_shader(abi.SHADER_DIFFUSE), film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, opts=opts)
+        ms.append(ctx.last_kernel_ms()[0])
+    out["c4_levelset_4k"] = {"ms_per_frame": float(np.median(ms[1:])), "Mrays_per_s": W * H / float(np.median(ms[1:])) / 1e3,
+                             "grid_gb": g.info.bytes / 1e9, "active_voxels": int(g.info.active_voxels),
+                             "hit_pixels": int((film[..., :3].sum(dim=2) > 0).sum().item())}
+    g.free()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,6 +220,7 @@ def main():
     ap.add_argument("--impl", default="vdbrt", choices=["vdbrt", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational fog (C3) and 4K (C4) timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -191,7 +240,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
     R, r, W, H = WORKLOADS[args.workload]
-    tr, look = camera_args(R, r)
+    tr, look = camera_args(R, r, args.workload)
 
     ctx = api.Context(local)
     # one non-default torch stream carries the library's kernels, torch's copies, NCCL and the timing events
@@ -200,7 +249,7 @@ def main():
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
-    grid = ctx.build_torus(R, r)                       # replicated on every GPU
+    grid = build_grid(ctx, api, args.workload)         # replicated on every GPU
     build_s = time.perf_counter() - t0
     cam = api.vdb_render_camera(W, H, tr, look)
     sh = api.make_shader(abi.SHADER_DIFFUSE)
@@ -293,7 +342,7 @@ def main():
         achieved = bpr * rays_per_launch / (kernel_ms_max * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_levelset_c2_dram_bytes.json")
-        if os.path.exists(tpath) and world == 1 and args.workload == "c2":
+        if os.path.exists(tpath) and world == 1 and args.workload == "c2":  # ncu capture of exactly this workload
             try:
                 traffic = json.load(open(tpath))["dram_bytes_per_launch"]
             except Exception:
@@ -302,8 +351,9 @@ def main():
             "metric": "primary Mrays/s, level-set ray tracer", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": level-set torus R=%g r=%g voxel 1 hw 3 (%d active voxels, %.2f GB grid, GPU-built in %.2f s), "
-                                   "%dx%d, 1 spp, DiffuseShader, perspective camera" % (R, r, grid.info.active_voxels, grid.info.bytes / 1e9, build_s, W, H),
+            "config": {"workload": args.workload + (": union of %d level-set spheres" % int(R) if args.workload.startswith("c4") else ": level-set torus R=%g r=%g" % (R, r))
+                                   + " voxel 1 hw 3 (%d active voxels, %.2f GB grid, GPU-built in %.2f s), %dx%d, 1 spp, DiffuseShader, perspective camera"
+                                   % (grid.info.active_voxels, grid.info.bytes / 1e9, build_s, W, H),
                        "partition": "%d GPU(s), %dx%d tiles interleaved, NCCL gather to rank 0" % (world, TILE_W, TILE_H) if world > 1 else "single GPU",
                        "l2": "grid (%.2f GB) is larger than the 126 MB L2; no explicit flush" % (grid.info.bytes / 1e9),
                        "hit_pixels": hits},
@@ -315,7 +365,12 @@ def main():
                          "algorithmic_bytes_per_ray": bpr, "rays_per_launch": rays_per_launch, "counters": counters},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_extras and world == 1 and args.workload == "c2":
+            try:
+                line["extras"] = extras(ctx, api, abi, torch)
+            except Exception as e:
+                line["extras"] = {"error": str(e)}
+        if not args.no_cpu_baseline and world == 1 and not args.workload.startswith("c4"):
             try:
                 line["cpu_baseline"] = cpu_reference(R, r, W, H, 3, 1)
             except Exception as e:  # the checker is optional for the product arm

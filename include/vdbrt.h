@@ -247,6 +247,9 @@ int  vdbrt_build_levelset_torus(vdbrt_ctx* ctx, double major_radius, double mino
 /* union (voxel-wise min, tools/Composite.h:886) of n spheres: spheres[i] = {cx,cy,cz,r} in world units          */
 int  vdbrt_build_levelset_spheres(vdbrt_ctx* ctx, const double* spheres, uint32_t n, double voxel_size,
                                   double half_width, vdbrt_grid** out);
+/* the sphere set of BASELINE configs 4/5: std::mt19937_64 rng(seed); per sphere, in this order, cx,cy,cz ~
+ * U(-extent,extent) and r ~ U(rmin,rmax) drawn with std::uniform_real_distribution<double>; out = n x {cx,cy,cz,r}           */
+int  vdbrt_random_spheres(uint64_t seed, uint32_t n, double extent, double rmin, double rmax, double* out);
 /* sdfToFogVolume of an existing level-set grid (cutoff = background)                                            */
 int  vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* levelset, vdbrt_grid** out);
 

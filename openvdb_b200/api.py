@@ -22,7 +22,7 @@ SYMBOLS = [
     "vdbrt_jitter_table", "vdbrt_vol_opts_default", "vdbrt_render_levelset", "vdbrt_render_volume",
     "vdbrt_intersect_levelset", "vdbrt_volume_spans", "vdbrt_count_levelset", "vdbrt_count_volume",
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
-    "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset",
+    "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
     L.vdbrt_build_levelset_torus.argtypes = [vp, dbl, dbl, P(dbl), dbl, dbl, P(vp)]
     L.vdbrt_build_levelset_spheres.argtypes = [vp, vp, u32, dbl, dbl, P(vp)]
     L.vdbrt_build_fog_from_levelset.argtypes = [vp, vp, P(vp)]
+    L.vdbrt_random_spheres.argtypes = [u64, u32, dbl, dbl, dbl, vp]
     _lib = L
     return L
 
@@ -303,3 +304,10 @@ class Context:
         ms, n = C.c_float(), C.c_uint32()
         _check(self.L.vdbrt_last_kernel_ms(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def random_spheres(n=10000, seed=20240607, extent=1988.0, rmin=10.0, rmax=60.0):
+    """the sphere set of BASELINE configs 4/5: n x (cx, cy, cz, r)"""
+    out = np.zeros((n, 4), np.float64)
+    _check(load_library().vdbrt_random_spheres(seed, n, extent, rmin, rmax, out.ctypes.data))
+    return out

@@ -159,6 +159,16 @@ int vdbrt_jitter_table(unsigned int seed, double out[16])
     return VDBRT_OK;
 }
 
+// sphere set of BASELINE configs 4/5
+int vdbrt_random_spheres(uint64_t seed, uint32_t n, double extent, double rmin, double rmax, double* out)
+{
+    if (!out) return vdbrt::setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> pos(-extent, extent), rad(rmin, rmax);
+    for (uint32_t s = 0; s < n; ++s) { out[4 * s] = pos(rng); out[4 * s + 1] = pos(rng); out[4 * s + 2] = pos(rng); out[4 * s + 3] = rad(rng); }
+    return VDBRT_OK;
+}
+
 // VolumeRender ctor defaults (tools/RayTracer.h:929-936)
 int vdbrt_vol_opts_default(vdbrt_vol_opts* o)
 {
