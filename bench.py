@@ -114,7 +114,7 @@ def bytes_per_ray(c):
             + 32 * c["stencil_refills"]) / n + 16.0
 
 
-def cpu_reference(R, r, W, H, steps, warmup, sample_div=4):
+def cpu_reference(R, r, W, H, steps, warmup, sample_div=1):
     """the reference's own CPU implementation (oracle/_ref: unmodified OpenVDB LevelSetRayTracer, threaded) on a bounded
     sample of the workload: the same grid and camera at (W/div) x (H/div) pixels.  Falls back to the oracle port."""
     from tests import refapi

@@ -414,7 +414,8 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     out->rays = h[0]; out->root_probes = h[1]; out->upper_probes = h[2]; out->lower_probes = h[3]; out->voxel_probes = h[4];
     out->stencil_refills = h[5]; out->primary_samples = h[6]; out->shadow_samples = h[7]; out->shadow_rays = h[8]; out->hits = h[9];
     if (std::getenv("VDBRT_DEBUG_TILES"))
-        std::fprintf(stderr, "[vdbrt] tiles %llu: max cycles %llu, max iterations %llu, mean cycles %.0f\n", h[13], h[10], h[11], h[13] ? double(h[12]) / double(h[13]) : 0.0);
+        std::fprintf(stderr, "[vdbrt] tiles %llu: max cycles %llu, max iterations %llu, mean cycles %.0f; %llu tiles > 1.5M cycles with mean active lanes %.2f\n", h[13], h[10], h[11],
+                     h[13] ? double(h[12]) / double(h[13]) : 0.0, h[14], h[14] ? double(h[15]) / 100.0 / double(h[14]) : 0.0);
     return VDBRT_OK;
 }
 

@@ -130,16 +130,19 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
 
-    long long tileStart = 0; unsigned long long tileIters = 0;
+    long long tileStart = 0; unsigned long long tileIters = 0, tileActive = 0;
     for (;;) {
         __syncwarp();
-        if (COUNT) ++tileIters;
+        if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
         // (1) refill idle lanes from the queue
         const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
         if (COUNT && idle == 0xffffffffu && lane == 0) {
             const long long now = clock64();
-            if (tileStart) { atomicMax(counters + 10, (unsigned long long)(now - tileStart)); atomicMax(counters + 11, tileIters); atomicAdd(counters + 12, (unsigned long long)(now - tileStart)); atomicAdd(counters + 13, 1ull); }
-            tileStart = now; tileIters = 0;
+            if (tileStart) {
+                atomicMax(counters + 10, (unsigned long long)(now - tileStart)); atomicMax(counters + 11, tileIters); atomicAdd(counters + 12, (unsigned long long)(now - tileStart)); atomicAdd(counters + 13, 1ull);
+                if (now - tileStart > 1500000) { atomicAdd(counters + 14, 1ull); atomicAdd(counters + 15, tileActive * 100ull / (tileIters ? tileIters : 1)); }
+            }
+            tileStart = now; tileIters = 0; tileActive = 0;
         }
         if (idle == 0xffffffffu && drained) break;
         if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillThreshold)) {
