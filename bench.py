@@ -114,7 +114,7 @@ def bytes_per_ray(c):
             + 32 * c["stencil_refills"]) / n + 16.0
 
 
-def cpu_reference(R, r, W, H, steps, warmup, sample_div=1):
+def cpu_reference(R, r, W, H, steps, warmup, sample_div=1, gpu_film=None):
     """the reference's own CPU implementation (oracle/_ref: unmodified OpenVDB LevelSetRayTracer, threaded) on a bounded
     sample of the workload: the same grid and camera at (W/div) x (H/div) pixels.  Falls back to the oracle port."""
     from tests import refapi
@@ -156,7 +156,12 @@ def cpu_reference(R, r, W, H, steps, warmup, sample_div=1):
         kind = "port"
         hits = int((film[..., :3].sum(axis=2) > 0).sum())
     t = float(np.median(times))
-    return {"value": w * h / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+    parity = None
+    if gpu_film is not None and gpu_film.shape == film.shape:
+        # the checker's frame against the GPU's frame of the same workload (both start from a (0,0,0,1) film)
+        bad = int((gpu_film != film).any(axis=2).sum())
+        parity = {"against": kind, "pixels": int(w * h), "mismatched_pixels": bad, "max_abs_diff": float(np.abs(gpu_film - film).max())}
+    return {"value": w * h / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind, "parity": parity,
             "sample": "%dx%d pixels of the same torus/camera (1/%d of the frame's rays), median of %d runs after %d warm-up, %d hit pixels"
                       % (w, h, sample_div * sample_div, steps, warmup, hits),
             "ms_per_sample": t * 1e3}
@@ -372,7 +377,7 @@ def main():
                 line["extras"] = {"error": str(e)}
         if not args.no_cpu_baseline and world == 1 and not args.workload.startswith("c4"):
             try:
-                line["cpu_baseline"] = cpu_reference(R, r, W, H, 3, 1)
+                line["cpu_baseline"] = cpu_reference(R, r, W, H, 3, 1, gpu_film=host.array.copy())
             except Exception as e:  # the checker is optional for the product arm
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
         print(json.dumps(line))

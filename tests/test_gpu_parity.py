@@ -304,3 +304,44 @@ def test_work_counters_match_oracle(ctx, oracle, dsphere, sphere100):
         assert c[k] == o[k], k
     # the GPU starts every ray with a cold stencil, the CPU keeps it across pixels: refills differ by < 1 %
     assert abs(c["stencil_refills"] - o["stencil_refills"]) < 0.01 * o["stencil_refills"]
+
+
+def test_config2_full_size_vs_oracle(ctx, oracle):
+    """BASELINE config 2 at full size: GPU-built torus R=650 r=325 (50 M active voxels, 0.58 GB), 1920x1080, Diffuse and Normal.
+    Every pixel's hit flag, first-hit voxel, time, position, normal and colour must equal the oracle's bit for bit."""
+    g = ctx.build_torus(650.0, 325.0)
+    assert g.info.active_voxels == 50038096 and g.info.leaf_count == 257488
+    og = oracle.open(g.download())
+    W, H = 1920, 1080
+    cam = api.vdb_render_camera(W, H, (0.0, 1.5 * 650, 3.0 * (650 + 325)), (0, 0, 0))
+    threads = os.cpu_count() or 4
+    for kind in (abi.SHADER_DIFFUSE, abi.SHADER_NORMAL):
+        film, aux = gpu_levelset(ctx, g, cam, api.make_shader(kind), W, H)
+        ofilm = refapi.new_film(W, H)
+        oaux, _ = oracle.render_levelset(og, cam, api.make_shader(kind), ofilm, aux=True, threads=threads)
+        assert int(aux.hit.sum()) == 1064534
+        assert_records_equal(aux, oaux)
+        assert np.array_equal(film, ofilm)
+    g.free()
+
+
+def test_config3_fog_vs_oracle(ctx, oracle):
+    """BASELINE config 3 grid (fog sphere r=509 in a 1024^3 box, GPU-built, 0.19 GB) at a quarter of the resolution per axis:
+    alpha>0 mask exact, colours within tolerance (measured: bit-identical)"""
+    ls = ctx.build_sphere(509.0)
+    fog = ctx.build_fog(ls)
+    ls.free()
+    og = oracle.open(fog.download())
+    W, H = 480, 270
+    cam = api.vdb_render_camera(W, H, (0.0, 0.0, 3 * 509.0), (0, 0, 0))
+    vo = api.vol_opts_default()
+    vo.primary_step = 0.5
+    film = refapi.new_film(W, H)
+    ctx.render_volume(fog, cam, vo, film)
+    ofilm = refapi.new_film(W, H)
+    oracle.render_volume(og, cam, vo, ofilm, threads=os.cpu_count() or 4)
+    assert (film[..., 3] > 0).sum() > 50000
+    assert np.array_equal(film[..., 3] > 0, ofilm[..., 3] > 0)
+    assert np.allclose(film, ofilm, rtol=RTOL, atol=ATOL)
+    print("C3 fog: %.5f%% pixels not bit-identical" % (100.0 * float((film != ofilm).any(axis=2).mean())))
+    fog.free()
