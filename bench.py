@@ -226,6 +226,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational fog (C3) and 4K (C4) timings")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU frame assembly: render kernels store their tiles straight into rank 0's film over NVLink "
+                         "(CUDA IPC mapping), or pack + NCCL gather + unpack")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -264,14 +267,29 @@ def main():
     opts = ctx.ls_opts(part=part, uniform_bg=True)
     opts.flags |= abi.ASYNC
 
-    # multi-GPU frame assembly (openvdb_b200/frame.py): rank r owns tiles r, r+world, ...; one gather per frame
+    # multi-GPU frame assembly.  "peer": every rank's render kernel stores the tiles it owns straight into rank 0's film (CUDA IPC
+    # mapping, NVLink peer stores) and a 4-byte all-reduce orders the streams -- compute and gather are one kernel.  "nccl":
+    # openvdb_b200/frame.py packs the owned tiles, gathers them with one NCCL collective and unpacks on rank 0.
     from openvdb_b200.frame import TileGather
-    gather = TileGather(H, W, TILE_H, TILE_W, rank, world, "cuda") if world > 1 else None
+    peer = world > 1 and args.gather == "peer"
+    gather = TileGather(H, W, TILE_H, TILE_W, rank, world, "cuda") if (world > 1 and not peer) else None
+    token = torch.zeros(1, dtype=torch.float32, device="cuda")
+    film_ptr = film.data_ptr()
+    shared = None
+    if peer:
+        def exchange(h):
+            t = torch.from_numpy(h.copy()).cuda()
+            dist.broadcast(t, src=0)
+            return t.cpu().numpy()
+        shared = api.SharedFilm(ctx, H, W, rank, exchange)
+        film_ptr = shared.ptr
 
     def step():
-        ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
+        ctx.render_levelset(grid, cam, sh, film_ptr, width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
         if gather:
             gather.gather(film)
+        elif peer:
+            dist.all_reduce(token)          # stream-ordered: rank 0 continues only after every rank's kernel has stored its tiles
 
     def barrier():
         torch.cuda.synchronize()
@@ -289,10 +307,12 @@ def main():
           for _ in range(args.steps)]
     for k in range(args.steps):
         ev[k][0].record(stream)
-        ctx.render_levelset(grid, cam, sh, film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
+        ctx.render_levelset(grid, cam, sh, film_ptr, width=W, height=H, memspace=abi.MEM_DEVICE, bg=bg, opts=opts)
         ev[k][1].record(stream)
         if gather:
             gather.gather(film)
+        elif peer:
+            dist.all_reduce(token)
         ev[k][2].record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -304,6 +324,8 @@ def main():
     total_ms, kernel_ms_max = float(tt[0]), float(tt[1])
     rays = W * H
     value = rays * args.steps / (total_ms * 1e-3) / 1e6
+    if peer and rank == 0:
+        api.memcpy(ctx, film.data_ptr(), shared.ptr, H * W * 16, 2)
     hits = int((film[..., :3].sum(dim=2) > 0).sum().item()) if rank == 0 else 0
 
     # ---- e2e: the call a user makes, host film in pinned memory, copies inside the timed region
@@ -315,6 +337,17 @@ def main():
     def e2e_step():
         if world == 1:
             ctx.render_levelset(grid, cam, sh, host.array, opts=opts_sync)       # H2D film + kernel + D2H film
+        elif peer:
+            if rank == 0:
+                api.memcpy(ctx, shared.ptr, host.array.ctypes.data, film_bytes, 0)      # H2D of this step's film into the shared film
+            dist.all_reduce(token)                                                   # peers start after the film is in place
+            step_opts = ctx.ls_opts(part=part)
+            step_opts.flags |= abi.ASYNC
+            ctx.render_levelset(grid, cam, sh, shared.ptr, width=W, height=H, memspace=abi.MEM_DEVICE, opts=step_opts)
+            dist.all_reduce(token)
+            if rank == 0:
+                api.memcpy(ctx, host.array.ctypes.data, shared.ptr, film_bytes, 1)      # D2H of the finished frame
+            torch.cuda.synchronize()
         else:
             film.copy_(torch.from_numpy(host.array), non_blocking=True)          # H2D of this step's film
             step_opts = ctx.ls_opts(part=part)
@@ -359,7 +392,9 @@ def main():
             "config": {"workload": args.workload + (": union of %d level-set spheres" % int(R) if args.workload.startswith("c4") else ": level-set torus R=%g r=%g" % (R, r))
                                    + " voxel 1 hw 3 (%d active voxels, %.2f GB grid, GPU-built in %.2f s), %dx%d, 1 spp, DiffuseShader, perspective camera"
                                    % (grid.info.active_voxels, grid.info.bytes / 1e9, build_s, W, H),
-                       "partition": "%d GPU(s), %dx%d tiles interleaved, NCCL gather to rank 0" % (world, TILE_W, TILE_H) if world > 1 else "single GPU",
+                       "partition": ("%d GPU(s), %dx%d tiles interleaved, " % (world, TILE_W, TILE_H)
+                                     + ("render kernels store straight into rank 0's film over NVLink (CUDA IPC)" if peer else "NCCL gather to rank 0"))
+                       if world > 1 else "single GPU",
                        "l2": "grid (%.2f GB) is larger than the 126 MB L2; no explicit flush" % (grid.info.bytes / 1e9),
                        "hit_pixels": hits},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": film_bytes, "d2h_bytes_per_step": film_bytes,

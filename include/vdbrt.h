@@ -185,6 +185,19 @@ int  vdbrt_synchronize(vdbrt_ctx* ctx);
 int  vdbrt_host_alloc(size_t bytes, void** out);         /* pinned host memory (cuda::DeviceBuffer semantics,   */
 int  vdbrt_host_free(void* p);                           /*  nanovdb/cuda/DeviceBuffer.h:316-344)               */
 
+/* Device buffers that can be shared between the processes of one node (one process per GPU): rank 0 allocates its film with
+ * vdbrt_device_alloc, exports it, every other rank imports the handle and renders the tiles it owns STRAIGHT INTO rank 0's
+ * film over NVLink (peer stores from the render kernel) -- the frame gather of SURVEY 8e without a separate collective.
+ * Thin wrappers of cudaMalloc / cudaIpcGetMemHandle / cudaIpcOpenMemHandle(cudaIpcMemLazyEnablePeerAccess).                  */
+#define VDBRT_IPC_HANDLE_BYTES 64
+int  vdbrt_device_alloc(vdbrt_ctx* ctx, size_t bytes, void** out);
+int  vdbrt_device_free(vdbrt_ctx* ctx, void* p);
+int  vdbrt_ipc_export(vdbrt_ctx* ctx, const void* device_ptr, unsigned char handle[VDBRT_IPC_HANDLE_BYTES]);
+int  vdbrt_ipc_import(vdbrt_ctx* ctx, const unsigned char handle[VDBRT_IPC_HANDLE_BYTES], void** device_ptr);
+int  vdbrt_ipc_close(vdbrt_ctx* ctx, void* device_ptr);
+/* cudaMemcpyAsync on the context's stream; kind: 0 host->device, 1 device->host, 2 device->device                            */
+int  vdbrt_memcpy(vdbrt_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
+
 /* ---- grids ------------------------------------------------------------------------------------------------
  * replaces nanovdb::GridHandle<cuda::DeviceBuffer>::deviceUpload (nanovdb/cuda/DeviceBuffer.h:411-456) plus the
  * constructor-time work of LinearSearchImpl / VolumeRayIntersector (validation, node-granular bbox:

@@ -23,6 +23,7 @@ SYMBOLS = [
     "vdbrt_intersect_levelset", "vdbrt_volume_spans", "vdbrt_count_levelset", "vdbrt_count_volume",
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
+    "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
 ]
 
 
@@ -78,6 +79,12 @@ def load_library():
     L.vdbrt_build_levelset_spheres.argtypes = [vp, vp, u32, dbl, dbl, P(vp)]
     L.vdbrt_build_fog_from_levelset.argtypes = [vp, vp, P(vp)]
     L.vdbrt_random_spheres.argtypes = [u64, u32, dbl, dbl, dbl, vp]
+    L.vdbrt_device_alloc.argtypes = [vp, C.c_size_t, P(vp)]
+    L.vdbrt_device_free.argtypes = [vp, vp]
+    L.vdbrt_ipc_export.argtypes = [vp, vp, vp]
+    L.vdbrt_ipc_import.argtypes = [vp, vp, P(vp)]
+    L.vdbrt_ipc_close.argtypes = [vp, vp]
+    L.vdbrt_memcpy.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
     _lib = L
     return L
 
@@ -311,3 +318,33 @@ def random_spheres(n=10000, seed=20240607, extent=1988.0, rmin=10.0, rmax=60.0):
     out = np.zeros((n, 4), np.float64)
     _check(load_library().vdbrt_random_spheres(seed, n, extent, rmin, rmax, out.ctypes.data))
     return out
+
+
+class SharedFilm:
+    """A device film that every rank of one node can write: rank 0 owns it (vdbrt_device_alloc), the other ranks map it through
+    a CUDA IPC handle and render their tiles straight into it over NVLink.  `exchange` broadcasts the 64-byte handle."""
+
+    def __init__(self, ctx, height, width, rank, exchange):
+        self.ctx, self.rank, self.nbytes = ctx, rank, height * width * 16
+        handle = np.zeros(64, np.uint8)
+        p = C.c_void_p()
+        if rank == 0:
+            _check(ctx.L.vdbrt_device_alloc(ctx.handle, self.nbytes, C.byref(p)))
+            _check(ctx.L.vdbrt_ipc_export(ctx.handle, p, handle.ctypes.data))
+        handle = exchange(handle)
+        if rank != 0:
+            _check(ctx.L.vdbrt_ipc_import(ctx.handle, handle.ctypes.data, C.byref(p)))
+        self.ptr = p.value
+
+    def close(self):
+        if self.ptr:
+            if self.rank == 0:
+                self.ctx.L.vdbrt_device_free(self.ctx.handle, self.ptr)
+            else:
+                self.ctx.L.vdbrt_ipc_close(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+
+def memcpy(ctx, dst, src, nbytes, kind):
+    """async copy on the context's stream; kind 0 H2D, 1 D2H, 2 D2D"""
+    _check(ctx.L.vdbrt_memcpy(ctx.handle, dst, src, nbytes, kind))

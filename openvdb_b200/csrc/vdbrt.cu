@@ -257,6 +257,56 @@ int vdbrt_host_alloc(size_t bytes, void** out)
 }
 int vdbrt_host_free(void* p) { CUDA_TRY(cudaFreeHost(p)); return VDBRT_OK; }
 
+int vdbrt_device_alloc(vdbrt_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaMalloc(out, bytes));
+    return VDBRT_OK;
+}
+int vdbrt_device_free(vdbrt_ctx* ctx, void* p)
+{
+    if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaFree(p));
+    return VDBRT_OK;
+}
+int vdbrt_ipc_export(vdbrt_ctx* ctx, const void* devicePtr, unsigned char handle[VDBRT_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !devicePtr || !handle) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VDBRT_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(devicePtr)));
+    std::memcpy(handle, &h, sizeof(h));
+    return VDBRT_OK;
+}
+int vdbrt_ipc_import(vdbrt_ctx* ctx, const unsigned char handle[VDBRT_IPC_HANDLE_BYTES], void** devicePtr)
+{
+    if (!ctx || !devicePtr || !handle) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(devicePtr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VDBRT_OK;
+}
+int vdbrt_ipc_close(vdbrt_ctx* ctx, void* devicePtr)
+{
+    if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaIpcCloseMemHandle(devicePtr));
+    return VDBRT_OK;
+}
+
+int vdbrt_memcpy(vdbrt_ctx* ctx, void* dst, const void* src, size_t bytes, int kind)
+{
+    if (!ctx || !dst || !src) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(ctx->device);
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    return VDBRT_OK;
+}
+
 int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out)
 {
     if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
