@@ -345,3 +345,57 @@ def test_config3_fog_vs_oracle(ctx, oracle):
     assert np.allclose(film, ofilm, rtol=RTOL, atol=ATOL)
     print("C3 fog: %.5f%% pixels not bit-identical" % (100.0 * float((film != ofilm).any(axis=2).mean())))
     fog.free()
+
+
+def test_many_root_tiles_fall_back_to_global_table(ctx, oracle):
+    """more root tiles than fit the shared-memory staging area (96): the kernels search the table in global memory instead"""
+    rng = np.random.default_rng(7)
+    n = 260
+    s = np.column_stack([rng.uniform(-9000, 9000, (n, 3)), rng.uniform(12, 30, n)])
+    s[0] = (0.0, 0.0, 0.0, 40.0)
+    g = ctx.build_spheres(s)
+    assert g.info.root_tiles > 96
+    og = oracle.open(g.download())
+    W, H = 160, 120
+    cam = api.vdb_render_camera(W, H, (3000.0, 2000.0, 30000.0), (0, 0, 0))
+    film, aux = gpu_levelset(ctx, g, cam, api.make_shader(), W, H)
+    ofilm = refapi.new_film(W, H)
+    oaux, _ = oracle.render_levelset(og, cam, api.make_shader(), ofilm, aux=True, threads=4)
+    assert_records_equal(aux, oaux)
+    assert np.array_equal(film, ofilm)
+    # and a close-up of the sphere at the origin so that something is hit
+    cam = api.vdb_render_camera(W, H, (20.0, 30.0, 150.0), (0, 0, 0))
+    film, aux = gpu_levelset(ctx, g, cam, api.make_shader(), W, H)
+    ofilm = refapi.new_film(W, H)
+    oaux, _ = oracle.render_levelset(og, cam, api.make_shader(), ofilm, aux=True, threads=4)
+    assert aux.hit.sum() > 2000
+    assert_records_equal(aux, oaux)
+    assert np.array_equal(film, ofilm)
+    g.free()
+
+
+def test_translated_grid_and_camera_inside(ctx, ref, oracle, sphere100):
+    """a ScaleTranslateMap (index->world translation patched into the NanoVDB map) and a camera inside the narrow band's bbox"""
+    buf = sphere100.buf.copy()
+    t = np.array([10.5, -3.25, 7.0])
+    buf[528:552] = np.frombuffer(t.astype("<f8").tobytes(), np.uint8)           # Map::mVecD
+    buf[296 + 72:296 + 84] = np.frombuffer(t.astype("<f4").tobytes(), np.uint8)  # Map::mVecF
+    buf = refapi.aligned_copy(buf)
+    rg = ref.from_nanovdb(buf)
+    og = oracle.open(buf)
+    g = ctx.upload(buf)
+    assert list(g.info.translation) == list(t)
+    W, H = 200, 150
+    for tr, look in (((30.0, 40.0, 290.0), tuple(t)), ((10.5, -3.25, 7.0), (100.0, 20.0, 30.0)), ((60.0, 0.0, 80.0), (200.0, 0.0, 100.0))):
+        d = refapi.camera_desc(W, H, translation=tr, lookat=look)
+        cam = api.vdb_render_camera(W, H, tr, look)
+        film, aux = gpu_levelset(ctx, g, cam, api.make_shader(abi.SHADER_POSITION, bbox_min=(-100, -100, -100), inv_dim=(0.005,) * 3), W, H)
+        ofilm = refapi.new_film(W, H)
+        oaux, _ = oracle.render_levelset(og, cam, api.make_shader(abi.SHADER_POSITION, bbox_min=(-100, -100, -100), inv_dim=(0.005,) * 3), ofilm, aux=True)
+        rfilm = refapi.new_film(W, H)
+        ref.render_levelset(rg, d, refapi.shader(abi.SHADER_POSITION, bbox_min=(-100, -100, -100), inv_dim=(0.005,) * 3), rfilm)
+        assert aux.hit.sum() > 1000
+        assert_records_equal(aux, oaux)
+        assert np.array_equal(film, ofilm)
+        assert np.array_equal(film, rfilm)
+    g.free()
