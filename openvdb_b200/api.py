@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("VDBRT_LIB", os.path.join(_HERE, "libvdbrt.so"))
+LIB_PATH = os.environ.get("VDBRT_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvdbrt.so")
 
 # every symbol include/vdbrt.h declares
 SYMBOLS = [

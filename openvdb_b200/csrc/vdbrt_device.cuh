@@ -181,27 +181,37 @@ struct TreeCursor {
 
     // the 8 corners of the cell (x..x+1, y..y+1, z..z+1) in BoxStencil slot order 000,001,011,010,100,101,111,110
     // (math/Stencils.h:285-293,414-423; same order as BoxSampler::probeValues, tools/Interpolation.h:663-689).
-    // A cell touches 2^(number of axes on which it straddles a leaf face) leaves: one rolled loop visits each of those
-    // leaves once (1.4 on average) and pulls all corners that live in it with predicated loads off one base pointer.
+    // A cell touches 2^(number of axes on which it straddles a leaf face) leaves.  The loop enumerates exactly those
+    // leaves (the sub-masks of fmask in ascending order), so the k-th trip of every lane of a warp is a leaf visit --
+    // a warp runs max(2^straddles) trips, not one per distinct neighbour code -- and pulls all corners that live in the
+    // visited leaf with predicated loads off one base pointer.  KEEP = false: the fetch works on a COPY of the cursor, so
+    // the caller's path cache keeps pointing at the node its DDA is walking (no re-descent after a stencil that straddled
+    // a face); KEEP = true: the cursor follows the fetch (the fog sampler's own cursor, tools/Interpolation.h:420-425).
+    template<bool KEEP>
     __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
     {
         const int fmask = (((x & 7) == 7) ? 4 : 0) | (((y & 7) == 7) ? 2 : 0) | (((z & 7) == 7) ? 1 : 0);
+        const uint32_t ox0 = uint32_t(x & 7) << 6, ox1 = uint32_t((x + 1) & 7) << 6, oy0 = uint32_t(y & 7) << 3, oy1 = uint32_t((y + 1) & 7) << 3;
+        const uint32_t oz0 = uint32_t(z & 7), oz1 = uint32_t((z + 1) & 7);
+        TreeCursor local = *this;
+        TreeCursor& t = KEEP ? *this : local;
+        int cmb = 0;
 #pragma unroll 1
-        for (int cmb = 0; cmb < 8; ++cmb) {
-            if (cmb & ~fmask) continue;                     // this neighbour leaf is not touched
+        do {
             const int rx = x + (cmb >> 2), ry = y + ((cmb >> 1) & 1), rz = z + (cmb & 1);   // a corner inside that leaf
-            const int depth = descend(g, s, rx, ry, rz);
+            const int depth = t.descend(g, s, rx, ry, rz);
             float tile = 0.f;
             const float* lv = nullptr;
-            if (depth == 0) lv = reinterpret_cast<const float*>(node(g, n0) + kLeafValues);
-            else valueAt(g, s, depth, rx, ry, rz, tile);     // one tile (or the background) covers the whole 8^3 block
+            if (depth == 0) lv = reinterpret_cast<const float*>(node(g, t.n0) + kLeafValues);
+            else t.valueAt(g, s, depth, rx, ry, rz, tile);     // one tile (or the background) covers the whole 8^3 block
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int dx = q >> 2, dy = (q >> 1) & 1, dz = (q ^ (q >> 1)) & 1;            // slot q -> corner offset
                 if ((((dx << 2) | (dy << 1) | dz) & fmask) == cmb)
-                    v[q] = lv ? __ldg(lv + leafOffset(x + dx, y + dy, z + dz)) : tile;
+                    v[q] = lv ? __ldg(lv + ((dx ? ox1 : ox0) | (dy ? oy1 : oy0) | (dz ? oz1 : oz0))) : tile;
             }
-        }
+            cmb = (cmb - fmask) & fmask;                        // next sub-mask of fmask; wraps to 0 after fmask itself
+        } while (cmb != 0);
     }
 };
 
@@ -285,6 +295,9 @@ struct Dda {
     double t0, t1, nx, ny, nz;
     int vx, vy, vz;
 
+    // double(+-2^shift) built from its bit pattern (exact; avoids an int->double conversion per step)
+    __device__ __forceinline__ static double signedDim(int shift, bool positive) { return __hiloint2double(((1023 + shift) << 20) | (positive ? 0 : int(0x80000000u)), 0); }
+
     // DDA::init(ray, startTime, maxTime) (DDA.h:52-75)
     __device__ __forceinline__ void init(const Ray& r, double start, double maxT, int shift)
     {
@@ -292,23 +305,29 @@ struct Dda {
         t0 = start; t1 = maxT;
         const double px = r.ex + r.dx * t0, py = r.ey + r.dy * t0, pz = r.ez + r.dz * t0;
         vx = int(floor(px)) & ~(dim - 1); vy = int(floor(py)) & ~(dim - 1); vz = int(floor(pz)) & ~(dim - 1);
-        nx = r.dx == 0.0 ? DBL_MAX : (r.ix > 0 ? t0 + ((vx + dim) - px) * r.ix : t0 + (vx - px) * r.ix);
-        ny = r.dy == 0.0 ? DBL_MAX : (r.iy > 0 ? t0 + ((vy + dim) - py) * r.iy : t0 + (vy - py) * r.iy);
-        nz = r.dz == 0.0 ? DBL_MAX : (r.iz > 0 ? t0 + ((vz + dim) - pz) * r.iz : t0 + (vz - pz) * r.iz);
+        const double ax = (double(r.ix > 0 ? vx + dim : vx) - px) * r.ix, ay = (double(r.iy > 0 ? vy + dim : vy) - py) * r.iy;
+        const double az = (double(r.iz > 0 ? vz + dim : vz) - pz) * r.iz;
+        nx = r.dx == 0.0 ? DBL_MAX : t0 + ax;
+        ny = r.dy == 0.0 ? DBL_MAX : t0 + ay;
+        nz = r.dz == 0.0 ? DBL_MAX : t0 + az;
     }
     // DDA::step (DDA.h:83-90); MinIndex ties go to the largest index (math/Math.h:999-1007).
-    // step/delta are rebuilt from the ray: step = 0/+DIM/-DIM, delta = DBL_MAX or double(step)*inv (DDA.h:61-73)
+    // step/delta are rebuilt from the ray: step = 0/+DIM/-DIM, delta = DBL_MAX or double(step)*inv (DDA.h:61-73).
+    // Branch-free: the three axes are handled by selects so that the lanes of a warp do not split on the axis.
     __device__ __forceinline__ bool step(const Ray& r, int shift)
     {
-        const int dim = 1 << shift;
-        int axis = 0;
-        double m = nx;
-        if (ny <= m) { axis = 1; m = ny; }
-        if (nz <= m) { axis = 2; m = nz; }
+        const bool b1 = ny <= nx;
+        double m = b1 ? ny : nx;
+        const bool a2 = nz <= m;
+        m = a2 ? nz : m;
+        const bool a1 = b1 && !a2, a0 = !b1 && !a2;
         t0 = m;
-        if (axis == 0) { const int st = r.dx == 0.0 ? 0 : (r.ix > 0 ? dim : -dim); nx += (r.dx == 0.0 ? DBL_MAX : st * r.ix); vx += st; }
-        else if (axis == 1) { const int st = r.dy == 0.0 ? 0 : (r.iy > 0 ? dim : -dim); ny += (r.dy == 0.0 ? DBL_MAX : st * r.iy); vy += st; }
-        else { const int st = r.dz == 0.0 ? 0 : (r.iz > 0 ? dim : -dim); nz += (r.dz == 0.0 ? DBL_MAX : st * r.iz); vz += st; }
+        const double d = a2 ? r.dz : (a1 ? r.dy : r.dx), iv = a2 ? r.iz : (a1 ? r.iy : r.ix);
+        const bool zero = d == 0.0, pos = iv > 0;
+        const int st = zero ? 0 : (pos ? (1 << shift) : -(1 << shift));
+        const double nn = m + (zero ? DBL_MAX : signedDim(shift, pos) * iv);     // mNext[axis] += mDelta[axis]
+        nx = a0 ? nn : nx; ny = a1 ? nn : ny; nz = a2 ? nn : nz;
+        vx += a0 ? st : 0; vy += a1 ? st : 0; vz += a2 ? st : 0;
         return t0 <= t1;
     }
     // DDA::next = math::Min(mT1, mNext[0], mNext[1], mNext[2]) (DDA.h:112, Math.h:734-738)
@@ -334,7 +353,7 @@ struct Stencil {
         if (i == cx && j == cy && k == cz) return;
         cx = i; cy = j; cz = k;
         if (COUNT) ++c.refills;
-        acc.fetchCell(g, s, i, j, k, v);
+        acc.template fetchCell<false>(g, s, i, j, k, v);
     }
     // interpolation(Vec3<float>) (:335-360): position converted to float first; every lerp in float
     __device__ __forceinline__ float interpolation(double x, double y, double z) const
@@ -618,7 +637,7 @@ __device__ __forceinline__ float boxSampleWorld(const DevGrid& g, const RootSmem
     const int i = int(floor(wx)), j = int(floor(wy)), k = int(floor(wz));
     const double u = wx - i, v = wy - j, w = wz - k;
     float d[8];   // 000,001,011,010,100,101,111,110
-    acc.fetchCell(g, s, i, j, k, d);
+    acc.template fetchCell<true>(g, s, i, j, k, d);
     return lerpBox(lerpBox(lerpBox(d[0], d[1], w), lerpBox(d[3], d[2], w), v),
                    lerpBox(lerpBox(d[4], d[5], w), lerpBox(d[7], d[6], w), v), u);
 }

@@ -82,7 +82,7 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 #define VDBRT_REFILL 32
 #endif
 #ifndef VDBRT_MINBLOCKS
-#define VDBRT_MINBLOCKS 3
+#define VDBRT_MINBLOCKS 4
 #endif
 // measured on the B200 (C2 workload): re-feeding single lanes costs more (ray set-up for a few lanes at a time, lost
 // coherence) than it gains; a warp takes a fresh 8x4 tile when all its lanes are done (profiles/r01_tuning.md)
