@@ -316,6 +316,7 @@ def main():
         ev[k][2].record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    launches_per_frame = int(ctx.last_kernel_ms()[1])      # 1, or 1 + the long-ray round kernels of a partitioned frame
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
     tt = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device="cuda")
@@ -399,9 +400,10 @@ def main():
                        "hit_pixels": hits},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": film_bytes, "d2h_bytes_per_step": film_bytes,
                     "ms_per_step": float(te[0]) * 1e3 / args.steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_frame,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k_render_levelset", "kernel_ms": kernel_ms_max,
+                         "peak_source": peak_src, "kernel": "k_render_levelset" + (" + %d long-ray round kernels (k_long_scout/march/finish)" % (launches_per_frame - 1) if launches_per_frame > 1 else ""),
+                         "kernel_ms": kernel_ms_max,
                          "algorithmic_bytes_per_ray": bpr, "rays_per_launch": rays_per_launch, "counters": counters},
             "clocks": clocks,
         }

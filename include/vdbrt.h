@@ -106,6 +106,12 @@ typedef struct vdbrt_ls_opts {
 } vdbrt_ls_opts;
 #define VDBRT_LS_UNIFORM_BG 1u /* every film pixel currently equals bg_rgba: skip the host->device film copy    */
 #define VDBRT_ASYNC         2u /* device-memory film only: enqueue on the context's stream and return at once   */
+/* Long-ray rounds (csrc/vdbrt_kernels.cuh): rays still running when their 8x4 tile has used up its iteration budget
+ * are finished by scout / march kernels that spread the leaf visits of one ray over many threads.  Same pixels either
+ * way.  Default: on for a small share of a partitioned frame (part.count > 1 and few tiles per resident warp, where
+ * the slowest tile bounds the frame time), off otherwise; one sample per pixel only.                            */
+#define VDBRT_LS_ROUNDS_ON  4u
+#define VDBRT_LS_ROUNDS_OFF 8u
 
 /* VolumeRender parameters (tools/RayTracer.h:162-207; defaults :929-936).                                      */
 typedef struct vdbrt_vol_opts {

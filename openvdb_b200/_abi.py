@@ -11,6 +11,8 @@ SPACE_WORLD, SPACE_INDEX = 0, 1
 GRID_CLASS_UNKNOWN, GRID_CLASS_LEVEL_SET, GRID_CLASS_FOG_VOLUME = 0, 1, 2
 LS_UNIFORM_BG = 1
 ASYNC = 2
+LS_ROUNDS_ON = 4
+LS_ROUNDS_OFF = 8
 
 ERR_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "BAD_GRID", 3: "NOT_FLOAT", 4: "NOT_LEVELSET", 5: "NONUNIFORM",

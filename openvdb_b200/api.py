@@ -259,7 +259,7 @@ class Context:
         f.bg_rgba = (C.c_float * 4)(*bg)
         return f
 
-    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None):
+    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None, rounds=None):
         o = abi.LsOpts()
         o.iso, o.spp = iso, spp
         if spp > 1:
@@ -268,6 +268,8 @@ class Context:
         if part is not None:
             o.part = part
         o.flags = abi.LS_UNIFORM_BG if uniform_bg else 0
+        if rounds is not None:      # long-ray rounds: None = library default (on for partitioned frames)
+            o.flags |= abi.LS_ROUNDS_ON if rounds else abi.LS_ROUNDS_OFF
         return o
 
     def render_levelset(self, grid, cam, shader, film, iso=0.0, spp=1, seed=0, part=None, aux=None, uniform_bg=False,

@@ -7,6 +7,7 @@
 #include "vdbrt_kernels.cuh"
 #include "vdbrt_host.h"
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -216,6 +217,14 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaMalloc(&ctx->scratch, 4096));
     CUDA_TRY(cudaMemset(ctx->scratch, 0, 4096));
+    // tuning knobs of the long-ray rounds (see vdbrt_kernels.cuh); the defaults were measured on the B200
+    const char* ev = std::getenv("VDBRT_LS_BUDGET");
+    ctx->ls_budget = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultBudget;
+    ev = std::getenv("VDBRT_LS_FACTOR");
+    ctx->ls_factor = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultFactor;
+    ev = std::getenv("VDBRT_LS_ROUNDS");
+    ctx->ls_rounds = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : uint32_t(kDefaultRounds);
+    if (ctx->ls_rounds > uint32_t(kMaxRounds)) ctx->ls_rounds = kMaxRounds;
     *out = ctx;
     return VDBRT_OK;
 }
@@ -228,6 +237,7 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
     if (ctx->film) cudaFree(ctx->film);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->io) cudaFree(ctx->io);
+    if (ctx->lng) cudaFree(ctx->lng);
     cudaFree(ctx->scratch);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->own_stream);
@@ -354,6 +364,21 @@ int vdbrt_grid_download(vdbrt_ctx* ctx, const vdbrt_grid* grid, void* dst, uint6
 // ---------------------------------------------------------------------------------------------------------------
 // LevelSetRayTracer::render
 // ---------------------------------------------------------------------------------------------------------------
+// carve the long-ray buffers out of one allocation sized for `slots` pixel slots
+static int longBuffers(vdbrt_ctx* ctx, size_t slots, LongBufs& lb)
+{
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t capLong = std::max<size_t>(slots / 4, 65536), capSeg = capLong * 8;
+    const size_t oCtl = 0, oA = up(sizeof(LongCtl)), oB = oA + up(capLong * 4), oR = oB + up(capLong * 4), oI = oR + up(capLong * sizeof(LongRay));
+    const size_t oO = oI + up(capSeg * sizeof(SegIn)), total = oO + up(capSeg * sizeof(SegOut));
+    if (int rc = ensureBuffer(&ctx->lng, &ctx->lng_cap, total)) return rc;
+    uint8_t* b = static_cast<uint8_t*>(ctx->lng);
+    lb.ctl = reinterpret_cast<LongCtl*>(b + oCtl); lb.liveA = reinterpret_cast<uint32_t*>(b + oA); lb.liveB = reinterpret_cast<uint32_t*>(b + oB);
+    lb.rays = reinterpret_cast<LongRay*>(b + oR); lb.segIn = reinterpret_cast<SegIn*>(b + oI); lb.segOut = reinterpret_cast<SegOut*>(b + oO);
+    lb.capLong = uint32_t(capLong); lb.capSeg = uint32_t(capSeg); lb.budget = ctx->ls_budget; lb.factor = ctx->ls_factor;
+    return VDBRT_OK;
+}
+
 static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_shader* shader,
                           const vdbrt_ls_opts* opts, const vdbrt_film* film, float4* dFilm, const AuxOut& aux, bool wantAux,
                           unsigned long long* dCounters)
@@ -365,21 +390,62 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     for (int a = 0; a < 3; ++a) { sh.bmin[a] = shader->bbox_min[a]; sh.inv[a] = shader->inv_dim[a]; }
     const DevCamera dc = toDev(*cam);
     unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
+    // long-ray rounds: one sample per pixel only (with more, the samples of a pixel are accumulated in order by one thread)
+    // They pay when ONE slow tile is long against everything else a warp has to do, i.e. when this launch has few tiles
+    // per resident warp -- a small share of a frame that is split over several GPUs (measured on C2, 1/8 of the frame:
+    // 1.9 -> 1.0 ms per rank).  With many tiles per warp the work queue balances the frame by itself and the rounds only
+    // cost (C2 whole frame 3.75 -> 3.9 ms, C4 at 1/8: 6.8 -> 8.3 ms), so the default is: partitioned frame AND fewer than
+    // kRoundsMaxTilesPerWarp tiles per warp.  VDBRT_LS_ROUNDS_ON / _OFF override.
+    const double tilesPerWarp = double(tm.items) / (double(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32));
+    const bool automatic = opts->part.count > 1 && tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
+    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && ctx->ls_budget != 0 && ctx->ls_rounds != 0;
+    LongBufs lb = {};
+    lb.budget = 0xffffffffu;
+    if (rounds) {
+        if (int rc = longBuffers(ctx, size_t(tm.items) * 32, lb)) return rc;
+        CUDA_TRY(cudaMemsetAsync(lb.ctl, 0, sizeof(LongCtl), ctx->stream));
+    }
     CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (dCounters) {
-        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<false, true>, tm.items);
-        k_render_levelset<false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters);
-    } else if (wantAux) {
-        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<true, false>, tm.items);
-        k_render_levelset<true, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr);
-    } else {
-        const int blocks = persistentGrid(ctx, (const void*)k_render_levelset<false, false>, tm.items);
-        k_render_levelset<false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr);
-    }
+    // LONG = true compiles the suspension of over-budget rays into the kernel
+    const void* kern = dCounters ? (const void*)k_render_levelset<false, true, false>
+                     : wantAux ? (rounds ? (const void*)k_render_levelset<true, false, true> : (const void*)k_render_levelset<true, false, false>)
+                               : (rounds ? (const void*)k_render_levelset<false, false, true> : (const void*)k_render_levelset<false, false, false>);
+    const int blocks = persistentGrid(ctx, kern, tm.items);
+    if (dCounters) k_render_levelset<false, true, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters, lb);
+    else if (wantAux && rounds) k_render_levelset<true, false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
+    else if (wantAux) k_render_levelset<true, false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
+    else if (rounds) k_render_levelset<false, false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
+    else k_render_levelset<false, false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->last_launches = 1;
+    if (rounds) {
+        // K leaf visits per ray and round: small first (most suspended rays hit soon), then growing
+        static const uint32_t kLeaves[kMaxRounds] = {2, 4, 12, 32, 64, 128, 128, 128};
+        const int wide = ctx->sm_count * 8;
+        const int nr = int(ctx->ls_rounds);
+        for (int r = 0; r < nr; ++r) {
+            if (wantAux) k_long_scout<true><<<wide * 2, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, r, kLeaves[r]);
+            else k_long_scout<false><<<wide * 2, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, r, kLeaves[r]);
+            k_long_march<<<wide * 2, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, lb, r, kLeaves[r], p.iso, p.vmin, p.vmax);
+        }
+        if (wantAux) k_long_finish<true><<<wide, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, nr);
+        else k_long_finish<false><<<wide, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, nr);
+        CUDA_TRY(cudaGetLastError());
+        ctx->last_launches = 2 + 2 * uint32_t(nr);
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (rounds && std::getenv("VDBRT_DEBUG_LONG")) {
+        LongCtl h;
+        CUDA_TRY(cudaMemcpyAsync(&h, lb.ctl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        std::fprintf(stderr, "[vdbrt] %u tiles, %u finished with mean %.1f iterations, %d blocks; long rays %u (cap %u), segment cap %u; live per round:",
+                     tm.items, h.tiles, h.tiles ? double(h.spent) / h.tiles : 0.0, blocks, h.nLong, lb.capLong, lb.capSeg);
+        for (int r = 0; r < int(ctx->ls_rounds); ++r) std::fprintf(stderr, " %u", h.live[r]);
+        std::fprintf(stderr, "; segment slots:");
+        for (int r = 0; r < int(ctx->ls_rounds); ++r) std::fprintf(stderr, " %u", h.segCount[r]);
+        std::fprintf(stderr, "\n");
+    }
     return VDBRT_OK;
 }
 

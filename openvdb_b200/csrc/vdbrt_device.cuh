@@ -432,12 +432,14 @@ struct LsWalk {
     bool skip;            // the current cell was already handled (we just came back up): only step
     bool pendLevel;       // a DDA must be initialised over [c0,c1] at `lvl`
     bool pendStep;        // the current cell is done: step
+    bool emit;            // scout mode only: a leaf was found, its range is [c0,c1] (see lsAdvance<.., SCOUT>)
 
     __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }   // 12, 7, 3, 0
     // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
     __device__ __forceinline__ void begin(const Ray& ray)
     {
         lvl = 0; skip = false; pendLevel = true; pendStep = false; pendInterp = 0; T0 = 0.0; V0 = 0.f; c0 = ray.t0; c1 = ray.t1; tq = 0.0;
+        emit = false;
     }
     __device__ __forceinline__ bool runnable() const { return !pendLevel && !pendInterp; }
 };
@@ -447,7 +449,11 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 // SYNC = true: the caller runs a warp-synchronous loop in which ALL 32 lanes call lsAdvance every iteration (lanes
 // without a ray pass active = false).  __syncwarp() between the phases makes the warp reconverge after each phase and
 // stops the compiler from cloning the later phases per control-flow path.  SYNC = false: plain per-thread use.
-template<bool COUNT, bool SYNC, int THREADS>
+// SCOUT = true: the walk never enters a leaf.  A leaf found by the lower node's DDA is reported instead (w.emit with its
+// time range in w.c0/w.c1, the cursor pointing at it) and the DDA steps on as if the leaf had returned "no hit": the
+// leaf visits of one ray are independent of each other (the tester is re-initialised per leaf, DDA.h:172-173), so they
+// can be marched by other threads (vdbrt_kernels.cuh, long-ray rounds).
+template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false>
 __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
                                          TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
                                          LsWalk& w, LsHit& out, Counters& c)
@@ -472,9 +478,12 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 if (depth <= 2 - w.lvl) {
                     // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
                     w.c0 = cur.t0; w.c1 = cur.next();
-                    sm.park(w.lvl, cur);
-                    ++w.lvl;
-                    w.pendLevel = true;
+                    if (SCOUT && w.lvl == 2) { w.emit = true; w.pendStep = true; }
+                    else {
+                        sm.park(w.lvl, cur);
+                        ++w.lvl;
+                        w.pendLevel = true;
+                    }
                 } else w.pendStep = true;
             } else {
                 // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)

@@ -14,6 +14,10 @@ struct vdbrt_ctx {
     void* film = nullptr;  size_t film_cap = 0; // device staging for host films
     void* aux = nullptr;   size_t aux_cap = 0;  // device staging for per-pixel records
     void* io = nullptr;    size_t io_cap = 0;   // device staging for ray batches / scratch films
+    void* lng = nullptr;   size_t lng_cap = 0;  // long-ray records, segment lists and their control block (vdbrt_kernels.cuh)
+    uint32_t ls_budget = 0;                     // warp iterations a tile may spend before its running rays are suspended (0 = never)
+    uint32_t ls_factor = 0;                     // ... or this many percent of a warp's share of the launch, if that is more
+    uint32_t ls_rounds = 0;                     // long-ray rounds per frame
 };
 
 struct vdbrt_grid {

@@ -102,11 +102,113 @@ __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket,
     return lx < m.tile_w && ly < m.tile_h && px < m.width && py < m.height;
 }
 
-template<bool AUX, bool COUNT>
+// getWorldPosAndNml (tools/RayIntersector.h:575-582) + shader + the optional per-pixel records of the primary ray
+template<bool AUX>
+__device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh, const LsHit& h, const Ray& ray, double wdx, double wdy, double wdz,
+                                           size_t pix, const AuxOut& aux, bool record)
+{
+    // normalise the gradient in double, map the position
+    double x = h.px, y = h.py, z = h.pz;
+    double nx = h.gx, ny = h.gy, nz = h.gz;
+    vnormalize(nx, ny, nz);
+    indexToWorldPos(g, x, y, z);
+    if (AUX && record) {
+        if (aux.ijk) { aux.ijk[3 * pix] = h.ix; aux.ijk[3 * pix + 1] = h.iy; aux.ijk[3 * pix + 2] = h.iz; }
+        if (aux.t_index) aux.t_index[pix] = h.time;
+        // getWorldTime (:588-591): mTime * |J dir|
+        if (aux.t_world) aux.t_world[pix] = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
+        if (aux.xyz) { aux.xyz[3 * pix] = x; aux.xyz[3 * pix + 1] = y; aux.xyz[3 * pix + 2] = z; }
+        if (aux.nml) { aux.nml[3 * pix] = nx; aux.nml[3 * pix + 1] = ny; aux.nml[3 * pix + 2] = nz; }
+    }
+    return shade(sh, x, y, z, nx, ny, nz, wdx, wdy, wdz);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Long rays.  A ray that grazes the surface marches hundreds of narrow-band voxels; one such ray per warp keeps the
+// whole warp (and, at the end of the frame, the whole GPU) waiting.  The render kernel therefore gives every 8x4 tile a
+// BUDGET of warp iterations; rays still running after that are suspended into LongRay records and finished by
+// "rounds" of three homogeneous kernels:
+//   scout   one thread per long ray walks the node levels only (root/upper/lower DDAs) and writes the next K leaf visits
+//           (time range + leaf handle) it finds as segments;
+//   march   one thread per SEGMENT runs the voxel DDA / zero-crossing search of that leaf (LevelSetHDDA<Tree,-1>::test);
+//   resolve one thread per long ray: the first segment with a hit wins -> shade + film; walked out of the grid -> miss;
+//           otherwise the ray stays for the next round (K grows).
+// A leaf visit depends only on the ray and its [t0,t1] (the tester is re-initialised per leaf, math/DDA.h:172-173), so
+// marching the leaves of one ray in parallel and taking the first hit in visit order is exactly the reference's result.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kNoHit = 0xffffffffu;
+constexpr int kMaxRounds = 8;
+constexpr uint32_t kDefaultBudget = 160;  // warp iterations per 8x4 tile before its running rays are suspended ...
+constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
+constexpr int kDefaultRounds = 6;
+constexpr double kRoundsMaxTilesPerWarp = 12.0;   // rounds are on by default only below this (see launchLevelSet)
+
+struct LongRay {
+    Ray ray;                          // index space, clipped
+    double wdx, wdy, wdz;             // world direction (shader input)
+    Dda cur; int lvl;                 // the DDA of the level the walk is on (<= 2 while suspended)
+    DdaSave park[2];                  // suspended parents: root level, upper level
+    double c0, c1;
+    int kx, ky, kz; uint32_t n2, n1, n0;
+    uint32_t pix, flags;              // flags: skip | pendLevel << 1 | pendStep << 2
+    uint32_t segBase, segCount, best, state;   // this round's segments; index of the first one that hit; 1 = walked out of the grid
+};
+struct SegIn { double t0, t1; int kx, ky, kz; uint32_t n2, n1, n0; };
+struct SegOut { double time, px, py, pz; float gx, gy, gz; int ix, iy, iz; };
+struct LongCtl { uint32_t nLong, tiles; unsigned long long spent; uint32_t segCount[kMaxRounds]; uint32_t live[kMaxRounds + 1]; };   // live[r]: rays that walked in round r; spent/tiles: iterations of the finished tiles
+struct LongBufs { LongRay* rays; uint32_t* liveA; uint32_t* liveB; SegIn* segIn; SegOut* segOut; LongCtl* ctl; uint32_t capLong, capSeg, budget, factor; };
+
+// Writes the record of a suspended ray.  Nothing of the caller's state is modified (the record is built from copies), so
+// the cold suspension path adds no merges to the registers the render loop carries from iteration to iteration.
+template<int THREADS>
+__device__ __forceinline__ void suspendRay(LongRay& r, const Ray& ray, double wdx, double wdy, double wdz, const LsWalk& w, const WalkSmem<THREADS>& sm,
+                                           const TreeCursor& acc, size_t pix)
+{
+    const int t = threadIdx.x;
+    r.ray = ray; r.wdx = wdx; r.wdy = wdy; r.wdz = wdz;
+    uint32_t flags = (w.skip ? 1u : 0u) | (w.pendLevel ? 2u : 0u) | (w.pendStep ? 4u : 0u);
+    if (w.lvl == 3) {
+        // rewind to the lower node's DDA standing on this leaf: the scout finds the leaf again and the march redoes the visit.
+        // (pendLevel: the leaf's own DDA was not set up yet, `cur` still is the lower node's)
+        r.lvl = 2; flags = 0u;
+        r.cur.t0 = w.pendLevel ? w.cur.t0 : w.c0;
+        r.cur.t1 = w.pendLevel ? w.cur.t1 : sm.t1[2][t]; r.cur.nx = w.pendLevel ? w.cur.nx : sm.nx[2][t];
+        r.cur.ny = w.pendLevel ? w.cur.ny : sm.ny[2][t]; r.cur.nz = w.pendLevel ? w.cur.nz : sm.nz[2][t];
+        r.cur.vx = w.pendLevel ? w.cur.vx : sm.vx[2][t]; r.cur.vy = w.pendLevel ? w.cur.vy : sm.vy[2][t]; r.cur.vz = w.pendLevel ? w.cur.vz : sm.vz[2][t];
+    } else { r.cur = w.cur; r.lvl = w.lvl; }
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        r.park[l].t1 = sm.t1[l][t]; r.park[l].nx = sm.nx[l][t]; r.park[l].ny = sm.ny[l][t]; r.park[l].nz = sm.nz[l][t];
+        r.park[l].vx = sm.vx[l][t]; r.park[l].vy = sm.vy[l][t]; r.park[l].vz = sm.vz[l][t];
+    }
+    r.c0 = w.c0; r.c1 = w.c1;
+    r.kx = acc.kx; r.ky = acc.ky; r.kz = acc.kz; r.n2 = acc.n2; r.n1 = acc.n1; r.n0 = acc.n0;
+    r.pix = uint32_t(pix); r.flags = flags;
+    r.segBase = 0u; r.segCount = 0u; r.best = kNoHit; r.state = 0u;
+}
+
+template<int THREADS>
+__device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w, WalkSmem<THREADS>& sm, TreeCursor& acc)
+{
+    ray = r.ray;
+    w.begin(ray);
+    w.cur = r.cur; w.lvl = r.lvl;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        sm.t1[l][t] = r.park[l].t1; sm.nx[l][t] = r.park[l].nx; sm.ny[l][t] = r.park[l].ny; sm.nz[l][t] = r.park[l].nz;
+        sm.vx[l][t] = r.park[l].vx; sm.vy[l][t] = r.park[l].vy; sm.vz[l][t] = r.park[l].vz;
+    }
+    w.c0 = r.c0; w.c1 = r.c1;
+    acc.kx = r.kx; acc.ky = r.ky; acc.kz = r.kz; acc.n2 = r.n2; acc.n1 = r.n1; acc.n0 = r.n0;
+    w.skip = (r.flags & 1u) != 0u; w.pendLevel = (r.flags & 2u) != 0u; w.pendStep = (r.flags & 4u) != 0u;
+}
+
+template<bool AUX, bool COUNT, bool LONG>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* __restrict__ film,
-                  AuxOut aux, unsigned int* queue, unsigned long long* counters)
+                  AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb)
 {
     __shared__ RootSmem root;
     __shared__ WalkSmem<kBlockThreads> wsm;
@@ -123,7 +225,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     uint32_t px = 0, py = 0, k = 0;
     size_t pix = 0;
     unsigned long long n = 0;
-    float4 bg = make_float4(0.f, 0.f, 0.f, 1.f), col = bg;
+    float4 col = make_float4(0.f, 0.f, 0.f, 1.f);       // the pixel's background is re-read when a ray misses (the film is written once, at the end)
     Ray ray; double wdx = 0.0, wdy = 0.0, wdz = 0.0;
     LsWalk walk; LsHit h;
     ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray);
@@ -131,9 +233,32 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
 
     long long tileStart = 0; unsigned long long tileIters = 0, tileActive = 0;
+    // warp iterations spent on the current tile, and what a tile may spend: at least lb.budget, and lb.factor percent of
+    // a warp's fair share of the whole launch (tiles per warp x the mean of the tiles the grid has finished so far, two
+    // atomics per tile).  Suspending pays when ONE tile is long against everything else a warp has to do -- a small
+    // partition of a frame; a launch with plenty of tiles per warp balances itself and suspends next to nothing.
+    const float tilesPerWarp = float(tm.items) / float(gridDim.x * (kBlockThreads / 32));
+    uint32_t spent = 0, limit = lb.budget;
+    bool longFull = false;              // no room left for suspended rays: finish everything in line
     for (;;) {
         __syncwarp();
         if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
+        // (0) the tile has used up its budget: suspend the rays that are still running (they continue in the long-ray rounds)
+        if (LONG && ++spent > limit && !longFull) {
+            const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
+            const unsigned m = __ballot_sync(0xffffffffu, sus);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
+                if (base + __popc(m) > lb.capLong) longFull = true;
+                if (sus && idx < lb.capLong) {
+                    suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
+                    rayOn = false; hasPix = false;
+                }
+            }
+        }
         // (1) refill idle lanes from the queue
         const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
         if (COUNT && idle == 0xffffffffu && lane == 0) {
@@ -145,6 +270,18 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             tileStart = now; tileIters = 0; tileActive = 0;
         }
         if (idle == 0xffffffffu && drained) break;
+        if (LONG && idle == 0xffffffffu) {
+            unsigned m = 0;
+            if (lane == 0) {
+                if (spent > 1u) { atomicAdd(&lb.ctl->spent, (unsigned long long)(spent < limit ? spent : limit)); atomicAdd(&lb.ctl->tiles, 1u); }
+                const unsigned long long sum = *reinterpret_cast<volatile unsigned long long*>(&lb.ctl->spent);
+                const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&lb.ctl->tiles);
+                m = n >= 64u ? uint32_t(0.01f * float(lb.factor) * tilesPerWarp * float(sum) / float(n)) : 0u;
+            }
+            m = __shfl_sync(0xffffffffu, m, 0);
+            limit = m > lb.budget ? m : lb.budget;
+            spent = 0;
+        }
         if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillThreshold)) {
             const unsigned want = __popc(idle);
             unsigned base = 0;
@@ -156,8 +293,6 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 if (ticket < total && ticketToPixel(tm, ticket, px, py)) {
                     hasPix = true; rayOn = false; k = 0;
                     pix = size_t(py) * tm.width + px;
-                    bg = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
-                    col = bg;
                     n = 2ull * p.sub * pix;
                 }
             }
@@ -189,25 +324,12 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         __syncwarp();
         // (4) a ray ended: shade / composite, then next sample or write the pixel
         if (status != kWalkContinue) {
-            float4 s = bg;
             const bool hit = status == kWalkHit;
+            float4 s;
             if (hit) {
                 if (COUNT) ++c.hits;
-                // getWorldPosAndNml (tools/RayIntersector.h:575-582): normalise the gradient in double, map the position
-                double x = h.px, y = h.py, z = h.pz;
-                double nx = h.gx, ny = h.gy, nz = h.gz;
-                vnormalize(nx, ny, nz);
-                indexToWorldPos(g, x, y, z);
-                s = shade(sh, x, y, z, nx, ny, nz, wdx, wdy, wdz);
-                if (AUX && k == 0) {
-                    if (aux.ijk) { aux.ijk[3 * pix] = h.ix; aux.ijk[3 * pix + 1] = h.iy; aux.ijk[3 * pix + 2] = h.iz; }
-                    if (aux.t_index) aux.t_index[pix] = h.time;
-                    // getWorldTime (:588-591): mTime * |J dir|
-                    if (aux.t_world) aux.t_world[pix] = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
-                    if (aux.xyz) { aux.xyz[3 * pix] = x; aux.xyz[3 * pix + 1] = y; aux.xyz[3 * pix + 2] = z; }
-                    if (aux.nml) { aux.nml[3 * pix] = nx; aux.nml[3 * pix + 1] = ny; aux.nml[3 * pix + 2] = nz; }
-                }
-            }
+                s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, k == 0);
+            } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
             if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
             if (k == 0) col = s;
             else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
@@ -219,6 +341,218 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         }
     }
     if (COUNT) flushCounters(c, counters);
+}
+
+// Round r works on the rays that walked in round r-1 (list r-1; all suspended rays for r = 0).  Its scout first RESOLVES
+// round r-1 for its ray -- the first segment that hit wins, a ray that left the grid without a hit is a miss -- and only
+// an unresolved ray walks on; those rays form list r, which the march kernel of round r and the scout of round r+1 read.
+__device__ __forceinline__ uint32_t liveCount(const LongBufs& lb, int round)
+{
+    const uint32_t n = round == 0 ? lb.ctl->nLong : lb.ctl->live[round - 1];
+    return n < lb.capLong ? n : lb.capLong;
+}
+__device__ __forceinline__ const uint32_t* liveList(const LongBufs& lb, int round) { return round == 0 ? nullptr : (((round - 1) & 1) ? lb.liveB : lb.liveA); }
+
+template<bool AUX>
+__device__ __forceinline__ void writeLongPixel(const DevGrid& g, const DevShader& sh, const LsParams& p, float4* film, const AuxOut& aux, const LongRay& r,
+                                               bool hit, const LsHit& h)
+{
+    const size_t pix = r.pix;
+    float4 s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
+    if (hit) s = shadeHit<AUX>(g, sh, h, r.ray, r.wdx, r.wdy, r.wdz, pix, aux, true);
+    if (AUX && aux.hit) aux.hit[pix] = hit ? 1 : 0;
+    film[pix] = make_float4(s.x * p.frac, s.y * p.frac, s.z * p.frac, 1.0f);      // one sample per pixel: c = s, bg = c*frac, alpha 1
+}
+
+// true when the ray is finished (pixel written)
+template<bool AUX>
+__device__ __forceinline__ bool resolveLong(const DevGrid& g, const DevShader& sh, const LsParams& p, float4* film, const AuxOut& aux, const LongBufs& lb, LongRay* r)
+{
+    if (r->best != kNoHit) {
+        const SegOut o = lb.segOut[r->segBase + r->best];
+        LsHit h;
+        h.time = o.time; h.ix = o.ix; h.iy = o.iy; h.iz = o.iz; h.px = o.px; h.py = o.py; h.pz = o.pz; h.gx = o.gx; h.gy = o.gy; h.gz = o.gz;
+        writeLongPixel<AUX>(g, sh, p, film, aux, *r, true, h);
+        return true;
+    }
+    if (r->state == 1u) {
+        LsHit h = {};
+        writeLongPixel<AUX>(g, sh, p, film, aux, *r, false, h);
+        return true;
+    }
+    return false;
+}
+
+// The scout is a plain per-thread loop (no phases, no warp synchronisation): LevelSetHDDA<Tree,2/1/0>::test (math/DDA.h:144-165)
+// with "enter the leaf" replaced by "write a segment".  Its state between rounds is "about to probe the current cell of
+// the DDA at `lvl`" plus what the render kernel may have left pending (a level to initialise, a cell to step past).
+// The walk of one ray is a sequential chain, and 32 different walks in one warp run one after the other; when there
+// are fewer rays than lanes in the grid the rays are therefore spread out, down to one ray per warp.
+template<bool AUX>
+__global__ void __launch_bounds__(kBlockThreads)
+k_long_scout(const __grid_constant__ DevGrid g, const __grid_constant__ DevShader sh, const __grid_constant__ LsParams p, float4* __restrict__ film,
+             AuxOut aux, const __grid_constant__ LongBufs lb, int round, uint32_t K)
+{
+    __shared__ RootSmem root;
+    __shared__ WalkSmem<kBlockThreads> wsm;
+    stageRoot(g, root);
+    __syncthreads();
+    const uint32_t nLive = liveCount(lb, round);
+    const uint32_t* list = liveList(lb, round);
+    uint32_t* next = (round & 1) ? lb.liveB : lb.liveA;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = gridDim.x * (kBlockThreads / 32);
+    uint32_t rpw = (nLive + warps - 1) / warps;                        // rays per warp
+    rpw = rpw < 1u ? 1u : (rpw > 32u ? 32u : rpw);
+    for (uint32_t base = (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)) * rpw; base < nLive; base += warps * rpw) {
+        const uint32_t i = base + lane;
+        if (lane >= rpw || i >= nLive) continue;
+        const uint32_t idx = list ? list[i] : i;
+        LongRay* r = lb.rays + idx;
+        if (round > 0 && resolveLong<AUX>(g, sh, p, film, aux, lb, r)) continue;
+        next[atomicAdd(&lb.ctl->live[round], 1u)] = idx;
+        const uint32_t sb = atomicAdd(&lb.ctl->segCount[round], K);    // K consecutive segment slots
+        if (sb + K > lb.capSeg) { r->segCount = 0u; r->best = kNoHit; continue; }      // no room this round: try again in the next one
+        Ray ray; LsWalk walk; TreeCursor acc;
+        resumeRay(*r, ray, walk, wsm, acc);
+        Dda& cur = walk.cur;
+        uint32_t emitted = 0;
+        bool exhausted = false;
+        bool advance = walk.pendStep || walk.skip;
+        if (walk.pendLevel) cur.init(ray, walk.c0, walk.c1, LsWalk::shiftOf(walk.lvl));
+#pragma unroll 1
+        for (;;) {
+            if (advance) {
+                // while (dda.step()); an exhausted level returns to its parent, which steps in turn (DDA.h:158-159)
+                bool alive = true, failed = !cur.step(ray, LsWalk::shiftOf(walk.lvl));
+#pragma unroll 1
+                for (;;) {
+#pragma unroll 1
+                    while (failed) {
+                        if (walk.lvl == 0) { alive = false; break; }
+                        --walk.lvl; wsm.unpark(walk.lvl, cur);
+                        failed = !cur.step(ray, LsWalk::shiftOf(walk.lvl));
+                    }
+                    if (!alive || emitted == K || walk.lvl != 2 || !acc.n1) break;
+                    // short cut: run through the empty cells of the lower node the cursor is in (one child-mask word per cell);
+                    // a cell with a leaf, or one that rounding pushed outside the node, goes to the general probe below
+                    const uint8_t* cm = TreeCursor::node(g, acc.n1) + kLowerCMask;
+#pragma unroll 1
+                    for (;;) {
+                        if (uint32_t((cur.vx ^ acc.kx) | (cur.vy ^ acc.ky) | (cur.vz ^ acc.kz)) & ~127u) break;
+                        const uint32_t n = lowerOffset(cur.vx, cur.vy, cur.vz);
+                        if ((ldg64(cm + 8u * (n >> 6)) >> (n & 63u)) & 1ull) break;
+                        if (!cur.step(ray, 3)) { failed = true; break; }
+                    }
+                    if (!failed) break;
+                }
+                if (!alive) { exhausted = true; break; }
+                if (emitted == K) break;
+            }
+            advance = true;
+            // tester.hasNode<NodeT>(dda.voxel()) (tools/RayIntersector.h:609-613)
+            const int depth = acc.descend(g, root, cur.vx, cur.vy, cur.vz);
+            if (depth <= 2 - walk.lvl) {
+                if (walk.lvl == 2) {
+                    SegIn sg;
+                    sg.t0 = cur.t0; sg.t1 = cur.next(); sg.kx = acc.kx; sg.ky = acc.ky; sg.kz = acc.kz; sg.n2 = acc.n2; sg.n1 = acc.n1; sg.n0 = acc.n0;
+                    lb.segIn[sb + emitted] = sg;
+                    ++emitted;                                   // the DDA steps past the leaf before the state is saved
+                } else {
+                    const double c0 = cur.t0, c1 = cur.next();    // tester.setRange(dda.time(), dda.next()) (DDA.h:154)
+                    wsm.park(walk.lvl, cur);
+                    ++walk.lvl;
+                    cur.init(ray, c0, c1, LsWalk::shiftOf(walk.lvl));
+                    advance = false;
+                }
+            }
+        }
+        walk.pendLevel = false; walk.pendStep = false; walk.skip = false;
+        suspendRay(*r, ray, r->wdx, r->wdy, r->wdz, walk, wsm, acc, size_t(r->pix));
+        r->segBase = sb; r->segCount = emitted; r->state = exhausted ? 1u : 0u;
+    }
+}
+
+// LevelSetHDDA<TreeT,-1>::test (math/DDA.h:166-177) with LinearSearchImpl (tools/RayIntersector.h:597-657) on one leaf visit
+__global__ void __launch_bounds__(kBlockThreads)
+k_long_march(const __grid_constant__ DevGrid g, const __grid_constant__ LongBufs lb, int round, uint32_t K, float iso, float vmin, float vmax)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+    const uint32_t nLive = liveCount(lb, round + 1);                  // the rays that walked in this round
+    const uint32_t* list = liveList(lb, round + 1);
+    const unsigned long long total = (unsigned long long)nLive * K;
+    Counters c = {};
+    for (unsigned long long t = blockIdx.x * (unsigned long long)kBlockThreads + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * kBlockThreads) {
+        const uint32_t i = uint32_t(t / K), j = uint32_t(t % K);
+        LongRay* r = lb.rays + list[i];
+        if (j >= r->segCount) continue;
+        const uint32_t slot = r->segBase + j;
+        const SegIn sg = lb.segIn[slot];
+        Ray ray = r->ray;
+        TreeCursor acc; acc.kx = sg.kx; acc.ky = sg.ky; acc.kz = sg.kz; acc.n2 = sg.n2; acc.n1 = sg.n1; acc.n0 = sg.n0;
+        Stencil st; st.reset();
+        Dda dda; dda.init(ray, sg.t0, sg.t1, 0);
+        // tester.init(dda.time()) (:597-601)
+        double T0 = sg.t0, px = ray.ex + ray.dx * T0, py = ray.ey + ray.dy * T0, pz = ray.ez + ray.dz * T0;
+        st.template moveTo<false>(g, root, acc, px, py, pz, c);
+        float V0 = st.interpolation(px, py, pz) - iso;
+        bool hit = false;
+        SegOut o;
+        do {
+            // tester(dda.voxel(), dda.next()) (:620-644)
+            float V;
+            const int depth = acc.descend(g, root, dda.vx, dda.vy, dda.vz);
+            if (acc.valueAt(g, root, depth, dda.vx, dda.vy, dda.vz, V) && V > vmin && V < vmax) {
+                const double tq = dda.next();
+                px = ray.ex + ray.dx * tq; py = ray.ey + ray.dy * tq; pz = ray.ez + ray.dz * tq;
+                st.template moveTo<false>(g, root, acc, px, py, pz, c);
+                const float V1 = st.interpolation(px, py, pz) - iso;
+                if (V0 * V1 <= 0.0f) {
+                    o.time = T0 + (tq - T0) * V0 / (V0 - V1);
+                    o.ix = dda.vx; o.iy = dda.vy; o.iz = dda.vz;
+                    hit = true;
+                    break;
+                }
+                T0 = tq; V0 = V1;
+            }
+        } while (dda.step(ray, 0));
+        if (hit) {
+            // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
+            o.px = ray.ex + ray.dx * o.time; o.py = ray.ey + ray.dy * o.time; o.pz = ray.ez + ray.dz * o.time;
+            st.template moveTo<false>(g, root, acc, o.px, o.py, o.pz, c);
+            st.gradient(g, o.px, o.py, o.pz, o.gx, o.gy, o.gz);
+            lb.segOut[slot] = o;
+            atomicMin(&r->best, j);
+        }
+    }
+}
+
+// after the last round: resolve it; rays that are still alive are walked to their end in line
+template<bool AUX>
+__global__ void __launch_bounds__(kBlockThreads)
+k_long_finish(const __grid_constant__ DevGrid g, const __grid_constant__ DevShader sh, const __grid_constant__ LsParams p, float4* __restrict__ film,
+              AuxOut aux, const __grid_constant__ LongBufs lb, int round)
+{
+    __shared__ RootSmem root;
+    __shared__ WalkSmem<kBlockThreads> wsm;
+    stageRoot(g, root);
+    __syncthreads();
+    const uint32_t nLive = liveCount(lb, round);
+    const uint32_t* list = liveList(lb, round);
+    Counters c = {};
+    for (uint32_t i = blockIdx.x * kBlockThreads + threadIdx.x; i < nLive; i += gridDim.x * kBlockThreads) {
+        LongRay* r = lb.rays + (list ? list[i] : i);
+        if (round > 0 && resolveLong<AUX>(g, sh, p, film, aux, lb, r)) continue;
+        Ray ray; LsWalk walk; TreeCursor acc; Stencil st; LsHit h = {};
+        acc.reset(); st.reset();
+        resumeRay(*r, ray, walk, wsm, acc);
+        int status;
+#pragma unroll 1
+        do { status = lsAdvance<false, false, kBlockThreads>(true, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
+        writeLongPixel<AUX>(g, sh, p, film, aux, *r, status == kWalkHit, h);
+    }
 }
 
 // LevelSetRayIntersector::intersectsWS / intersectsIS on arbitrary rays (tools/RayIntersector.h:119-240)
