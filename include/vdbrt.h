@@ -42,7 +42,8 @@ enum {
     VDBRT_ERR_SPP_ZERO      = 8,  /* ValueError "pixelSamples must be larger than zero" (RayTracer.h:877-879)   */
     VDBRT_ERR_CUDA          = 9,  /* CUDA runtime error or no usable device                                     */
     VDBRT_ERR_UNSUPPORTED   = 10, /* e.g. a map that is not scale(+translate)                                   */
-    VDBRT_ERR_NOMEM         = 11
+    VDBRT_ERR_NOMEM         = 11,
+    VDBRT_ERR_IO            = 12  /* file cannot be opened / read / written, or has no such grid                     */
 };
 
 enum { VDBRT_MEM_HOST = 0, VDBRT_MEM_DEVICE = 1 };
@@ -271,6 +272,30 @@ int  vdbrt_build_levelset_spheres(vdbrt_ctx* ctx, const double* spheres, uint32_
 int  vdbrt_random_spheres(uint64_t seed, uint32_t n, double extent, double rmin, double rmax, double* out);
 /* sdfToFogVolume of an existing level-set grid (cutoff = background)                                            */
 int  vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* levelset, vdbrt_grid** out);
+
+/* ---- ingestion: NanoVDB files (replaces nanovdb::io::readGrid / readGridMetaData / writeGrid, nanovdb/io/IO.h,
+ *      for the grid this path renders; segment layout NanoVDB.h:5860-5929).  Codecs NONE and ZIP; host-only code. ---- */
+enum { VDBRT_CODEC_NONE = 0, VDBRT_CODEC_ZIP = 1 };
+typedef struct vdbrt_nvdb_meta {   /* io::FileGridMetaData (NanoVDB.h:5913-5929)                                   */
+    char     name[256];
+    uint64_t grid_bytes, file_bytes, active_voxels;
+    uint32_t grid_type;       /* nanovdb::GridType, 1 = Float                                                    */
+    uint32_t grid_class;      /* VDBRT_GRID_CLASS_*                                                              */
+    uint32_t codec, pad;
+    int32_t  index_bbox[6];
+    double   world_bbox[6];
+    double   voxel_size[3];
+} vdbrt_nvdb_meta;
+/* all grids of all segments of the file (or the one grid of a raw grid buffer); *count = number found           */
+int  vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, uint32_t* count);
+/* grid_name NULL or "": the first float grid (vdb_render's rule, openvdb_cmd/vdb_render/main.cc:771-786).  The buffer
+ * is a 32-byte aligned host allocation owned by the caller: pass it to vdbrt_upload_grid, release with vdbrt_buffer_free */
+int  vdbrt_nvdb_read(const char* path, const char* grid_name, void** buffer, uint64_t* bytes);
+int  vdbrt_nvdb_write(const char* path, const void* buffer, uint64_t bytes, uint32_t codec);
+int  vdbrt_buffer_free(void* buffer);
+/* tools::Film::savePPM (tools/RayTracer.h:300-335): P6, channel = (unsigned char)(255.0f * value), ".ppm" appended
+ * when the name has no extension                                                                                */
+int  vdbrt_film_save_ppm(const char* file_name, const float* rgba, uint32_t width, uint32_t height);
 
 #ifdef __cplusplus
 }

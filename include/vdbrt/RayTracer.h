@@ -75,6 +75,26 @@ public:
         check(vdbrt_build_levelset_torus(ctx.get(), majorRadius, minorRadius, c, voxelSize, halfWidth, &g));
         return Ptr(new FloatGrid(ctx, g));
     }
+    /// nanovdb::io::readGrid + deviceUpload (nanovdb/io/IO.h, GridHandle.h:243-327): the named grid of a .nvdb file, or the
+    /// first floating-point grid when no name is given (vdb_render's rule, openvdb_cmd/vdb_render/main.cc:771-786)
+    static Ptr read(Context& ctx, const std::string& fileName, const std::string& gridName = "")
+    {
+        void* buf = nullptr; uint64_t bytes = 0;
+        check(vdbrt_nvdb_read(fileName.c_str(), gridName.empty() ? nullptr : gridName.c_str(), &buf, &bytes));
+        vdbrt_grid* g = nullptr;
+        const int rc = vdbrt_upload_grid(ctx.get(), buf, bytes, VDBRT_MEM_HOST, &g);
+        vdbrt_buffer_free(buf);
+        check(rc);
+        return Ptr(new FloatGrid(ctx, g));
+    }
+    /// nanovdb::io::writeGrid of the grid as it lives on the device
+    void write(const std::string& fileName, uint32_t codec = VDBRT_CODEC_NONE) const
+    {
+        const vdbrt_grid_info i = info();
+        std::vector<unsigned char> host(i.bytes);
+        check(vdbrt_grid_download(mCtx->get(), mGrid, host.data(), i.bytes));
+        check(vdbrt_nvdb_write(fileName.c_str(), host.data(), i.bytes, codec));
+    }
     /// openvdb::tools::sdfToFogVolume
     Ptr sdfToFogVolume() const
     {

@@ -16,8 +16,9 @@ LS_ROUNDS_OFF = 8
 
 ERR_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "BAD_GRID", 3: "NOT_FLOAT", 4: "NOT_LEVELSET", 5: "NONUNIFORM",
-    6: "EMPTY_GRID", 7: "ISO_RANGE", 8: "SPP_ZERO", 9: "CUDA", 10: "UNSUPPORTED", 11: "NOMEM",
+    6: "EMPTY_GRID", 7: "ISO_RANGE", 8: "SPP_ZERO", 9: "CUDA", 10: "UNSUPPORTED", 11: "NOMEM", 12: "IO",
 }
+ERR_BAD_GRID, ERR_NOT_FLOAT, ERR_UNSUPPORTED, ERR_IO = 2, 3, 10, 12
 
 
 class Ray(C.Structure):
@@ -80,6 +81,15 @@ class GridInfo(C.Structure):
                 ("lower_count", C.c_uint32), ("upper_count", C.c_uint32), ("root_tiles", C.c_uint32),
                 ("index_bbox", C.c_int32 * 6), ("node_bbox", C.c_int32 * 6), ("voxel_size", C.c_double * 3),
                 ("translation", C.c_double * 3), ("background", C.c_float), ("grid_class", C.c_uint32)]
+
+
+class NvdbMeta(C.Structure):
+    _fields_ = [("name", C.c_char * 256), ("grid_bytes", C.c_uint64), ("file_bytes", C.c_uint64), ("active_voxels", C.c_uint64),
+                ("grid_type", C.c_uint32), ("grid_class", C.c_uint32), ("codec", C.c_uint32), ("pad", C.c_uint32),
+                ("index_bbox", C.c_int32 * 6), ("world_bbox", C.c_double * 6), ("voxel_size", C.c_double * 3)]
+
+
+CODEC_NONE, CODEC_ZIP = 0, 1
 
 
 def vec3(v):

@@ -24,6 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
+    "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm",
 ]
 
 
@@ -85,6 +86,11 @@ def load_library():
     L.vdbrt_ipc_import.argtypes = [vp, vp, P(vp)]
     L.vdbrt_ipc_close.argtypes = [vp, vp]
     L.vdbrt_memcpy.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    L.vdbrt_nvdb_list.argtypes = [C.c_char_p, P(abi.NvdbMeta), u32, P(u32)]
+    L.vdbrt_nvdb_read.argtypes = [C.c_char_p, C.c_char_p, P(vp), P(u64)]
+    L.vdbrt_nvdb_write.argtypes = [C.c_char_p, vp, u64, u32]
+    L.vdbrt_buffer_free.argtypes = [vp]
+    L.vdbrt_film_save_ppm.argtypes = [C.c_char_p, vp, u32, u32]
     _lib = L
     return L
 
@@ -120,11 +126,11 @@ def orthographic_camera(width, height, rotation=(0, 0, 0), translation=(0, 0, 0)
     return cam
 
 
-def vdb_render_camera(width, height, translation, lookat, rotation=(0, 0, 0)):
+def vdb_render_camera(width, height, translation, lookat, rotation=(0, 0, 0), focal=None):
     """the perspective camera exactly as vdb_render builds it: float options widened to double (SURVEY 0.8,
     openvdb_cmd/vdb_render/main.cc:62,83-87,425-436)"""
-    return perspective_camera(width, height, rotation, translation, float(np.float32(50.0)), float(np.float32(41.2136)),
-                              float(np.float32(1e-3)), FLT_MAX, lookat=lookat)
+    return perspective_camera(width, height, rotation, translation, float(np.float32(50.0 if focal is None else focal)),
+                              float(np.float32(41.2136)), float(np.float32(1e-3)), FLT_MAX, lookat=lookat)
 
 
 def jitter_table(seed=0):
@@ -313,6 +319,43 @@ class Context:
         ms, n = C.c_float(), C.c_uint32()
         _check(self.L.vdbrt_last_kernel_ms(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def nvdb_list(path):
+    """nanovdb::io::readGridMetaData: one abi.NvdbMeta per grid of the file"""
+    L = load_library()
+    n = C.c_uint32(0)
+    _check(L.vdbrt_nvdb_list(os.fsencode(path), None, 0, C.byref(n)))
+    out = (abi.NvdbMeta * max(n.value, 1))()
+    _check(L.vdbrt_nvdb_list(os.fsencode(path), out, n.value, C.byref(n)))
+    return list(out[:n.value])
+
+
+def nvdb_read(path, name=None):
+    """nanovdb::io::readGrid: the serialised grid as a 32-byte aligned uint8 array (first float grid when name is None)"""
+    L = load_library()
+    p, n = C.c_void_p(), C.c_uint64(0)
+    _check(L.vdbrt_nvdb_read(os.fsencode(path), name.encode() if name else None, C.byref(p), C.byref(n)))
+    try:
+        raw = np.empty(n.value + 32, np.uint8)
+        off = (-raw.ctypes.data) % 32
+        buf = raw[off:off + n.value]
+        C.memmove(buf.ctypes.data, p, n.value)
+    finally:
+        L.vdbrt_buffer_free(p)
+    return buf
+
+
+def nvdb_write(path, buf, codec=abi.CODEC_NONE):
+    """nanovdb::io::writeGrid of one serialised grid"""
+    buf = np.ascontiguousarray(buf, np.uint8)
+    _check(load_library().vdbrt_nvdb_write(os.fsencode(path), buf.ctypes.data, buf.size, codec))
+
+
+def film_save_ppm(path, film):
+    """tools::Film::savePPM"""
+    f = np.ascontiguousarray(film, np.float32)
+    _check(load_library().vdbrt_film_save_ppm(os.fsencode(path), f.ctypes.data, f.shape[1], f.shape[0]))
 
 
 def random_spheres(n=10000, seed=20240607, extent=1988.0, rmin=10.0, rmax=60.0):

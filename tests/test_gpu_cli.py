@@ -1,0 +1,103 @@
+"""vdbrt_render (openvdb_b200/csrc/vdbrt_render.cc): the option set of OpenVDB's vdb_render (openvdb_cmd/vdb_render/main.cc)
+over the GPU path.  The image it writes must be the PPM of the film the oracle renders with vdb_render's camera rules."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from openvdb_b200 import api, _abi as abi
+from tests import refapi
+from tests.test_nvdb_io import golden
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "openvdb_b200", "vdbrt_render")
+
+
+def read_ppm(path):
+    raw = open(path, "rb").read()
+    assert raw[:3] == b"P6\n"
+    w, h = [int(x) for x in raw.split(b"\n")[1].split()]
+    head = len(b"P6\n%d %d\n255\n" % (w, h))
+    return np.frombuffer(raw[head:], np.uint8).reshape(h, w, 3)
+
+
+def to_bits(film):
+    return (np.float32(255.0) * film[..., :3]).astype(np.uint8)          # Film::convertToBitBuffer (tools/RayTracer.h:300-317)
+
+
+def run(*args):
+    return subprocess.run([CLI] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+
+
+def test_levelset_from_a_zip_file_with_default_lookat(ctx, oracle, tmp_path):
+    """no -rotate / -lookat: the camera points at the centre of the active voxel bbox (main.cc:807-813)"""
+    buf = api.nvdb_read(golden("io_zip.nvdb"))
+    og = oracle.open(buf)
+    info = ctx.upload(buf).info
+    centre = [0.5 * (info.index_bbox[a] + info.index_bbox[3 + a]) * info.voxel_size[a] + info.translation[a] for a in range(3)]
+    W, H = 200, 120
+    out = tmp_path / "ls.ppm"
+    r = run(golden("io_zip.nvdb"), out, "-res", "%dx%d" % (W, H), "-translate", "22,25,60", "-v")
+    assert r.returncode == 0, r.stderr
+    assert "ray-tracing..." in r.stdout and "...completed in" in r.stdout and " -lookat %g,%g,%g" % tuple(centre) in r.stdout
+    cam = api.vdb_render_camera(W, H, (22.0, 25.0, 60.0), tuple(centre))
+    film = refapi.new_film(W, H)
+    oracle.render_levelset(og, cam, api.make_shader(abi.SHADER_DIFFUSE), film, threads=4)
+    assert (film[..., 0] > 0).sum() > 500
+    assert np.array_equal(read_ppm(str(out)), to_bits(film))
+
+
+def test_named_grid_normal_shader_samples_and_fov(ctx, oracle, tmp_path):
+    buf = api.nvdb_read(golden("io_two_zip.nvdb"), "ls_sphere")
+    og = oracle.open(buf)
+    W, H = 160, 100
+    out = tmp_path / "n.ppm"
+    r = run(golden("io_two_zip.nvdb"), out, "-name", "ls_sphere", "-res", "%dx%d" % (W, H), "-t", "20,20,50", "-lookat", "20,20,20",
+            "-shader", "normal", "-samples", "4", "-fov", "40")
+    assert r.returncode == 0, r.stderr
+    # fieldOfViewToFocalLength in double on the float options, stored back as float (main.cc:728-731, RayTracer.h:472-475)
+    focal = float(np.float32(float(np.float32(41.2136)) / (2.0 * np.tan(float(np.float32(40.0)) * np.pi / 360.0))))
+    cam = api.vdb_render_camera(W, H, (20.0, 20.0, 50.0), (20.0, 20.0, 20.0), focal=focal)
+    film = refapi.new_film(W, H)
+    oracle.render_levelset(og, cam, api.make_shader(abi.SHADER_NORMAL), film, spp=4, jitter=api.jitter_table(0), threads=1)
+    assert np.array_equal(read_ppm(str(out)), to_bits(film))
+
+
+def test_fog_volume_from_the_first_float_grid(ctx, oracle, tmp_path):
+    """io_two_zip.nvdb: the first float grid is the fog volume -> VolumeRender with vdb_render's defaults, -step 0.5"""
+    buf = api.nvdb_read(golden("io_two_zip.nvdb"))
+    og = oracle.open(buf)
+    W, H = 120, 80
+    out = tmp_path / "fog.ppm"
+    r = run(golden("io_two_zip.nvdb"), out, "-res", "%dx%d" % (W, H), "-t", "20,20,50", "-lookat", "20,20,20", "-step", "0.5",
+            "-absorb", "0.4,0.2,0.1", "-light", "0.2,0.5,0.1")
+    assert r.returncode == 0, r.stderr
+    cam = api.vdb_render_camera(W, H, (20.0, 20.0, 50.0), (20.0, 20.0, 20.0))
+    vo = api.vol_opts_default()
+    vo.primary_step = 0.5
+    n = np.sqrt(0.2 ** 2 + 0.5 ** 2 + 0.1 ** 2)
+    for a, v in enumerate((0.2, 0.5, 0.1)):
+        vo.light_dir[a] = v / n
+    for a, v in enumerate((0.4, 0.2, 0.1)):
+        vo.absorption[a] = v
+    film = refapi.new_film(W, H)
+    oracle.render_volume(og, cam, vo, film, threads=4)
+    assert (film[..., 3] > 0).sum() > 300
+    got, want = read_ppm(str(out)).astype(int), to_bits(film).astype(int)
+    assert np.abs(got - want).max() <= 1           # fog colours are double exp() results: 1e-4 relative -> at most one 8-bit step
+
+
+def test_generators_and_errors(tmp_path):
+    r = run("sphere:30", tmp_path / "s.ppm", "-res", "96x64", "-t", "0,0,100")
+    assert r.returncode == 0, r.stderr
+    img = read_ppm(str(tmp_path / "s.ppm"))
+    assert img.shape == (64, 96, 3) and (img[..., 0] > 0).sum() > 500
+    assert run("sphere:30", tmp_path / "s.exr").returncode != 0
+    assert run("sphere:30", tmp_path / "s.ppm", "-color", "Cd").returncode != 0
+    assert run("sphere:30", tmp_path / "s.ppm", "-isovalue", "5").returncode != 0          # outside the narrow band -> ValueError
+    assert run("sphere:30", tmp_path / "s.ppm", "-samples", "0").returncode != 0
+    assert run(tmp_path / "missing.nvdb", tmp_path / "s.ppm").returncode != 0
+    assert run("sphere:30", tmp_path / "s.ppm", "-bogus").returncode != 0
