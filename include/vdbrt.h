@@ -123,7 +123,13 @@ typedef struct vdbrt_vol_opts {
     double scattering[3];
     vdbrt_partition part;
     uint32_t flags;           /* VDBRT_ASYNC                                                                    */
-    uint32_t reserved;
+    /* EXTENSION (BASELINE config 5; the reference's VolumeRender takes one sample per pixel): samples per pixel, 0 or 1 =
+     * the reference's behaviour.  Sample 0 goes through the pixel centre, the others through the jittered offsets of
+     * LevelSetRayTracer::operator() (RayTracer.h:903-913, index n(i,j) = 2*(spp-1)*(j*W+i)); the pixel is the sum of the
+     * samples' RGBA (a sample that misses the volume's bbox is (0,0,0,0)) times float(1/spp), accumulated in float in
+     * sample order.                                                                                             */
+    uint32_t spp;
+    double   jitter[16];
 } vdbrt_vol_opts;
 
 /* tools::Film (tools/RayTracer.h:226-345): row-major RGBA float4, pixel (w,h) at [w + h*width].               */
@@ -236,6 +242,10 @@ int  vdbrt_vol_opts_default(vdbrt_vol_opts* opts);
 int  vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
                            const vdbrt_shader* shader, const vdbrt_ls_opts* opts, vdbrt_film* film, vdbrt_aux* aux);
 /* VolumeRender<VolumeRayIntersector<FloatGrid>, BoxSampler>::render (RayTracer.h:985-1070).                     */
+/* Film::RGBA::over (tools/RayTracer.h:252-259) per pixel: top = top.over(bottom), i.e. s = bottom.a*(1-top.a);
+ * rgb = top.a*top.rgb + s*bottom.rgb; a = top.a + s.  Both films in the same memory space and of the same size.
+ * (BASELINE config 5: the fog film over the level-set film.)                                                    */
+int  vdbrt_film_over(vdbrt_ctx* ctx, vdbrt_film* top, const vdbrt_film* bottom);
 int  vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam,
                          const vdbrt_vol_opts* opts, vdbrt_film* film);
 /* LevelSetRayIntersector::intersectsWS / intersectsIS on a batch of arbitrary rays (RayIntersector.h:119-240).  */

@@ -49,7 +49,7 @@ class VolOpts(C.Structure):
     _fields_ = [("primary_step", C.c_double), ("shadow_step", C.c_double), ("cutoff", C.c_double),
                 ("light_gain", C.c_double), ("light_dir", C.c_double * 3), ("light_color", C.c_double * 3),
                 ("absorption", C.c_double * 3), ("scattering", C.c_double * 3), ("part", Partition),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("spp", C.c_uint32), ("jitter", C.c_double * 16)]
 
 
 class Film(C.Structure):

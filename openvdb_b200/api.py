@@ -24,7 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
-    "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm",
+    "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.vdbrt_nvdb_write.argtypes = [C.c_char_p, vp, u64, u32]
     L.vdbrt_buffer_free.argtypes = [vp]
     L.vdbrt_film_save_ppm.argtypes = [C.c_char_p, vp, u32, u32]
+    L.vdbrt_film_over.argtypes = [vp, P(abi.Film), P(abi.Film)]
     _lib = L
     return L
 
@@ -139,9 +140,13 @@ def jitter_table(seed=0):
     return np.array(out[:], np.float64)
 
 
-def vol_opts_default():
+def vol_opts_default(spp=1, seed=0):
+    """VolumeRender's defaults (tools/RayTracer.h:929-936); spp > 1 is this library's extension (include/vdbrt.h)"""
     o = abi.VolOpts()
     _check(load_library().vdbrt_vol_opts_default(C.byref(o)))
+    if spp > 1:
+        o.spp = spp
+        o.jitter = (C.c_double * 16)(*jitter_table(seed))
     return o
 
 
@@ -285,6 +290,11 @@ class Context:
         f = self._film_pod(film, width, height, memspace, bg)
         _check(self.L.vdbrt_render_levelset(self.handle, grid.handle, C.byref(cam), C.byref(shader), C.byref(o), C.byref(f),
                                             C.byref(aux) if aux is not None else None))
+
+    def film_over(self, top, bottom, width=None, height=None, memspace=abi.MEM_HOST):
+        """top = top.over(bottom), Film::RGBA::over per pixel"""
+        t, b = self._film_pod(top, width, height, memspace), self._film_pod(bottom, width, height, memspace)
+        _check(self.L.vdbrt_film_over(self.handle, C.byref(t), C.byref(b)))
 
     def render_volume(self, grid, cam, opts, film, width=None, height=None, memspace=abi.MEM_HOST):
         f = self._film_pod(film, width, height, memspace)

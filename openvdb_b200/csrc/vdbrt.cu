@@ -183,6 +183,9 @@ void vol_params(const vdbrt_vol_opts* o, VolParams& p)
         p.ext[a] = -o->scattering[a] - o->absorption[a];                                        // tools/RayTracer.h:996
         p.albedo[a] = o->light_color[a] * o->scattering[a] / (o->scattering[a] + o->absorption[a]); // :997
     }
+    p.sub = o->spp > 1 ? o->spp - 1 : 0u;
+    p.frac = 1.0f / (1.0f + float(p.sub));
+    for (int i = 0; i < 16; ++i) p.jitter[i] = o->jitter[i];
 }
 
 } // namespace
@@ -579,6 +582,35 @@ int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     if (int rc = launchVolume(ctx, grid, cam, opts, film->width, film->height, dFilm, nullptr)) return rc;
     if (host) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (host || !(opts->flags & VDBRT_ASYNC)) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VDBRT_OK;
+}
+
+int vdbrt_film_over(vdbrt_ctx* ctx, vdbrt_film* top, const vdbrt_film* bottom)
+{
+    if (!ctx || !top || !bottom || !top->pixels || !bottom->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (top->width != bottom->width || top->height != bottom->height || top->memspace != bottom->memspace)
+        return setError(VDBRT_ERR_INVALID_ARG, "films differ in size or memory space");
+    DeviceGuard guard(ctx->device);
+    const size_t npx = size_t(top->width) * top->height;
+    float4* dTop = reinterpret_cast<float4*>(top->pixels);
+    const float4* dBot = reinterpret_cast<const float4*>(bottom->pixels);
+    const bool host = top->memspace == VDBRT_MEM_HOST;
+    if (host) {
+        if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
+        if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->film, top->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->io, bottom->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        dTop = static_cast<float4*>(ctx->film); dBot = static_cast<const float4*>(ctx->io);
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    k_film_over<<<unsigned((npx + 255) / 256), 256, 0, ctx->stream>>>(dTop, dBot, npx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = 1;
+    if (host) {
+        CUDA_TRY(cudaMemcpyAsync(top->pixels, dTop, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     return VDBRT_OK;
 }
 

@@ -634,6 +634,8 @@ struct VolParams {
     double pstep, sstep, cutoff, gain;
     double light[3];            // world-space unit light direction
     double ext[3], albedo[3];   // extinction = -scattering-absorption; albedo = lightColor*scattering/(scattering+absorption)
+    uint32_t sub; float frac;   // samples per pixel - 1, 1/samples (EXTENSION: the reference's VolumeRender has one sample per pixel)
+    double jitter[16];
 };
 
 // Per-lane state machine, warp-synchronous like the level-set kernel.  A lane works on its primary ray or on a shadow
@@ -676,7 +678,11 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
     int mode = kFogIdle, pendExp = 0;
     int span = 0;                        // 0: looking for a span, 1: inside an open span (end >= walk.bound), 2: span closed at tend
     bool drained = false;
+    bool needRay = false;                // the lane's pixel wants its next sample
     size_t pix = 0;
+    uint32_t k = 0;                      // samples of the pixel taken so far
+    unsigned long long n = 0;            // jitter index, as in LevelSetRayTracer::operator() (tools/RayTracer.h:903-913)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     Ray ray; SpanWalk walk;
     ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0;
     walk.begin(ray); walk.lvl = -1;
@@ -689,7 +695,7 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
     for (;;) {
         __syncwarp();
         // (1) a warp takes a fresh 8x4 tile when all its lanes are done
-        const unsigned idle = __ballot_sync(0xffffffffu, mode == kFogIdle);
+        const unsigned idle = __ballot_sync(0xffffffffu, mode == kFogIdle && !needRay);
         if (idle == 0xffffffffu) {
             if (drained) break;
             unsigned item = 0;
@@ -699,14 +705,23 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
             uint32_t px, py;
             if (ticketToPixel(tm, item * 32u + lane, px, py)) {
                 pix = size_t(py) * tm.width + px;
-                cameraRay(cam, px, py, 0.5, 0.5, ray);
-                if (COUNT) ++c.rays;
-                worldToIndex(g, ray);
-                if (clipRay(ray, g, 1)) {                                // mPrimary->setWorldRay(pRay) (:1022)
-                    Tx = Ty = Tz = 1.0; Lx = Ly = Lz = 0.0;
-                    walk.begin(ray); mode = kFogPrimary; pendExp = 0; span = 0;
-                } else film[pix] = make_float4(0.f, 0.f, 0.f, 0.f);      // bg.a = bg.r = bg.g = bg.b = 0 (:1020), continue
+                k = 0; n = 2ull * p.sub * pix; needRay = true;
             }
+        }
+        bool fin = false;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);                   // bg.a = bg.r = bg.g = bg.b = 0 (:1020): a sample that misses the bbox
+        // (1b) the next sample of the lane's pixel: the centre first, then the jittered offsets of LevelSetRayTracer (:907-909)
+        if (needRay) {
+            needRay = false;
+            const bool first = k == 0;
+            cameraRay(cam, uint32_t(pix % tm.width), uint32_t(pix / tm.width), first ? 0.5 : p.jitter[n & 15], first ? 0.5 : p.jitter[(n + 1) & 15], ray);
+            if (!first) n += 2;
+            if (COUNT) ++c.rays;
+            worldToIndex(g, ray);
+            if (clipRay(ray, g, 1)) {                                    // mPrimary->setWorldRay(pRay) (:1022)
+                Tx = Ty = Tz = 1.0; Lx = Ly = Lz = 0.0;
+                walk.begin(ray); mode = kFogPrimary; pendExp = 0; span = 0;
+            } else fin = true;                                           // `continue` (:1022): the sample stays (0,0,0,0)
         }
         __syncwarp();
         // for (pT = pStep*ceil(t0/pStep); pT <= pT1; pT += pStep): past the end of a closed span -> look for the next one
@@ -719,7 +734,7 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
         const bool runW = nW >= kFogBatch || (nM < kFogBatch && nE < kFogBatch);
         const bool runM = nM >= kFogBatch || (nW < kFogBatch && nE < kFogBatch);
         const bool runE = nE >= kFogBatch || (nW < kFogBatch && nM < kFogBatch);
-        bool lum = false, fin = false;
+        bool lum = false;
         // (2) walk: one unit of VolumeHDDA::hits for the active ray
         if (walking && runW) {
             double a, b;
@@ -805,15 +820,30 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                 mode = kFogPrimary;
             }
         }
-        // (6) Pixel (:1063-1067)
+        // (6) Pixel (:1063-1067); with more than one sample the results are summed in order and scaled by 1/samples
         if (fin) {
-            const float4 out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
-            if (COUNT && out.w > 0.f) ++c.hits;
-            film[pix] = out;
+            if (mode != kFogIdle) {
+                out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
+                if (COUNT && out.w > 0.f) ++c.hits;
+            }
+            if (k == 0) acc = out;
+            else { acc.x += out.x; acc.y += out.y; acc.z += out.z; acc.w += out.w; }
             mode = kFogIdle; pendExp = 0;
+            if (++k > p.sub) film[pix] = make_float4(acc.x * p.frac, acc.y * p.frac, acc.z * p.frac, acc.w * p.frac);
+            else needRay = true;
         }
     }
     if (COUNT) flushCounters(c, counters);
+}
+
+// Film::RGBA::over (tools/RayTracer.h:252-259), one pixel per thread: 32 B read + 16 B written per pixel, HBM-bound
+__global__ void k_film_over(float4* __restrict__ top, const float4* __restrict__ bottom, size_t n)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float4 t = top[i], b = bottom[i];
+    const float s = b.w * (1.0f - t.w);
+    top[i] = make_float4(t.w * t.x + s * b.x, t.w * t.y + s * b.y, t.w * t.z + s * b.z, t.w + s);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -740,13 +740,22 @@ int oracle_render_volume(const oracle_grid* g, const vdbrt_camera* cam, const vd
         std::vector<TimeSpan> pTS, sTS;
         Ray sRay; sRay.eye = Vec3{0, 0, 0}; sRay.setDir(Vec3{o->light_dir[0], o->light_dir[1], o->light_dir[2]});
         sRay.t0 = 1e-9; sRay.t1 = DBL_MAX;                                                              // Ray ctor defaults (Ray.h:57-63)
+        // EXTENSION (include/vdbrt.h, vdbrt_vol_opts::spp): sample 0 through the pixel centre, the others through the jittered
+        // offsets of LevelSetRayTracer::operator() (tools/RayTracer.h:903-913); pixel = (sum of the samples' RGBA) * float(1/spp)
+        const uint32_t sub = o->spp > 1 ? o->spp - 1 : 0u;
+        const float frac = 1.0f / (1.0f + float(sub));
         for (uint32_t j = j0; j < j1; ++j) for (uint32_t i = 0; i < W; ++i) {
             if (!ownsPixel(o->part, i, j, W)) continue;
-            float* px = film->pixels + 4 * (size_t(j) * W + i);
-            px[0] = px[1] = px[2] = px[3] = 0.f;                                                        // :1020
-            const Ray pRay = cameraRay(*cam, i, j, 0.5, 0.5);
+            const size_t pixel = size_t(j) * W + i;
+            float* px = film->pixels + 4 * pixel;
+            RGBA acc{0.f, 0.f, 0.f, 0.f};
+            uint64_t n = uint64_t(2) * sub * pixel;
+            for (uint32_t smp = 0; smp <= sub; ++smp) {
+            RGBA out{0.f, 0.f, 0.f, 0.f};                                                               // :1020
+            const Ray pRay = smp == 0 ? cameraRay(*cam, i, j, 0.5, 0.5) : cameraRay(*cam, i, j, o->jitter[n & 15], o->jitter[(n + 1) & 15]);
+            if (smp > 0) n += 2;
             ++c.rays;
-            if (!primary.setWorldRay(pRay)) continue;
+            if (primary.setWorldRay(pRay)) {
             Vec3 pTrans{1.0, 1.0, 1.0}, pLumi{0.0, 0.0, 0.0};
             primary.hits(pTS);
             bool done = false;
@@ -779,12 +788,29 @@ int oracle_render_volume(const oracle_grid* g, const vdbrt_camera* cam, const vd
                     if (pTrans.x * pTrans.x + pTrans.y * pTrans.y + pTrans.z * pTrans.z < cutoff) { done = true; break; }     // goto Pixel
                 }
             }
-            px[0] = float(pLumi.x); px[1] = float(pLumi.y); px[2] = float(pLumi.z);
-            px[3] = float(1.0f - (pTrans.x + pTrans.y + pTrans.z) / 3.0f);
-            if (px[3] > 0.f) ++c.hits;
+            out.r = float(pLumi.x); out.g = float(pLumi.y); out.b = float(pLumi.z);
+            out.a = float(1.0f - (pTrans.x + pTrans.y + pTrans.z) / 3.0f);
+            if (out.a > 0.f) ++c.hits;
+            }
+            if (smp == 0) acc = out;
+            else { acc.r += out.r; acc.g += out.g; acc.b += out.b; acc.a += out.a; }
+            }
+            px[0] = acc.r * frac; px[1] = acc.g * frac; px[2] = acc.b * frac; px[3] = acc.a * frac;
         }
     });
     addCounters(ctr, counters);
+    return VDBRT_OK;
+}
+
+// Film::RGBA::over (tools/RayTracer.h:252-259) per pixel: top = top.over(bottom)
+int oracle_film_over(float* top, const float* bottom, uint64_t pixels)
+{
+    for (uint64_t i = 0; i < pixels; ++i) {
+        float* t = top + 4 * i; const float* b = bottom + 4 * i;
+        const float s = b[3] * (1.0f - t[3]);
+        t[0] = t[3] * t[0] + s * b[0]; t[1] = t[3] * t[1] + s * b[1]; t[2] = t[3] * t[2] + s * b[2];
+        t[3] = t[3] + s;
+    }
     return VDBRT_OK;
 }
 

@@ -34,6 +34,7 @@ int  oracle_intersect_levelset(const oracle_grid* g, const vdbrt_ray* rays, uint
 int  oracle_volume_spans(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, uint32_t max_spans,
                          double* spans, int32_t* counts);
 /* BaseCamera::getRay for pixels ij[2k],ij[2k+1] with offsets (NULL -> 0.5,0.5) */
+int  oracle_film_over(float* top, const float* bottom, uint64_t pixels);     /* Film::RGBA::over per pixel, top = top.over(bottom) */
 int  oracle_camera_rays(const vdbrt_camera* cam, const uint32_t* ij, const double* offsets, uint64_t n, vdbrt_ray* rays);
 /* math::DDA<Ray,Log2Dim> trace for the TestRay.testDDA known answers: writes up to max_steps records of
  * {time, next, voxel x,y,z} (5 doubles each) and returns the number of records                                 */

@@ -306,6 +306,7 @@ class Oracle:
         L.oracle_intersect_levelset.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_float, vp]
         L.oracle_volume_spans.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
         L.oracle_camera_rays.argtypes = [C.POINTER(abi.Camera), vp, vp, C.c_uint64, vp]
+        L.oracle_film_over.argtypes = [vp, vp, C.c_uint64]
         L.oracle_dda_trace.argtypes = [C.POINTER(abi.Ray), C.c_int, C.c_int, vp]
         L.oracle_ray_clip.argtypes = [C.POINTER(abi.Ray), vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         self._keep = {}
@@ -364,6 +365,11 @@ class Oracle:
         self.check(self.L.oracle_render_volume(g, C.byref(cam), C.byref(opts), C.byref(f),
                                                C.byref(ctr) if counters else None, threads))
         return ctr
+
+    def film_over(self, top, bottom):
+        """top = top.over(bottom), Film::RGBA::over per pixel (tools/RayTracer.h:252-259)"""
+        assert top.shape == bottom.shape and top.dtype == np.float32 and bottom.dtype == np.float32
+        self.check(self.L.oracle_film_over(top.ctypes.data, np.ascontiguousarray(bottom).ctypes.data, top.shape[0] * top.shape[1]))
 
     def intersect(self, g, rays, space=abi.SPACE_WORLD, iso=0.0):
         n = len(rays)
