@@ -169,7 +169,8 @@ def cpu_reference(R, r, W, H, steps, warmup, sample_div=1, gpu_film=None):
 
 def extras(ctx, api, abi, torch):
     """informational timings of the other BASELINE configs (device-resident film, CUDA-event kernel time, 3 frames each):
-    C3 fog sphere (1024^3 bbox, step 0.5, 1920x1080) and C4 union of 10 000 spheres at 3840x2160 ('ms per 4K frame')"""
+    C3 fog sphere (1024^3 bbox, step 0.5, 1920x1080), C4 union of 10 000 spheres at 3840x2160 ('ms per 4K frame') and one
+    GPU's share of C5 (level set + fog overlay, 16 samples per pixel)"""
     out = {}
     ls = ctx.build_sphere(509.0)
     fog = ctx.build_fog(ls)
@@ -198,6 +199,30 @@ def extras(ctx, api, abi, torch):
     out["c4_levelset_4k"] = {"ms_per_frame": float(np.median(ms[1:])), "Mrays_per_s": W * H / float(np.median(ms[1:])) / 1e3,
                              "grid_gb": g.info.bytes / 1e9, "active_voxels": int(g.info.active_voxels),
                              "hit_pixels": int((film[..., :3].sum(dim=2) > 0).sum().item())}
+    # C5 (extension): the same union under its own fog volume, 16 jittered samples per pixel, fog.over(level set).
+    # The config names the whole 8-GPU box: this one GPU renders rank 0's share of an 8-way tile split, once.
+    try:
+        fog = ctx.build_fog(g)
+        spp, share = 16, 8
+        part = api.partition(0, share, TILE_W, TILE_H)
+        f2 = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        ctx.render_levelset(g, cam, api.make_shader(abi.SHADER_DIFFUSE), film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE,
+                            opts=ctx.ls_opts(spp=spp, seed=0, uniform_bg=True, part=part))
+        ms_ls = ctx.last_kernel_ms()[0]
+        vo = api.vol_opts_default(spp=spp, seed=0)
+        vo.primary_step = 0.5
+        vo.part = part
+        ctx.render_volume(fog, cam, vo, f2.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE)
+        ms_fog = ctx.last_kernel_ms()[0]
+        ctx.film_over(f2.data_ptr(), film.data_ptr(), width=W, height=H, memspace=abi.MEM_DEVICE)
+        ms_over = ctx.last_kernel_ms()[0]
+        rays = W * H * spp // share
+        out["c5_overlay_4k_16spp_rank0_of_8"] = {"ms_level_set": ms_ls, "ms_fog": ms_fog, "ms_over_whole_film": ms_over,
+                                                 "ms_per_frame": ms_ls + ms_fog + ms_over, "primary_rays": 2 * rays,
+                                                 "Mrays_per_s": 2 * rays / (ms_ls + ms_fog + ms_over) / 1e3, "fog_grid_gb": fog.info.bytes / 1e9}
+        fog.free()
+    except Exception as e:
+        out["c5_overlay_4k_16spp_rank0_of_8"] = {"error": str(e)}
     g.free()
     return out
 

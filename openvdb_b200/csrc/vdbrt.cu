@@ -173,6 +173,17 @@ void ls_params(const vdbrt_grid* grid, const vdbrt_ls_opts* o, const vdbrt_film*
     p.uniform_bg = (o->flags & VDBRT_LS_UNIFORM_BG) ? 1u : 0u;
     for (int i = 0; i < 4; ++i) p.bg[i] = film ? film->bg_rgba[i] : 0.f;
     for (int i = 0; i < 16; ++i) p.jitter[i] = o->jitter[i];
+    p.bg_film = nullptr;
+}
+
+// A pinned host film is written by the kernels directly (unified addressing: the stores travel over PCIe while the rest of
+// the frame is still being traced), so no device->host copy of the film follows the render.  Returns the device alias of
+// the host pointer, or null for pageable memory.
+float4* pinnedAlias(const void* host)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? static_cast<float4*>(a.devicePointer) : nullptr;
 }
 
 void vol_params(const vdbrt_vol_opts* o, VolParams& p)
@@ -383,10 +394,11 @@ static int longBuffers(vdbrt_ctx* ctx, size_t slots, LongBufs& lb)
 }
 
 static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_shader* shader,
-                          const vdbrt_ls_opts* opts, const vdbrt_film* film, float4* dFilm, const AuxOut& aux, bool wantAux,
+                          const vdbrt_ls_opts* opts, const vdbrt_film* film, float4* dFilm, const float4* dBg, const AuxOut& aux, bool wantAux,
                           unsigned long long* dCounters)
 {
     LsParams p; ls_params(grid, opts, film, p);
+    p.bg_film = dBg;
     const TileMap tm = makeTileMap(film->width, film->height, opts->part.tile_w, opts->part.tile_h, opts->part.rank, opts->part.count);
     DevShader sh;
     sh.kind = shader->kind; sh.r = shader->rgba[0]; sh.g = shader->rgba[1]; sh.b = shader->rgba[2]; sh.a = shader->rgba[3];
@@ -465,15 +477,22 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     const size_t npx = size_t(film->width) * film->height;
     const bool host = film->memspace == VDBRT_MEM_HOST;
     float4* dFilm = reinterpret_cast<float4*>(film->pixels);
+    const float4* dBg = dFilm;
+    bool copyBack = false;
     if (host) {
-        if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
-        dFilm = static_cast<float4*>(ctx->film);
-        // level-set misses keep the previous pixel, so the film is an input too (tools/RayTracer.h:908)
-        if (!(opts->flags & VDBRT_LS_UNIFORM_BG)) CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
-        else if (opts->part.count > 1) {
-            // other ranks' pixels must come back unchanged: start from the caller's film
-            CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        // level-set misses keep the previous pixel, so the film is an input too (tools/RayTracer.h:908): unless it is known
+        // to be uniform, it is staged on the device for the kernels to read.  The OUTPUT goes straight to a pinned host film
+        // (only the pixels this rank owns are written, the rest of the caller's film stays as it is); a pageable film takes
+        // the staging buffer and one device->host copy.
+        const bool uniform = (opts->flags & VDBRT_LS_UNIFORM_BG) != 0;
+        float4* alias = pinnedAlias(film->pixels);
+        if (!uniform || !alias) {
+            if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
+            if (!uniform || opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(ctx->film, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
         }
+        dBg = uniform ? nullptr : static_cast<const float4*>(ctx->film);
+        if (alias) dFilm = alias;
+        else { dFilm = static_cast<float4*>(ctx->film); copyBack = true; }
     }
     AuxOut a = {};
     const bool wantAux = aux && (aux->hit || aux->ijk || aux->t_index || aux->t_world || aux->xyz || aux->nml);
@@ -495,9 +514,9 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
             a.hit = aux->hit; a.ijk = aux->ijk; a.t_index = aux->t_index; a.t_world = aux->t_world; a.xyz = aux->xyz; a.nml = aux->nml;
         }
     }
-    if (int rc = launchLevelSet(ctx, grid, cam, shader, opts, film, dFilm, a, wantAux, nullptr)) return rc;
+    if (int rc = launchLevelSet(ctx, grid, cam, shader, opts, film, dFilm, dBg, a, wantAux, nullptr)) return rc;
     if (host) {
-        CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (copyBack) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
         if (wantAux) {
             const uint8_t* b = static_cast<const uint8_t*>(ctx->aux);
             if (aux->hit) CUDA_TRY(cudaMemcpyAsync(aux->hit, b, npx, cudaMemcpyDeviceToHost, ctx->stream));
@@ -526,7 +545,7 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     vdbrt_film film = {}; film.width = cam->width; film.height = cam->height;
     vdbrt_shader sh = {}; sh.kind = VDBRT_SHADER_DIFFUSE; sh.rgba[0] = sh.rgba[1] = sh.rgba[2] = sh.rgba[3] = 1.f;
     AuxOut a = {};
-    if (int rc = launchLevelSet(ctx, grid, cam, &sh, opts, &film, static_cast<float4*>(ctx->io), a, false, dC)) return rc;
+    if (int rc = launchLevelSet(ctx, grid, cam, &sh, opts, &film, static_cast<float4*>(ctx->io), static_cast<const float4*>(ctx->io), a, false, dC)) return rc;
     unsigned long long h[16];
     CUDA_TRY(cudaMemcpyAsync(h, dC, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -573,14 +592,19 @@ int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     const size_t npx = size_t(film->width) * film->height;
     const bool host = film->memspace == VDBRT_MEM_HOST;
     float4* dFilm = reinterpret_cast<float4*>(film->pixels);
+    bool copyBack = false;
     if (host) {
-        if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
-        dFilm = static_cast<float4*>(ctx->film);
-        // every owned pixel is overwritten (tools/RayTracer.h:1020); only a partitioned render needs the old film
-        if (opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        // every owned pixel is overwritten (tools/RayTracer.h:1020) and nothing is read: a pinned film is written in place by
+        // the kernel; a pageable one is staged (a partitioned render then needs the old film for the pixels of other ranks)
+        if (float4* alias = pinnedAlias(film->pixels)) dFilm = alias;
+        else {
+            if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
+            dFilm = static_cast<float4*>(ctx->film); copyBack = true;
+            if (opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(dFilm, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     if (int rc = launchVolume(ctx, grid, cam, opts, film->width, film->height, dFilm, nullptr)) return rc;
-    if (host) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (copyBack) CUDA_TRY(cudaMemcpyAsync(film->pixels, dFilm, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (host || !(opts->flags & VDBRT_ASYNC)) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VDBRT_OK;
 }

@@ -55,7 +55,8 @@ __device__ __forceinline__ bool nextPixel(const TileMap& m, unsigned int* queue,
 }
 
 struct AuxOut { uint8_t* hit; int32_t* ijk; double* t_index; double* t_world; double* xyz; double* nml; };
-struct LsParams { float iso, vmin, vmax, frac; uint32_t sub; uint32_t uniform_bg; float bg[4]; double jitter[16]; };
+struct LsParams { float iso, vmin, vmax, frac; uint32_t sub; uint32_t uniform_bg; float bg[4]; double jitter[16];
+                  const float4* bg_film; };   // where a miss reads its old pixel from (the film itself, or the device copy of a host film)
 
 __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long long* out)
 {
@@ -207,7 +208,7 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
 template<bool AUX, bool COUNT, bool LONG>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
-                  const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* __restrict__ film,
+                  const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
                   AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb)
 {
     __shared__ RootSmem root;
@@ -329,7 +330,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (hit) {
                 if (COUNT) ++c.hits;
                 s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, k == 0);
-            } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
+            } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
             if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
             if (k == 0) col = s;
             else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
@@ -358,7 +359,7 @@ __device__ __forceinline__ void writeLongPixel(const DevGrid& g, const DevShader
                                                bool hit, const LsHit& h)
 {
     const size_t pix = r.pix;
-    float4 s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : film[pix];
+    float4 s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
     if (hit) s = shadeHit<AUX>(g, sh, h, r.ray, r.wdx, r.wdy, r.wdz, pix, aux, true);
     if (AUX && aux.hit) aux.hit[pix] = hit ? 1 : 0;
     film[pix] = make_float4(s.x * p.frac, s.y * p.frac, s.z * p.frac, 1.0f);      // one sample per pixel: c = s, bg = c*frac, alpha 1
