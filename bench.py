@@ -423,8 +423,14 @@ def main():
                        if world > 1 else "single GPU",
                        "l2": "grid (%.2f GB) is larger than the 126 MB L2; no explicit flush" % (grid.info.bytes / 1e9),
                        "hit_pixels": hits},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": film_bytes, "d2h_bytes_per_step": film_bytes,
-                    "ms_per_step": float(te[0]) * 1e3 / args.steps},
+            # single GPU: the pinned host film is read (old pixel of every miss) and written (every pixel) in place by the kernels;
+            # multi GPU: the film is copied into and out of rank 0's shared device film
+            "e2e": {"value": e2e_value, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": (W * H - hits) * 16 if world == 1 else film_bytes, "d2h_bytes_per_step": film_bytes,
+                    "ms_per_step": float(te[0]) * 1e3 / args.steps,
+                    "how": ("vdbrt_render_levelset on a pinned host film (tools::Film): misses read their old pixel and all pixels are "
+                            "stored over PCIe by the render kernel itself, no staging copies") if world == 1 else
+                           "H2D of the film into rank 0's shared device film, partitioned render with peer stores, D2H of the frame"},
             "gpu_launches": args.steps * launches_per_frame,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_render_levelset" + (" + %d long-ray round kernels (k_long_scout/march/finish)" % (launches_per_frame - 1) if launches_per_frame > 1 else ""),

@@ -480,19 +480,18 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     const float4* dBg = dFilm;
     bool copyBack = false;
     if (host) {
-        // level-set misses keep the previous pixel, so the film is an input too (tools/RayTracer.h:908): unless it is known
-        // to be uniform, it is staged on the device for the kernels to read.  The OUTPUT goes straight to a pinned host film
-        // (only the pixels this rank owns are written, the rest of the caller's film stays as it is); a pageable film takes
-        // the staging buffer and one device->host copy.
+        // level-set misses keep the previous pixel, so the film is an input too (tools/RayTracer.h:908).  A PINNED host film is
+        // used in place: a miss reads its old pixel over PCIe right before the same thread overwrites it (what the reference's
+        // `bg = mCamera->pixel(i,j)` does), every owned pixel is stored straight to host memory while the rest of the frame is
+        // still being traced, and the pixels of other ranks are never touched -- no film copy in either direction.  A pageable
+        // film is staged on the device: one copy in (unless the old film is known to be uniform), one copy out.
         const bool uniform = (opts->flags & VDBRT_LS_UNIFORM_BG) != 0;
-        float4* alias = pinnedAlias(film->pixels);
-        if (!uniform || !alias) {
+        if (float4* alias = pinnedAlias(film->pixels)) { dFilm = alias; dBg = uniform ? nullptr : alias; }
+        else {
             if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
             if (!uniform || opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(ctx->film, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+            dFilm = static_cast<float4*>(ctx->film); dBg = uniform ? nullptr : dFilm; copyBack = true;
         }
-        dBg = uniform ? nullptr : static_cast<const float4*>(ctx->film);
-        if (alias) dFilm = alias;
-        else { dFilm = static_cast<float4*>(ctx->film); copyBack = true; }
     }
     AuxOut a = {};
     const bool wantAux = aux && (aux->hit || aux->ijk || aux->t_index || aux->t_world || aux->xyz || aux->nml);
