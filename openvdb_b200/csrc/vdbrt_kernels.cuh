@@ -241,25 +241,12 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     const float tilesPerWarp = float(tm.items) / float(gridDim.x * (kBlockThreads / 32));
     uint32_t spent = 0, limit = lb.budget;
     bool longFull = false;              // no room left for suspended rays: finish everything in line
+    // Two nested loops.  The OUTER one runs once per refill: it takes tickets from the queue and sets up the next ray of
+    // every lane that needs one (the only place the ray registers are written).  The INNER one advances the running rays
+    // and finishes the ones that end, until a lane wants its next ray or no lane is running: nothing of the outer loop's
+    // bookkeeping is executed per traversal step.
     for (;;) {
         __syncwarp();
-        if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
-        // (0) the tile has used up its budget: suspend the rays that are still running (they continue in the long-ray rounds)
-        if (LONG && ++spent > limit && !longFull) {
-            const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
-            const unsigned m = __ballot_sync(0xffffffffu, sus);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
-                if (base + __popc(m) > lb.capLong) longFull = true;
-                if (sus && idx < lb.capLong) {
-                    suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
-                    rayOn = false; hasPix = false;
-                }
-            }
-        }
         // (1) refill idle lanes from the queue
         const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
         if (COUNT && idle == 0xffffffffu && lane == 0) {
@@ -276,8 +263,8 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (lane == 0) {
                 if (spent > 1u) { atomicAdd(&lb.ctl->spent, (unsigned long long)(spent < limit ? spent : limit)); atomicAdd(&lb.ctl->tiles, 1u); }
                 const unsigned long long sum = *reinterpret_cast<volatile unsigned long long*>(&lb.ctl->spent);
-                const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&lb.ctl->tiles);
-                m = n >= 64u ? uint32_t(0.01f * float(lb.factor) * tilesPerWarp * float(sum) / float(n)) : 0u;
+                const uint32_t nt = *reinterpret_cast<volatile uint32_t*>(&lb.ctl->tiles);
+                m = nt >= 64u ? uint32_t(0.01f * float(lb.factor) * tilesPerWarp * float(sum) / float(nt)) : 0u;
             }
             m = __shfl_sync(0xffffffffu, m, 0);
             limit = m > lb.budget ? m : lb.budget;
@@ -311,34 +298,58 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (clipRay(ray, g, 0)) { walk.begin(ray); rayOn = true; }
             else status = kWalkMiss;
         }
-        __syncwarp();
-        // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
-        // The rare phases run when enough lanes wait for them, or when too few lanes could do anything else.
-        {
-            const int nA = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendLevel));
-            const int nC = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendInterp != 0));
-            const int nRun = __popc(__ballot_sync(0xffffffffu, rayOn && walk.runnable()));
-            const bool runA = nA >= kBatchLevel || nRun < kBatchRunnable, runC = nC >= kBatchInterp || nRun < kBatchRunnable;
-            const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, runA, runC, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
-            if (rayOn) status = r;
-        }
-        __syncwarp();
-        // (4) a ray ended: shade / composite, then next sample or write the pixel
-        if (status != kWalkContinue) {
-            const bool hit = status == kWalkHit;
-            float4 s;
-            if (hit) {
-                if (COUNT) ++c.hits;
-                s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, k == 0);
-            } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
-            if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
-            if (k == 0) col = s;
-            else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
-            rayOn = false;
-            if (++k > p.sub) {
-                film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
-                hasPix = false;
+#pragma unroll 1
+        for (;;) {
+            __syncwarp();
+            if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
+            // (0) the tile has used up its budget: suspend the rays that are still running (they continue in the long-ray rounds)
+            if (LONG && ++spent > limit && !longFull) {
+                const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
+                const unsigned m = __ballot_sync(0xffffffffu, sus);
+                if (m) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
+                    if (base + __popc(m) > lb.capLong) longFull = true;
+                    if (sus && idx < lb.capLong) {
+                        suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
+                        rayOn = false; hasPix = false;
+                    }
+                }
             }
+            // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
+            // The rare phases run when enough lanes wait for them, or when too few lanes could do anything else.
+            {
+                const int nA = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendLevel));
+                const int nC = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendInterp != 0));
+                const int nRun = __popc(__ballot_sync(0xffffffffu, rayOn && walk.runnable()));
+                const bool runA = nA >= kBatchLevel || nRun < kBatchRunnable, runC = nC >= kBatchInterp || nRun < kBatchRunnable;
+                const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, runA, runC, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
+                if (rayOn) status = r;
+            }
+            __syncwarp();
+            // (4) a ray ended: shade / composite, then next sample or write the pixel
+            if (status != kWalkContinue) {
+                const bool hit = status == kWalkHit;
+                float4 s;
+                if (hit) {
+                    if (COUNT) ++c.hits;
+                    s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, k == 0);
+                } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
+                if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
+                if (k == 0) col = s;
+                else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+                rayOn = false;
+                if (++k > p.sub) {
+                    film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+                    hasPix = false;
+                }
+                status = kWalkContinue;
+            }
+            // back to the outer loop when a lane wants its next ray (or fresh pixels), or when nothing is running any more
+            const unsigned running = __ballot_sync(0xffffffffu, rayOn);
+            if (running == 0u || (kRefillThreshold < 32 && __popc(running) <= 32 - kRefillThreshold) || __any_sync(0xffffffffu, hasPix && !rayOn)) break;
         }
     }
     if (COUNT) flushCounters(c, counters);
