@@ -134,7 +134,7 @@ struct TreeCursor {
                 const uint32_t n = upperOffset(x, y, z);
                 const unsigned long long word = ldg64(u + kUpperCMask + 8u * (n >> 6));
                 const long long ent = ldgs64(u + kUpperTable + 8u * n);
-                if ((word >> (n & 63u)) & 1ull) n1 = uint32_t((((unsigned long long)n2 << 5) + (unsigned long long)ent) >> 5);
+                if ((word >> (n & 63u)) & 1ull) n1 = n2 + uint32_t(int(ent >> 5));      // offsets are multiples of 32
             }
         }
         n0 = 0u;
@@ -143,7 +143,7 @@ struct TreeCursor {
             const uint32_t n = lowerOffset(x, y, z);
             const unsigned long long word = ldg64(l + kLowerCMask + 8u * (n >> 6));
             const long long ent = ldgs64(l + kLowerTable + 8u * n);
-            if ((word >> (n & 63u)) & 1ull) n0 = uint32_t((((unsigned long long)n1 << 5) + (unsigned long long)ent) >> 5);
+            if ((word >> (n & 63u)) & 1ull) n0 = n1 + uint32_t(int(ent >> 5));
         }
         kx = x; ky = y; kz = z;
         return n0 ? 0 : (n1 ? 1 : (n2 ? 2 : 3));
@@ -460,14 +460,8 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
 {
     Dda& cur = w.cur;
     int status = kWalkContinue;
-    // ---- phase A: level set-up: math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
-    if (active && w.pendLevel && runA) {
-        cur.init(ray, w.c0, w.c1, LsWalk::shiftOf(w.lvl));
-        w.pendLevel = false;
-        if (w.lvl == 3) { w.pendInterp = 1; w.tq = w.c0; }               // tester.init(dda.time()) (:597-601)
-    }
-    if (SYNC) __syncwarp();
-    // ---- phase B: probe the current cell
+    // ---- phase B: probe the current cell.  (B comes before A: a lane that finds a leaf sets up the leaf's DDA and evaluates the
+    // tester's first value in the SAME call, one warp iteration per leaf visit less than with the set-up first.)
     if (active && !w.pendLevel && !w.pendInterp && !w.pendStep) {
         if (w.skip) { w.skip = false; w.pendStep = true; }
         else {
@@ -493,6 +487,13 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 w.pendStep = true;
             }
         }
+    }
+    if (SYNC) __syncwarp();
+    // ---- phase A: level set-up: math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
+    if (active && w.pendLevel && runA) {
+        cur.init(ray, w.c0, w.c1, LsWalk::shiftOf(w.lvl));
+        w.pendLevel = false;
+        if (w.lvl == 3) { w.pendInterp = 1; w.tq = w.c0; }               // tester.init(dda.time()) (:597-601)
     }
     if (SYNC) __syncwarp();
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso

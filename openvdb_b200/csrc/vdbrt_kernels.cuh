@@ -88,9 +88,6 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 // measured on the B200 (C2 workload): re-feeding single lanes costs more (ray set-up for a few lanes at a time, lost
 // coherence) than it gains; a warp takes a fresh 8x4 tile when all its lanes are done (profiles/r01_tuning.md)
 constexpr int kRefillThreshold = VDBRT_REFILL;   // refill when at least this many lanes are idle
-constexpr int kBatchLevel = 4;           // run the level set-up phase when this many lanes wait for it ...
-constexpr int kBatchInterp = 4;          // ... the stencil phase when this many lanes wait for it ...
-constexpr int kBatchRunnable = 8;        // ... or when fewer lanes than this could probe / step instead
 
 __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket, uint32_t& px, uint32_t& py)
 {
@@ -319,13 +316,9 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 }
             }
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
-            // The rare phases run when enough lanes wait for them, or when too few lanes could do anything else.
+            // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
-                const int nA = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendLevel));
-                const int nC = __popc(__ballot_sync(0xffffffffu, rayOn && walk.pendInterp != 0));
-                const int nRun = __popc(__ballot_sync(0xffffffffu, rayOn && walk.runnable()));
-                const bool runA = nA >= kBatchLevel || nRun < kBatchRunnable, runC = nC >= kBatchInterp || nRun < kBatchRunnable;
-                const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, runA, runC, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
+                const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
                 if (rayOn) status = r;
             }
             __syncwarp();
@@ -704,6 +697,8 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
     double Tx = 1.0, Ty = 1.0, Tz = 1.0, Lx = 0.0, Ly = 0.0, Lz = 0.0;      // pTrans, pLumi
     double Sx = 1.0, Sy = 1.0, Sz = 1.0, dTx = 1.0, dTy = 1.0, dTz = 1.0;  // sTrans, dT of the primary sample being lit
 
+    // OUTER loop: tile refill and the set-up of the next sample's primary ray (camera, world->index, clip);
+    // INNER loop: walk | sample | exp | luminance | pixel, until a lane wants its next primary ray or no lane is busy.
     for (;;) {
         __syncwarp();
         // (1) a warp takes a fresh 8x4 tile when all its lanes are done
@@ -735,114 +730,120 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                 walk.begin(ray); mode = kFogPrimary; pendExp = 0; span = 0;
             } else fin = true;                                           // `continue` (:1022): the sample stays (0,0,0,0)
         }
-        __syncwarp();
-        // for (pT = pStep*ceil(t0/pStep); pT <= pT1; pT += pStep): past the end of a closed span -> look for the next one
-        if (span == 2 && !(tcur <= tend)) span = 0;
-        const bool busy = mode != kFogIdle && !pendExp;
-        const bool marching = busy && (span == 2 || (span == 1 && tcur <= walk.bound && (walk.bound - walk.ts0) > 1e-9));
-        const bool walking = busy && !marching;
-        const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
-        const int nE = __popc(__ballot_sync(0xffffffffu, pendExp != 0));
-        const bool runW = nW >= kFogBatch || (nM < kFogBatch && nE < kFogBatch);
-        const bool runM = nM >= kFogBatch || (nW < kFogBatch && nE < kFogBatch);
-        const bool runE = nE >= kFogBatch || (nW < kFogBatch && nM < kFogBatch);
-        bool lum = false;
-        // (2) walk: one unit of VolumeHDDA::hits for the active ray
-        if (walking && runW) {
-            double a, b;
-            const int r = walk.template advance<COUNT>(g, root, sm, mode == kFogPrimary ? 0 : 2, accW, ray, a, b, c);
-            if (r == kSpanEmit) { tend = b; span = 2; }                  // the open span closed at b (valid: b - a > 1e-9)
-            else if (r == kSpanDone) { if (mode == kFogPrimary) fin = true; else lum = true; }   // shadow spans exhausted: Luminance
-            else if (span == 1 && walk.ts0 < 0.0) span = 0;              // it closed, but too short to count (TimeSpan::valid)
-            if (span == 0 && r != kSpanDone && (walk.ts0 >= 0.0 || r == kSpanEmit)) {
-                // a span opened at a: first sample time pStep*ceil(t0/pStep) (:1030-1032, :1045-1047)
-                const double st = mode == kFogPrimary ? p.pstep : p.sstep;
-                const double t0s = r == kSpanEmit ? a : walk.ts0;
-                tcur = st * ceil(t0s / st);
-                span = r == kSpanEmit ? 2 : 1;
+#pragma unroll 1
+        for (;;) {
+            __syncwarp();
+            // for (pT = pStep*ceil(t0/pStep); pT <= pT1; pT += pStep): past the end of a closed span -> look for the next one
+            if (span == 2 && !(tcur <= tend)) span = 0;
+            const bool busy = mode != kFogIdle && !pendExp;
+            const bool marching = busy && (span == 2 || (span == 1 && tcur <= walk.bound && (walk.bound - walk.ts0) > 1e-9));
+            const bool walking = busy && !marching;
+            const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
+            const int nE = __popc(__ballot_sync(0xffffffffu, pendExp != 0));
+            const bool runW = nW >= kFogBatch || (nM < kFogBatch && nE < kFogBatch);
+            const bool runM = nM >= kFogBatch || (nW < kFogBatch && nE < kFogBatch);
+            const bool runE = nE >= kFogBatch || (nW < kFogBatch && nM < kFogBatch);
+            bool lum = false;
+            // (2) walk: one unit of VolumeHDDA::hits for the active ray
+            if (walking && runW) {
+                double a, b;
+                const int r = walk.template advance<COUNT>(g, root, sm, mode == kFogPrimary ? 0 : 2, accW, ray, a, b, c);
+                if (r == kSpanEmit) { tend = b; span = 2; }                  // the open span closed at b (valid: b - a > 1e-9)
+                else if (r == kSpanDone) { if (mode == kFogPrimary) fin = true; else lum = true; }   // shadow spans exhausted: Luminance
+                else if (span == 1 && walk.ts0 < 0.0) span = 0;              // it closed, but too short to count (TimeSpan::valid)
+                if (span == 0 && r != kSpanDone && (walk.ts0 >= 0.0 || r == kSpanEmit)) {
+                    // a span opened at a: first sample time pStep*ceil(t0/pStep) (:1030-1032, :1045-1047)
+                    const double st = mode == kFogPrimary ? p.pstep : p.sstep;
+                    const double t0s = r == kSpanEmit ? a : walk.ts0;
+                    tcur = st * ceil(t0s / st);
+                    span = r == kSpanEmit ? 2 : 1;
+                }
             }
-        }
-        __syncwarp();
-        // (3) sample: density at the current march time of the active ray
-        if (marching && runM) {
-            // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
-            double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
-            indexToWorldPos(g, wx, wy, wz);
-            const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
-            if (COUNT) { if (mode == kFogPrimary) ++c.psamples; else ++c.ssamples; }
-            if (d < p.cutoff) tcur += mode == kFogPrimary ? p.pstep : p.sstep;        // continue
-            else { dens = d; pendExp = mode; }
-        }
-        __syncwarp();
-        // (4) exp: dT = Exp(extinction*density*pStep) (:1037) or sTrans *= Exp(extinction*d*sStep/(1+sT*sGain)) (:1053)
-        if (pendExp && runE) {
-            const bool prim = pendExp == kFogPrimary;
-            pendExp = 0;
-            const double den = 1.0 + tcur * p.gain;
-            const double ax = prim ? p.ext[0] * dens * p.pstep : p.ext[0] * dens * p.sstep / den;
-            const double ay = prim ? p.ext[1] * dens * p.pstep : p.ext[1] * dens * p.sstep / den;
-            const double az = prim ? p.ext[2] * dens * p.pstep : p.ext[2] * dens * p.sstep / den;
-            const double ex = exp(ax), ey = exp(ay), ez = exp(az);
-            if (prim) {
-                dTx = ex; dTy = ey; dTz = ez;
-                Sx = Sy = Sz = 1.0;
-                // sRay.setEye(pPos); mShadow->setWorldRay(sRay) (:1039-1040)
+            __syncwarp();
+            // (3) sample: density at the current march time of the active ray
+            if (marching && runM) {
+                // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
                 double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
                 indexToWorldPos(g, wx, wy, wz);
-                worldToIndexPos(g, wx, wy, wz);
-                Ray sRay;
-                sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
-                sRay.dx = sm.sbase[0]; sRay.dy = sm.sbase[1]; sRay.dz = sm.sbase[2];
-                sRay.ix = sm.sbase[3]; sRay.iy = sm.sbase[4]; sRay.iz = sm.sbase[5];
-                sRay.t0 = sm.sbase[6]; sRay.t1 = sm.sbase[7];
-                if (COUNT) ++c.srays;
-                if (!clipRay(sRay, g, 1)) tcur += p.pstep;              // `continue`: no luminance for this sample
-                else {
-                    // suspend the primary walk and ray, switch the lane to the shadow ray
-                    sm.park(4, walk.cur);
-                    sm.dt0[tid] = walk.cur.t0; sm.ts0[tid] = walk.ts0; sm.topT1[tid] = walk.topT1; sm.tcur[tid] = tcur; sm.tend[tid] = tend;
-                    sm.bound[tid] = walk.bound; sm.c0[tid] = walk.c0; sm.c1[tid] = walk.c1;
-                    sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0) | (walk.pendLevel ? 512 : 0) | (span << 12);
-                    sm.ray[0][tid] = ray.ex; sm.ray[1][tid] = ray.ey; sm.ray[2][tid] = ray.ez; sm.ray[3][tid] = ray.dx; sm.ray[4][tid] = ray.dy;
-                    sm.ray[5][tid] = ray.dz;
-                    ray = sRay;
-                    walk.begin(ray);
-                    mode = kFogShadow; span = 0;
+                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
+                if (COUNT) { if (mode == kFogPrimary) ++c.psamples; else ++c.ssamples; }
+                if (d < p.cutoff) tcur += mode == kFogPrimary ? p.pstep : p.sstep;        // continue
+                else { dens = d; pendExp = mode; }
+            }
+            __syncwarp();
+            // (4) exp: dT = Exp(extinction*density*pStep) (:1037) or sTrans *= Exp(extinction*d*sStep/(1+sT*sGain)) (:1053)
+            if (pendExp && runE) {
+                const bool prim = pendExp == kFogPrimary;
+                pendExp = 0;
+                const double den = 1.0 + tcur * p.gain;
+                const double ax = prim ? p.ext[0] * dens * p.pstep : p.ext[0] * dens * p.sstep / den;
+                const double ay = prim ? p.ext[1] * dens * p.pstep : p.ext[1] * dens * p.sstep / den;
+                const double az = prim ? p.ext[2] * dens * p.pstep : p.ext[2] * dens * p.sstep / den;
+                const double ex = exp(ax), ey = exp(ay), ez = exp(az);
+                if (prim) {
+                    dTx = ex; dTy = ey; dTz = ez;
+                    Sx = Sy = Sz = 1.0;
+                    // sRay.setEye(pPos); mShadow->setWorldRay(sRay) (:1039-1040)
+                    double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
+                    indexToWorldPos(g, wx, wy, wz);
+                    worldToIndexPos(g, wx, wy, wz);
+                    Ray sRay;
+                    sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
+                    sRay.dx = sm.sbase[0]; sRay.dy = sm.sbase[1]; sRay.dz = sm.sbase[2];
+                    sRay.ix = sm.sbase[3]; sRay.iy = sm.sbase[4]; sRay.iz = sm.sbase[5];
+                    sRay.t0 = sm.sbase[6]; sRay.t1 = sm.sbase[7];
+                    if (COUNT) ++c.srays;
+                    if (!clipRay(sRay, g, 1)) tcur += p.pstep;              // `continue`: no luminance for this sample
+                    else {
+                        // suspend the primary walk and ray, switch the lane to the shadow ray
+                        sm.park(4, walk.cur);
+                        sm.dt0[tid] = walk.cur.t0; sm.ts0[tid] = walk.ts0; sm.topT1[tid] = walk.topT1; sm.tcur[tid] = tcur; sm.tend[tid] = tend;
+                        sm.bound[tid] = walk.bound; sm.c0[tid] = walk.c0; sm.c1[tid] = walk.c1;
+                        sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0) | (walk.pendLevel ? 512 : 0) | (span << 12);
+                        sm.ray[0][tid] = ray.ex; sm.ray[1][tid] = ray.ey; sm.ray[2][tid] = ray.ez; sm.ray[3][tid] = ray.dx; sm.ray[4][tid] = ray.dy;
+                        sm.ray[5][tid] = ray.dz;
+                        ray = sRay;
+                        walk.begin(ray);
+                        mode = kFogShadow; span = 0;
+                    }
+                } else {
+                    Sx *= ex; Sy *= ey; Sz *= ez;
+                    if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) lum = true;                      // goto Luminance (:1054)
+                    else tcur += p.sstep;
                 }
-            } else {
-                Sx *= ex; Sy *= ey; Sz *= ez;
-                if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) lum = true;                      // goto Luminance (:1054)
-                else tcur += p.sstep;
             }
-        }
-        // (5) Luminance (:1057-1060): back to the primary ray
-        if (lum) {
-            Lx += p.albedo[0] * Sx * Tx * (1.0 - dTx); Ly += p.albedo[1] * Sy * Ty * (1.0 - dTy); Lz += p.albedo[2] * Sz * Tz * (1.0 - dTz);
-            Tx *= dTx; Ty *= dTy; Tz *= dTz;
-            if (Tx * Tx + Ty * Ty + Tz * Tz < p.cutoff) fin = true;                         // goto Pixel
-            else {
-                sm.unpark(4, walk.cur);
-                walk.cur.t0 = sm.dt0[tid]; walk.ts0 = sm.ts0[tid]; walk.topT1 = sm.topT1[tid]; tend = sm.tend[tid];
-                walk.bound = sm.bound[tid]; walk.c0 = sm.c0[tid]; walk.c1 = sm.c1[tid];
-                tcur = sm.tcur[tid] + p.pstep;
-                const int m = sm.misc[tid];
-                walk.lvl = (m & 255) - 1; walk.needStep = (m & 256) != 0; walk.pendLevel = (m & 512) != 0; span = m >> 12;
-                ray.ex = sm.ray[0][tid]; ray.ey = sm.ray[1][tid]; ray.ez = sm.ray[2][tid]; ray.dx = sm.ray[3][tid]; ray.dy = sm.ray[4][tid];
-                ray.setDir(ray.dx, ray.dy, sm.ray[5][tid]);          // invDir = 1/dir, the same division as at ray set-up
-                mode = kFogPrimary;
+            // (5) Luminance (:1057-1060): back to the primary ray
+            if (lum) {
+                Lx += p.albedo[0] * Sx * Tx * (1.0 - dTx); Ly += p.albedo[1] * Sy * Ty * (1.0 - dTy); Lz += p.albedo[2] * Sz * Tz * (1.0 - dTz);
+                Tx *= dTx; Ty *= dTy; Tz *= dTz;
+                if (Tx * Tx + Ty * Ty + Tz * Tz < p.cutoff) fin = true;                         // goto Pixel
+                else {
+                    sm.unpark(4, walk.cur);
+                    walk.cur.t0 = sm.dt0[tid]; walk.ts0 = sm.ts0[tid]; walk.topT1 = sm.topT1[tid]; tend = sm.tend[tid];
+                    walk.bound = sm.bound[tid]; walk.c0 = sm.c0[tid]; walk.c1 = sm.c1[tid];
+                    tcur = sm.tcur[tid] + p.pstep;
+                    const int m = sm.misc[tid];
+                    walk.lvl = (m & 255) - 1; walk.needStep = (m & 256) != 0; walk.pendLevel = (m & 512) != 0; span = m >> 12;
+                    ray.ex = sm.ray[0][tid]; ray.ey = sm.ray[1][tid]; ray.ez = sm.ray[2][tid]; ray.dx = sm.ray[3][tid]; ray.dy = sm.ray[4][tid];
+                    ray.setDir(ray.dx, ray.dy, sm.ray[5][tid]);          // invDir = 1/dir, the same division as at ray set-up
+                    mode = kFogPrimary;
+                }
             }
-        }
-        // (6) Pixel (:1063-1067); with more than one sample the results are summed in order and scaled by 1/samples
-        if (fin) {
-            if (mode != kFogIdle) {
-                out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
-                if (COUNT && out.w > 0.f) ++c.hits;
+            // (6) Pixel (:1063-1067); with more than one sample the results are summed in order and scaled by 1/samples
+            if (fin) {
+                if (mode != kFogIdle) {
+                    out = make_float4(float(Lx), float(Ly), float(Lz), float(1.0f - (Tx + Ty + Tz) / 3.0f));
+                    if (COUNT && out.w > 0.f) ++c.hits;
+                }
+                if (k == 0) acc = out;
+                else { acc.x += out.x; acc.y += out.y; acc.z += out.z; acc.w += out.w; }
+                mode = kFogIdle; pendExp = 0;
+                if (++k > p.sub) film[pix] = make_float4(acc.x * p.frac, acc.y * p.frac, acc.z * p.frac, acc.w * p.frac);
+                else needRay = true;
             }
-            if (k == 0) acc = out;
-            else { acc.x += out.x; acc.y += out.y; acc.z += out.z; acc.w += out.w; }
-            mode = kFogIdle; pendExp = 0;
-            if (++k > p.sub) film[pix] = make_float4(acc.x * p.frac, acc.y * p.frac, acc.z * p.frac, acc.w * p.frac);
-            else needRay = true;
+                fin = false;
+            out = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (__any_sync(0xffffffffu, needRay) || !__any_sync(0xffffffffu, mode != kFogIdle)) break;
         }
     }
     if (COUNT) flushCounters(c, counters);
