@@ -18,6 +18,7 @@ struct vdbrt_ctx {
     uint32_t ls_budget = 0;                     // warp iterations a tile may spend before its running rays are suspended (0 = never)
     uint32_t ls_factor = 0;                     // ... or this many percent of a warp's share of the launch, if that is more
     uint32_t ls_rounds = 0;                     // long-ray rounds per frame
+    uint32_t ls_leaves[8] = {};                 // leaf visits per ray in round r
 };
 
 struct vdbrt_grid {

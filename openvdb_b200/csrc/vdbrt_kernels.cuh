@@ -125,12 +125,12 @@ __device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh
 // Long rays.  A ray that grazes the surface marches hundreds of narrow-band voxels; one such ray per warp keeps the
 // whole warp (and, at the end of the frame, the whole GPU) waiting.  The render kernel therefore gives every 8x4 tile a
 // BUDGET of warp iterations; rays still running after that are suspended into LongRay records and finished by
-// "rounds" of three homogeneous kernels:
-//   scout   one thread per long ray walks the node levels only (root/upper/lower DDAs) and writes the next K leaf visits
-//           (time range + leaf handle) it finds as segments;
-//   march   one thread per SEGMENT runs the voxel DDA / zero-crossing search of that leaf (LevelSetHDDA<Tree,-1>::test);
-//   resolve one thread per long ray: the first segment with a hit wins -> shade + film; walked out of the grid -> miss;
-//           otherwise the ray stays for the next round (K grows).
+// "rounds" of two homogeneous kernels (default: two rounds, K = 8 then 128 leaf visits per ray):
+//   scout   one thread per long ray first RESOLVES the previous round -- the first segment with a hit wins -> shade + film;
+//           walked out of the grid -> miss -- and otherwise walks the node levels only (root/upper/lower DDAs) and writes
+//           the next K leaf visits (time range + leaf handle) it finds as segments;
+//   march   one thread per SEGMENT runs the voxel DDA / zero-crossing search of that leaf (LevelSetHDDA<Tree,-1>::test).
+// k_long_finish resolves the last round and walks whatever is still alive to its end in line.
 // A leaf visit depends only on the ray and its [t0,t1] (the tester is re-initialised per leaf, math/DDA.h:172-173), so
 // marching the leaves of one ray in parallel and taking the first hit in visit order is exactly the reference's result.
 // ------------------------------------------------------------------------------------------------------------
@@ -138,7 +138,7 @@ constexpr uint32_t kNoHit = 0xffffffffu;
 constexpr int kMaxRounds = 8;
 constexpr uint32_t kDefaultBudget = 160;  // warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
-constexpr int kDefaultRounds = 6;
+constexpr int kDefaultRounds = 2;
 constexpr double kRoundsMaxTilesPerWarp = 12.0;   // rounds are on by default only below this (see launchLevelSet)
 
 struct LongRay {
@@ -244,6 +244,23 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     // bookkeeping is executed per traversal step.
     for (;;) {
         __syncwarp();
+        // (0) the tile has used up its budget (the inner loop leaves when that happens): suspend the rays that are still running,
+        // they continue in the long-ray rounds.  Kept out of the inner loop so that the hot loop is the same with and without it.
+        if (LONG && spent > limit && !longFull) {
+            const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
+            const unsigned m = __ballot_sync(0xffffffffu, sus);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
+                if (base + __popc(m) > lb.capLong) longFull = true;
+                if (sus && idx < lb.capLong) {
+                    suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
+                    rayOn = false; hasPix = false;
+                }
+            }
+        }
         // (1) refill idle lanes from the queue
         const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
         if (COUNT && idle == 0xffffffffu && lane == 0) {
@@ -299,22 +316,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         for (;;) {
             __syncwarp();
             if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
-            // (0) the tile has used up its budget: suspend the rays that are still running (they continue in the long-ray rounds)
-            if (LONG && ++spent > limit && !longFull) {
-                const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
-                const unsigned m = __ballot_sync(0xffffffffu, sus);
-                if (m) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
-                    if (base + __popc(m) > lb.capLong) longFull = true;
-                    if (sus && idx < lb.capLong) {
-                        suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
-                        rayOn = false; hasPix = false;
-                    }
-                }
-            }
+            if (LONG) ++spent;
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
@@ -343,6 +345,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             // back to the outer loop when a lane wants its next ray (or fresh pixels), or when nothing is running any more
             const unsigned running = __ballot_sync(0xffffffffu, rayOn);
             if (running == 0u || (kRefillThreshold < 32 && __popc(running) <= 32 - kRefillThreshold) || __any_sync(0xffffffffu, hasPix && !rayOn)) break;
+            if (LONG && spent > limit && !longFull) break;
         }
     }
     if (COUNT) flushCounters(c, counters);

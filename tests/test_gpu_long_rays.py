@@ -26,8 +26,8 @@ def render(ctx, grid, cam, sh, W, H, bg=(0, 0, 0, 1), want_aux=True, **opts):
 @pytest.fixture(scope="module")
 def tiny_budget_ctx():
     """a context whose tiles may spend only a handful of iterations: nearly every ray that enters the grid is suspended"""
-    old = {k: os.environ.get(k) for k in ("VDBRT_LS_BUDGET", "VDBRT_LS_FACTOR", "VDBRT_LS_ROUNDS")}
-    os.environ.update(VDBRT_LS_BUDGET="6", VDBRT_LS_FACTOR="0", VDBRT_LS_ROUNDS="3")
+    old = {k: os.environ.get(k) for k in ("VDBRT_LS_BUDGET", "VDBRT_LS_FACTOR", "VDBRT_LS_LEAVES")}
+    os.environ.update(VDBRT_LS_BUDGET="6", VDBRT_LS_FACTOR="0", VDBRT_LS_LEAVES="2,4,12")
     c = api.Context(0)
     for k, v in old.items():
         if v is None:
