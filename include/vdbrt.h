@@ -86,6 +86,10 @@ typedef struct vdbrt_shader {
     uint32_t reserved;
     double   bbox_min[3];     /* PositionShader: bbox.min()            (RayTracer.h:675)                        */
     double   inv_dim[3];      /* PositionShader: 1.0 / bbox.extents()                                           */
+    /* NULL: the constant-colour shaders above.  Else a grid from vdbrt_upload_color_grid: the GridT = Vec3SGrid forms of the
+     * four shaders (RayTracer.h:542-562, 591-611, 640-668, 702-725) with the default PointSampler -- the colour is the
+     * grid's value at the voxel nearest to the hit position (tools/Interpolation.h:600-617), rgba[] is not used.   */
+    const struct vdbrt_grid* color_grid;
 } vdbrt_shader;
 
 /* Which film tiles this context renders (multi-GPU): the film is cut into tile_w x tile_h tiles numbered
@@ -216,6 +220,10 @@ int  vdbrt_memcpy(vdbrt_ctx* ctx, void* dst, const void* src, size_t bytes, int 
  * constructor-time work of LinearSearchImpl / VolumeRayIntersector (validation, node-granular bbox:
  * tools/RayIntersector.h:299-319,527-541).  The buffer is a complete NanoGrid<float> (GridData first).        */
 int  vdbrt_upload_grid(vdbrt_ctx* ctx, const void* nanovdb_buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out);
+/* A NanoGrid<Vec3f> (GridType::Vec3f; createNanoGrid of an openvdb::Vec3SGrid) used as vdbrt_shader::color_grid; replaces
+ * the `const GridT& grid` argument of the colour-grid shader constructors.  Scale(+translate) maps only.  Released with
+ * vdbrt_free_grid; cannot be rendered itself.                                                                   */
+int  vdbrt_upload_color_grid(vdbrt_ctx* ctx, const void* nanovdb_buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out);
 int  vdbrt_free_grid(vdbrt_ctx* ctx, vdbrt_grid* grid);
 int  vdbrt_grid_get_info(const vdbrt_grid* grid, vdbrt_grid_info* info);
 /* copy the serialised grid back (device -> host), e.g. after vdbrt_build_* */
@@ -301,6 +309,9 @@ int  vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, 
 /* grid_name NULL or "": the first float grid (vdb_render's rule, openvdb_cmd/vdb_render/main.cc:771-786).  The buffer
  * is a 32-byte aligned host allocation owned by the caller: pass it to vdbrt_upload_grid, release with vdbrt_buffer_free */
 int  vdbrt_nvdb_read(const char* path, const char* grid_name, void** buffer, uint64_t* bytes);
+/* the same for another value type: grid_type = nanovdb::GridType (1 Float, 6 Vec3f: the colour grid of vdb_render's
+ * -color option, main.cc:788-795), 0 = any                                                                      */
+int  vdbrt_nvdb_read_typed(const char* path, const char* grid_name, uint32_t grid_type, void** buffer, uint64_t* bytes);
 int  vdbrt_nvdb_write(const char* path, const void* buffer, uint64_t bytes, uint32_t codec);
 int  vdbrt_buffer_free(void* buffer);
 /* tools::Film::savePPM (tools/RayTracer.h:300-335): P6, channel = (unsigned char)(255.0f * value), ".ppm" appended

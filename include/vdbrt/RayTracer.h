@@ -111,6 +111,36 @@ private:
     Context* mCtx; vdbrt_grid* mGrid;
 };
 
+/// A NanoGrid<Vec3f> resident on the GPU: the colour grid of the GridT = Vec3SGrid shaders (openvdb::Vec3SGrid serialised with
+/// nanovdb::tools::createNanoGrid).  The shader objects keep a reference to it, like the reference's shaders keep an accessor.
+class Vec3SGrid
+{
+public:
+    using Ptr = std::shared_ptr<Vec3SGrid>;
+    static Ptr upload(Context& ctx, const void* nanovdbBuffer, uint64_t bytes)
+    {
+        vdbrt_grid* g = nullptr;
+        check(vdbrt_upload_color_grid(ctx.get(), nanovdbBuffer, bytes, VDBRT_MEM_HOST, &g));
+        return Ptr(new Vec3SGrid(ctx, g));
+    }
+    /// the named Vec3f grid of a .nvdb file (vdb_render -color, openvdb_cmd/vdb_render/main.cc:788-795)
+    static Ptr read(Context& ctx, const std::string& fileName, const std::string& gridName)
+    {
+        void* buf = nullptr; uint64_t bytes = 0;
+        check(vdbrt_nvdb_read_typed(fileName.c_str(), gridName.c_str(), 6u, &buf, &bytes));
+        vdbrt_grid* g = nullptr;
+        const int rc = vdbrt_upload_color_grid(ctx.get(), buf, bytes, VDBRT_MEM_HOST, &g);
+        vdbrt_buffer_free(buf);
+        check(rc);
+        return Ptr(new Vec3SGrid(ctx, g));
+    }
+    ~Vec3SGrid() { vdbrt_free_grid(mCtx->get(), mGrid); }
+    const vdbrt_grid* get() const { return mGrid; }
+private:
+    Vec3SGrid(Context& ctx, vdbrt_grid* g) : mCtx(&ctx), mGrid(g) {}
+    Context* mCtx; vdbrt_grid* mGrid;
+};
+
 namespace tools {
 
 /// tools::Film (RayTracer.h:226-345): pixels live in pinned host memory so the copies to/from the GPU run at full speed.
@@ -249,6 +279,26 @@ template<> class PositionShader<Film::RGBA> : public BaseShader { public:
     BaseShader* copy() const override { return new PositionShader(*this); } };
 template<> class DiffuseShader<Film::RGBA> : public BaseShader { public:
     DiffuseShader(const Film::RGBA& d = Film::RGBA(1.0f)) : BaseShader(VDBRT_SHADER_DIFFUSE, d) {}
+    BaseShader* copy() const override { return new DiffuseShader(*this); } };
+
+// the colour-grid forms (RayTracer.h:542-562, 591-611, 640-668, 702-725; default PointSampler): colour = the grid's value at the
+// voxel nearest to the hit position.  The grid must outlive the shader (the reference's shaders hold an accessor the same way).
+template<> class MatteShader<Vec3SGrid> : public BaseShader { public:
+    MatteShader(const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_MATTE, Film::RGBA(1.0f)) { mPod.color_grid = grid.get(); }
+    BaseShader* copy() const override { return new MatteShader(*this); } };
+template<> class NormalShader<Vec3SGrid> : public BaseShader { public:
+    NormalShader(const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_NORMAL, Film::RGBA(1.0f)) { mPod.color_grid = grid.get(); }
+    BaseShader* copy() const override { return new NormalShader(*this); } };
+template<> class PositionShader<Vec3SGrid> : public BaseShader { public:
+    PositionShader(const Vec3R& bboxMin, const Vec3R& bboxMax, const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_POSITION, Film::RGBA(1.0f))
+    {
+        mPod.bbox_min[0] = bboxMin.x; mPod.bbox_min[1] = bboxMin.y; mPod.bbox_min[2] = bboxMin.z;
+        mPod.inv_dim[0] = 1.0 / (bboxMax.x - bboxMin.x); mPod.inv_dim[1] = 1.0 / (bboxMax.y - bboxMin.y); mPod.inv_dim[2] = 1.0 / (bboxMax.z - bboxMin.z);
+        mPod.color_grid = grid.get();
+    }
+    BaseShader* copy() const override { return new PositionShader(*this); } };
+template<> class DiffuseShader<Vec3SGrid> : public BaseShader { public:
+    DiffuseShader(const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_DIFFUSE, Film::RGBA(1.0f)) { mPod.color_grid = grid.get(); }
     BaseShader* copy() const override { return new DiffuseShader(*this); } };
 
 /// tools::LevelSetRayIntersector (RayIntersector.h:79-246): validates at construction, batches of rays on the device

@@ -33,7 +33,7 @@ class Camera(C.Structure):
 
 class Shader(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("rgba", C.c_float * 4), ("reserved", C.c_uint32),
-                ("bbox_min", C.c_double * 3), ("inv_dim", C.c_double * 3)]
+                ("bbox_min", C.c_double * 3), ("inv_dim", C.c_double * 3), ("color_grid", C.c_void_p)]
 
 
 class Partition(C.Structure):

@@ -24,7 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
-    "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over",
+    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over",
 ]
 
 
@@ -61,6 +61,7 @@ def load_library():
     L.vdbrt_host_free.argtypes = [vp]
     L.vdbrt_upload_grid.argtypes = [vp, vp, u64, u32, P(vp)]
     L.vdbrt_free_grid.argtypes = [vp, vp]
+    L.vdbrt_upload_color_grid.argtypes = [vp, vp, u64, u32, P(vp)]
     L.vdbrt_grid_get_info.argtypes = [vp, P(abi.GridInfo)]
     L.vdbrt_grid_download.argtypes = [vp, vp, vp, u64]
     L.vdbrt_camera_perspective.argtypes = [P(abi.Camera), u32, u32, P(dbl), P(dbl), dbl, dbl, dbl, dbl]
@@ -88,6 +89,7 @@ def load_library():
     L.vdbrt_memcpy.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
     L.vdbrt_nvdb_list.argtypes = [C.c_char_p, P(abi.NvdbMeta), u32, P(u32)]
     L.vdbrt_nvdb_read.argtypes = [C.c_char_p, C.c_char_p, P(vp), P(u64)]
+    L.vdbrt_nvdb_read_typed.argtypes = [C.c_char_p, C.c_char_p, u32, P(vp), P(u64)]
     L.vdbrt_nvdb_write.argtypes = [C.c_char_p, vp, u64, u32]
     L.vdbrt_buffer_free.argtypes = [vp]
     L.vdbrt_film_save_ppm.argtypes = [C.c_char_p, vp, u32, u32]
@@ -150,12 +152,14 @@ def vol_opts_default(spp=1, seed=0):
     return o
 
 
-def make_shader(kind=abi.SHADER_DIFFUSE, rgba=(1, 1, 1, 1), bbox_min=(0, 0, 0), inv_dim=(1, 1, 1)):
+def make_shader(kind=abi.SHADER_DIFFUSE, rgba=(1, 1, 1, 1), bbox_min=(0, 0, 0), inv_dim=(1, 1, 1), color_grid=None):
+    """color_grid: a Grid from Context.upload_color -> the GridT = Vec3SGrid form of the shader (keep the Grid alive)"""
     s = abi.Shader()
     s.kind = kind
     s.rgba = (C.c_float * 4)(*rgba)
     s.bbox_min = abi.vec3(bbox_min)
     s.inv_dim = abi.vec3(inv_dim)
+    s.color_grid = color_grid.handle if color_grid is not None else None
     return s
 
 
@@ -229,6 +233,13 @@ class Context:
         buf = np.ascontiguousarray(buf, np.uint8)
         g = C.c_void_p()
         _check(self.L.vdbrt_upload_grid(self.handle, buf.ctypes.data, buf.size, abi.MEM_HOST, C.byref(g)))
+        return Grid(self, g.value)
+
+    def upload_color(self, buf):
+        """buf: uint8 numpy array holding a serialised NanoGrid<Vec3f> (the colour grid of the colour-grid shaders)"""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        g = C.c_void_p()
+        _check(self.L.vdbrt_upload_color_grid(self.handle, buf.ctypes.data, buf.size, abi.MEM_HOST, C.byref(g)))
         return Grid(self, g.value)
 
     def upload_device(self, dev_ptr, nbytes):
@@ -341,11 +352,12 @@ def nvdb_list(path):
     return list(out[:n.value])
 
 
-def nvdb_read(path, name=None):
-    """nanovdb::io::readGrid: the serialised grid as a 32-byte aligned uint8 array (first float grid when name is None)"""
+def nvdb_read(path, name=None, grid_type=1):
+    """nanovdb::io::readGrid: the serialised grid as a 32-byte aligned uint8 array (first grid of that type when name is None;
+    grid_type 1 = Float, 6 = Vec3f, 0 = any)"""
     L = load_library()
     p, n = C.c_void_p(), C.c_uint64(0)
-    _check(L.vdbrt_nvdb_read(os.fsencode(path), name.encode() if name else None, C.byref(p), C.byref(n)))
+    _check(L.vdbrt_nvdb_read_typed(os.fsencode(path), name.encode() if name else None, grid_type, C.byref(p), C.byref(n)))
     try:
         raw = np.empty(n.value + 32, np.uint8)
         off = (-raw.ctypes.data) % 32

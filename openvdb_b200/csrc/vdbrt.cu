@@ -125,6 +125,7 @@ namespace {
 int checkLevelSet(const vdbrt_grid* g, float iso)
 {
     const vdbrt_grid_info& i = g->info;
+    if (g->is_color) return setError(VDBRT_ERR_NOT_FLOAT, "grid value type is not float");
     // the member LinearSearchImpl is constructed before the intersector's own checks run (tools/RayIntersector.h:98,533-539)
     if (i.root_tiles == 0) return setError(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids"); // :533-535
     if (iso <= -i.background || iso >= i.background)
@@ -138,6 +139,7 @@ int checkLevelSet(const vdbrt_grid* g, float iso)
 int checkVolume(const vdbrt_grid* g)
 {
     const vdbrt_grid_info& i = g->info;
+    if (g->is_color) return setError(VDBRT_ERR_NOT_FLOAT, "grid value type is not float");
     if (std::fabs(i.voxel_size[0] - i.voxel_size[1]) > 5e-7 || std::fabs(i.voxel_size[0] - i.voxel_size[2]) > 5e-7)
         return setError(VDBRT_ERR_NONUNIFORM, "VolumeRayIntersector only supports uniform voxels!");           // :305-308
     if (i.root_tiles == 0) return setError(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids"); // :309-311
@@ -358,6 +360,60 @@ int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32
     return VDBRT_OK;
 }
 
+int vdbrt_upload_color_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out)
+{
+    if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (bytes < GRID_SIZE + TREE_SIZE) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    DeviceGuard guard(ctx->device);
+    auto* g = new vdbrt_grid;
+    g->bytes = bytes; g->device = ctx->device; g->is_color = true;
+    cudaError_t e = cudaMalloc(&g->dev, bytes);
+    if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
+    auto fail = [&](int rc) { cudaFree(g->dev); delete g; return rc; };
+    e = cudaMemcpyAsync(g->dev, buffer, bytes, memspace == VDBRT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return fail(cudaFail(e, "cudaMemcpyAsync(grid)"));
+    uint8_t head[GRID_SIZE + TREE_SIZE];
+    if (cudaMemcpyAsync(head, g->dev, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return fail(setError(VDBRT_ERR_CUDA, "reading the grid header back failed"));
+    const uint64_t magic = rd<uint64_t>(head);
+    if (magic != MAGIC_NUMB && magic != MAGIC_GRID) return fail(setError(VDBRT_ERR_BAD_GRID, "not a NanoVDB grid (bad magic number)"));
+    if ((rd<uint32_t>(head + OFF_VERSION) >> 21) != 32) return fail(setError(VDBRT_ERR_BAD_GRID, "incompatible NanoVDB major version (need 32)"));
+    if (rd<uint32_t>(head + OFF_TYPE) != 6) return fail(setError(VDBRT_ERR_NOT_FLOAT, "colour grid value type is not Vec3f"));
+    const uint8_t* tree = head + GRID_SIZE;
+    const uint64_t rootOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 24));
+    if (rootOff + kColRootTiles > bytes) return fail(setError(VDBRT_ERR_BAD_GRID, "root offset outside the buffer"));
+    uint8_t rootHead[kColRootTiles];
+    if (cudaMemcpyAsync(rootHead, g->dev + rootOff, sizeof(rootHead), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return fail(setError(VDBRT_ERR_CUDA, "reading the root header back failed"));
+    double m[9];
+    for (int i = 0; i < 9; ++i) m[i] = rd<double>(head + OFF_MATD + 8 * i);
+    if (m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0)
+        return fail(setError(VDBRT_ERR_UNSUPPORTED, "only scale(+translate) index->world maps are supported"));
+    vdbrt_grid_info& info = g->info;
+    std::memset(&info, 0, sizeof(info));
+    info.bytes = bytes;
+    info.leaf_count = rd<uint32_t>(tree + 32); info.lower_count = rd<uint32_t>(tree + 36); info.upper_count = rd<uint32_t>(tree + 40);
+    info.active_voxels = rd<uint64_t>(tree + 56);
+    info.root_tiles = rd<uint32_t>(rootHead + kRootTableSize);
+    info.background = rd<float>(rootHead + kRootBackground);
+    info.grid_class = rd<uint32_t>(head + OFF_CLASS);
+    for (int i = 0; i < 6; ++i) info.index_bbox[i] = info.node_bbox[i] = rd<int32_t>(rootHead + 4 * i);
+    DevColor& c = g->dcolor;
+    std::memset(&c, 0, sizeof(c));
+    std::memset(&g->dgrid, 0, sizeof(g->dgrid));
+    c.base = g->dev; c.root_off = rootOff; c.tiles = g->dev + rootOff + kColRootTiles; c.table_size = info.root_tiles;
+    for (int a = 0; a < 3; ++a) {
+        c.background[a] = rd<float>(rootHead + kRootBackground + 4 * a);
+        const double scale = m[4 * a];
+        c.inv[a] = 1.0 / scale;                                  // ScaleMap::mScaleValuesInverse (math/Maps.h:674)
+        c.trans[a] = rd<double>(head + OFF_VECD + 8 * a);
+        info.voxel_size[a] = std::fabs(scale); info.translation[a] = c.trans[a];
+    }
+    c.has_translation = (c.trans[0] != 0 || c.trans[1] != 0 || c.trans[2] != 0) ? 1u : 0u;
+    *out = g;
+    return VDBRT_OK;
+}
+
 int vdbrt_free_grid(vdbrt_ctx* ctx, vdbrt_grid* grid)
 {
     if (!grid) return VDBRT_OK;
@@ -413,6 +469,8 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     DevShader sh;
     sh.kind = shader->kind; sh.r = shader->rgba[0]; sh.g = shader->rgba[1]; sh.b = shader->rgba[2]; sh.a = shader->rgba[3];
     for (int a = 0; a < 3; ++a) { sh.bmin[a] = shader->bbox_min[a]; sh.inv[a] = shader->inv_dim[a]; }
+    std::memset(&sh.col, 0, sizeof(sh.col));
+    if (shader->color_grid) sh.col = shader->color_grid->dcolor;
     const DevCamera dc = toDev(*cam);
     unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
     // long-ray rounds: one sample per pixel only (with more, the samples of a pixel are accumulated in order by one thread)
@@ -480,7 +538,10 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     if (!ctx || !grid || !cam || !shader || !opts || !film || !film->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (film->width == 0 || film->height == 0) return setError(VDBRT_ERR_INVALID_ARG, "empty film");
     if (cam->width != film->width || cam->height != film->height) return setError(VDBRT_ERR_INVALID_ARG, "camera was built for a different film size");
-    if (shader->kind > VDBRT_SHADER_DIFFUSE) return setError(VDBRT_ERR_UNSUPPORTED, "only the four constant-colour shaders run on the device");
+    if (shader->kind > VDBRT_SHADER_DIFFUSE) return setError(VDBRT_ERR_UNSUPPORTED, "only the matte, normal, position and diffuse shaders run on the device");
+    if (shader->color_grid && (!shader->color_grid->is_color || shader->color_grid->device != ctx->device))
+        return setError(VDBRT_ERR_INVALID_ARG, "color_grid is not a Vec3f grid uploaded to this device with vdbrt_upload_color_grid");
+    if (grid->is_color) return setError(VDBRT_ERR_NOT_FLOAT, "a colour grid cannot be rendered itself");
     if (opts->spp == 0) return setError(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
     if (int rc = checkLevelSet(grid, opts->iso)) return rc;
     DeviceGuard guard(ctx->device);

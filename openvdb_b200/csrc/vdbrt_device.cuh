@@ -661,7 +661,48 @@ struct DevCamera {
     double eye[3], dir[3];
     double scale_w, scale_h, t0, t1;
 };
-struct DevShader { uint32_t kind; float r, g, b, a; double bmin[3], inv[3]; };
+// A NanoGrid<Vec3f> that colours the surface (the GridT = Vec3SGrid forms of the shaders, tools/RayTracer.h:542-725).
+// Node layout of the Vec3f build (nanovdb/NanoVDB.h, verified with a sizeof/offsetof probe): RootData 96 B + 32 B tiles
+// (value at +20), internal nodes: same mask offsets as the float build, 16-byte table entries (Vec3f value | int64 child),
+// leaves: value mask at +16, 512 x 12 B values at +128.
+constexpr uint32_t kColRootTiles = 96, kColTileValue = 20, kColUpperTable = 8256, kColLowerTable = 1088, kColLeafValues = 128;
+struct DevColor {
+    const uint8_t* base;      // null: constant colour
+    const uint8_t* tiles;
+    uint64_t root_off;
+    uint32_t table_size, has_translation;
+    float    background[3];
+    double   inv[3], trans[3];
+};
+struct DevShader { uint32_t kind; float r, g, b, a; double bmin[3], inv[3]; DevColor col; };
+
+// tools::PointSampler::sample(acc, xform.worldToIndex(xyz), v) (tools/Interpolation.h:600-617): probeValue at the nearest
+// voxel, ::round half away from zero; the value of a tile or the background where the tree has no voxel
+__device__ __forceinline__ void colorAt(const DevColor& c, double wx, double wy, double wz, float v[3])
+{
+    if (c.has_translation) { wx = (wx - c.trans[0]) * c.inv[0]; wy = (wy - c.trans[1]) * c.inv[1]; wz = (wz - c.trans[2]) * c.inv[2]; }
+    else { wx = wx * c.inv[0]; wy = wy * c.inv[1]; wz = wz * c.inv[2]; }
+    const int x = int(round(wx)), y = int(round(wy)), z = int(round(wz));
+    const uint8_t* p = nullptr;                                     // where the three floats are
+    const unsigned long long key = rootKey(x, y, z);
+    for (uint32_t i = 0; i < c.table_size; ++i) {
+        const uint8_t* t = c.tiles + kTileSize * i;
+        if (ldg64(t) != key) continue;
+        const long long child = ldgs64(t + 8);
+        if (!child) { p = t + kColTileValue; break; }
+        const uint8_t* u = c.base + c.root_off + child;
+        uint32_t n = upperOffset(x, y, z);
+        if (!maskBit(u + kUpperCMask, n)) { p = u + kColUpperTable + 16u * n; break; }
+        const uint8_t* l = u + ldgs64(u + kColUpperTable + 16u * n);
+        n = lowerOffset(x, y, z);
+        if (!maskBit(l + kLowerCMask, n)) { p = l + kColLowerTable + 16u * n; break; }
+        const uint8_t* f = l + ldgs64(l + kColLowerTable + 16u * n);
+        p = f + kColLeafValues + 12u * leafOffset(x, y, z);
+        break;
+    }
+    if (p) { v[0] = ldgf(p); v[1] = ldgf(p + 4); v[2] = ldgf(p + 8); }
+    else { v[0] = c.background[0]; v[1] = c.background[1]; v[2] = c.background[2]; }
+}
 
 __device__ __forceinline__ void cameraRay(const DevCamera& c, uint32_t i, uint32_t j, double io, double jo, Ray& ray)
 {
@@ -691,6 +732,23 @@ __device__ __forceinline__ void cameraRay(const DevCamera& c, uint32_t i, uint32
 __device__ __forceinline__ float4 shade(const DevShader& s, double wx, double wy, double wz, double nx, double ny, double nz,
                                         double dx, double dy, double dz)
 {
+    if (s.col.base) {
+        // colour from a Vec3f grid sampled at the hit position (GridT = Vec3SGrid, SamplerType = PointSampler)
+        float v[3];
+        colorAt(s.col, wx, wy, wz, v);
+        switch (s.kind) {
+        case 0: return make_float4(v[0], v[1], v[2], 1.0f);                                         // MatteShader<GridT> (:542-562)
+        case 1: return make_float4(float(v[0] * (nx + 1.0)), float(v[1] * (ny + 1.0)), float(v[2] * (nz + 1.0)), 1.0f);   // NormalShader<GridT> (:591-611)
+        case 2: {                                                                                    // PositionShader<GridT> (:640-668)
+            const double rx = (wx - s.bmin[0]) * s.inv[0], ry = (wy - s.bmin[1]) * s.inv[1], rz = (wz - s.bmin[2]) * s.inv[2];
+            return make_float4(v[0] * float(rx), v[1] * float(ry), v[2] * float(rz), 1.0f);
+        }
+        default: {                                                                                   // DiffuseShader<GridT> (:702-725)
+            const float f = float(fabs(nx * dx + ny * dy + nz * dz));
+            return make_float4(v[0] * f, v[1] * f, v[2] * f, 1.0f);
+        }
+        }
+    }
     switch (s.kind) {
     case 0: return make_float4(s.r, s.g, s.b, s.a);                                              // MatteShader (:565-581)
     case 1: {                                                                                    // NormalShader (:614-630)

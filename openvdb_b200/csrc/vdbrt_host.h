@@ -27,6 +27,8 @@ struct vdbrt_grid {
     int device = 0;
     vdbrt_grid_info info;
     vdbrt::DevGrid dgrid;
+    bool is_color = false;                      // a NanoGrid<Vec3f> for the colour-grid shaders (dcolor instead of dgrid)
+    vdbrt::DevColor dcolor;
 };
 
 namespace vdbrt {

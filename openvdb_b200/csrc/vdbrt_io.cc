@@ -144,6 +144,11 @@ int vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, u
 
 int vdbrt_nvdb_read(const char* path, const char* gridName, void** buffer, uint64_t* bytes)
 {
+    return vdbrt_nvdb_read_typed(path, gridName, 1u, buffer, bytes);
+}
+
+int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridType, void** buffer, uint64_t* bytes)
+{
     if (!path || !buffer || !bytes) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     *buffer = nullptr; *bytes = 0;
     File in(path, "rb");
@@ -162,17 +167,18 @@ int vdbrt_nvdb_read(const char* path, const char* gridName, void** buffer, uint6
     std::rewind(in.f);
     std::vector<Entry> all;
     if (int rc = scan(in, all)) return rc;
+    const char* what = gridType == 1u ? "scalar, floating-point" : (gridType == 6u ? "vec3s color" : "matching");
     const Entry* pick = nullptr;
     for (const Entry& e : all) {
         if (gridName && *gridName) { if (e.name == gridName) { pick = &e; break; } }
-        else if (e.meta.gridType == 1u) { pick = &e; break; }       // vdb_render: the first floating-point volume (main.cc:771-786)
+        else if (gridType == 0u || e.meta.gridType == gridType) { pick = &e; break; }   // vdb_render: the first floating-point volume (main.cc:771-786)
     }
     if (!pick) {
         if (gridName && *gridName) return setError(VDBRT_ERR_IO, std::string("no grid named \"") + gridName + "\" in file " + path);
-        return setError(VDBRT_ERR_NOT_FLOAT, std::string("no scalar, floating-point volumes in file ") + path);
+        return setError(VDBRT_ERR_NOT_FLOAT, std::string("no ") + what + " volumes in file " + path);
     }
-    if (gridName && *gridName && pick->meta.gridType != 1u)
-        return setError(VDBRT_ERR_NOT_FLOAT, std::string(gridName) + " is not a scalar, floating-point volume");
+    if (gridType != 0u && pick->meta.gridType != gridType)
+        return setError(VDBRT_ERR_NOT_FLOAT, std::string(gridName ? gridName : "") + " is not a " + what + " volume");   // main.cc:766-769,790-794
     void* p = alignedAlloc(pick->meta.gridSize);
     if (!p) return setError(VDBRT_ERR_IO, "out of host memory");
     std::fseek(in.f, pick->payload, SEEK_SET);

@@ -7,7 +7,7 @@
 //   * the input is a NanoVDB file (.nvdb: segments, codecs NONE / ZIP, or a raw grid buffer) instead of a .vdb file, or one of
 //     the built-in generators  sphere:R[,voxel[,halfwidth]]  torus:R,r  fogsphere:R  (the GPU box has no asset files);
 //   * only .ppm output (the reference needs OpenEXR / libpng for the others and says so the same way);
-//   * -color (a Vec3SGrid shader input) is rejected: the device runs the four constant-colour shaders;
+//   * -color NAME names a Vec3f grid of the same file (the colour-grid forms of the four shaders);
 //   * -cpus is accepted and ignored, -gpu N picks the device.
 #include <vdbrt/RayTracer.h>
 
@@ -101,6 +101,7 @@ std::ostream& operator<<(std::ostream& os, const RenderOpts& o)    // RenderOpts
 "    -v                verbose (print timing and diagnostics)\n"
 "    -h, -help         print this usage message and exit\n"
 "Level set options:\n"
+"    -color S          name of a vec3s volume to be used to set material colors\n"
 "    -isovalue F       isovalue in world units for level set ray intersection (default: " << o.isovalue << ")\n"
 "    -samples N        number of samples (rays) per pixel (default: " << o.samples << ")\n"
 "    -shader S         shader name; either \"diffuse\", \"matte\", \"normal\" or \"position\" (default: " << o.shader << ")\n"
@@ -146,7 +147,7 @@ FloatGrid::Ptr openGrid(Context& ctx, const std::string& name, const std::string
 }
 
 // render<GridType>() of main.cc:414-520
-void render(FloatGrid& grid, const std::string& imgFilename, const RenderOpts& opts)
+void render(FloatGrid& grid, const Vec3SGrid* colorgrid, const std::string& imgFilename, const RenderOpts& opts)
 {
     const vdbrt_grid_info info = grid.info();
     const bool isLevelSet = info.grid_class == VDBRT_GRID_CLASS_LEVEL_SET;
@@ -159,8 +160,8 @@ void render(FloatGrid& grid, const std::string& imgFilename, const RenderOpts& o
     if (opts.lookat) camera->lookAt(opts.target, opts.up);
 
     std::unique_ptr<tools::BaseShader> shader;
-    if (opts.shader == "matte") shader.reset(new tools::MatteShader<>());
-    else if (opts.shader == "normal") shader.reset(new tools::NormalShader<>());
+    if (opts.shader == "matte") { if (colorgrid) shader.reset(new tools::MatteShader<Vec3SGrid>(*colorgrid)); else shader.reset(new tools::MatteShader<>()); }
+    else if (opts.shader == "normal") { if (colorgrid) shader.reset(new tools::NormalShader<Vec3SGrid>(*colorgrid)); else shader.reset(new tools::NormalShader<>()); }
     else if (opts.shader == "position") {
         // bboxIndex(bbox.min().asVec3d(), bbox.max().asVec3d()).applyMap(map): scale(+translate) maps keep the corners (main.cc:452-455)
         double lo[3], hi[3];
@@ -168,8 +169,10 @@ void render(FloatGrid& grid, const std::string& imgFilename, const RenderOpts& o
             const double p = info.index_bbox[a] * info.voxel_size[a] + info.translation[a], q = info.index_bbox[3 + a] * info.voxel_size[a] + info.translation[a];
             lo[a] = std::min(p, q); hi[a] = std::max(p, q);
         }
-        shader.reset(new tools::PositionShader<>(Vec3R(lo[0], lo[1], lo[2]), Vec3R(hi[0], hi[1], hi[2])));
-    } else shader.reset(new tools::DiffuseShader<>());
+        if (colorgrid) shader.reset(new tools::PositionShader<Vec3SGrid>(Vec3R(lo[0], lo[1], lo[2]), Vec3R(hi[0], hi[1], hi[2]), *colorgrid));
+        else shader.reset(new tools::PositionShader<>(Vec3R(lo[0], lo[1], lo[2]), Vec3R(hi[0], hi[1], hi[2])));
+    } else if (colorgrid) shader.reset(new tools::DiffuseShader<Vec3SGrid>(*colorgrid));
+    else shader.reset(new tools::DiffuseShader<>());
 
     if (opts.verbose) std::cout << gProgName << ": ray-tracing..." << std::endl;
     const auto start = std::chrono::steady_clock::now();
@@ -261,7 +264,6 @@ int main(int argc, char* argv[])
     int retcode = EXIT_SUCCESS;
     try {
         if (!endsWith(imgFilename, ".ppm")) throw RuntimeError("vdbrt_render only writes .ppm files (" + imgFilename + ")");
-        if (!opts.color.empty()) throw RuntimeError("-color needs a Vec3SGrid shader input, which the device shaders do not have");
         const auto start = std::chrono::steady_clock::now();
         if (opts.verbose) {
             std::cout << gProgName << ": reading ";
@@ -270,6 +272,8 @@ int main(int argc, char* argv[])
         }
         Context ctx(opts.gpu);
         FloatGrid::Ptr grid = openGrid(ctx, vdbFilename, gridName);
+        Vec3SGrid::Ptr colorgrid;
+        if (!opts.color.empty()) colorgrid = Vec3SGrid::read(ctx, vdbFilename, opts.color);     // "... is not a vec3s color volume" otherwise
         if (opts.verbose) {
             std::ostringstream o;
             o << gProgName << ": ...completed in " << std::setprecision(3) << std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count() << " sec";
@@ -285,7 +289,7 @@ int main(int argc, char* argv[])
             opts.lookat = true;
         }
         if (opts.verbose) std::cout << opts << std::endl;
-        render(*grid, imgFilename, opts);
+        render(*grid, colorgrid.get(), imgFilename, opts);
     } catch (const std::exception& e) {
         std::cerr << gProgName << ": " << e.what() << std::endl;
         retcode = EXIT_FAILURE;

@@ -322,9 +322,94 @@ std::unique_ptr<tools::BaseShader> makeShader(const vdbrt_shader& s)
     }
 }
 
+struct RefColor {
+    Vec3SGrid::Ptr grid;
+    nanovdb::GridHandle<nanovdb::HostBuffer> nano;
+};
+
+// the GridT = Vec3SGrid forms of the shaders (tools/RayTracer.h:542-725), default PointSampler
+std::unique_ptr<tools::BaseShader> makeColorShader(const vdbrt_shader& s, const Vec3SGrid& cg)
+{
+    switch (s.kind) {
+    case VDBRT_SHADER_MATTE: return std::unique_ptr<tools::BaseShader>(new tools::MatteShader<Vec3SGrid>(cg));
+    case VDBRT_SHADER_NORMAL: return std::unique_ptr<tools::BaseShader>(new tools::NormalShader<Vec3SGrid>(cg));
+    case VDBRT_SHADER_POSITION: {
+        math::BBox<Vec3R> bb(Vec3R(0.0), Vec3R(1.0));
+        auto* p = new tools::PositionShader<Vec3SGrid>(bb, cg);
+        const_cast<Vec3R&>(p->mMin) = Vec3R(s.bbox_min[0], s.bbox_min[1], s.bbox_min[2]);
+        const_cast<Vec3R&>(p->mInvDim) = Vec3R(s.inv_dim[0], s.inv_dim[1], s.inv_dim[2]);
+        return std::unique_ptr<tools::BaseShader>(p);
+    }
+    default: return std::unique_ptr<tools::BaseShader>(new tools::DiffuseShader<Vec3SGrid>(cg));
+    }
+}
+
 } // namespace
 
 extern "C" {
+
+// A Vec3SGrid to colour the level set `h` with: its own transform (voxel size `voxel`, translation `t`), one voxel for every
+// active voxel of the level set (nearest colour voxel of its world position) with a colour derived from the coordinate, one
+// active 8^3 tile, background (0.2, 0.4, 0.6).
+void* vdbref_color_grid(void* h, double voxel, const double* t)
+{
+    try {
+        ensureInit();
+        auto* g = static_cast<RefGrid*>(h);
+        auto* c = new RefColor;
+        c->grid = Vec3SGrid::create(Vec3s(0.2f, 0.4f, 0.6f));
+        math::Transform::Ptr xf = math::Transform::createLinearTransform(voxel);
+        xf->postTranslate(Vec3d(t[0], t[1], t[2]));
+        c->grid->setTransform(xf);
+        auto acc = c->grid->getAccessor();
+        Coord first; bool haveFirst = false;
+        for (auto it = g->grid->cbeginValueOn(); it; ++it) {
+            if (!it.isVoxelValue()) continue;
+            const Vec3d w = g->grid->indexToWorld(it.getCoord());
+            const Vec3d p = xf->worldToIndex(w);
+            const Coord ijk(int(::round(p[0])), int(::round(p[1])), int(::round(p[2])));
+            const uint32_t hsh = uint32_t(ijk[0]) * 73856093u ^ uint32_t(ijk[1]) * 19349663u ^ uint32_t(ijk[2]) * 83492791u;
+            acc.setValue(ijk, Vec3s(0.1f + 0.8f * float(hsh & 255u) / 255.0f, 0.1f + 0.8f * float((hsh >> 8) & 255u) / 255.0f,
+                                    0.1f + 0.8f * float((hsh >> 16) & 255u) / 255.0f));
+            if (!haveFirst) { first = ijk; haveFirst = true; }
+        }
+        if (haveFirst) c->grid->tree().addTile(/*level=*/1, first, Vec3s(0.9f, 0.1f, 0.3f), /*active=*/true);   // replaces one leaf by a tile
+        return c;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void vdbref_color_free(void* h) { delete static_cast<RefColor*>(h); }
+uint64_t vdbref_color_nanovdb(void* h, const void** out)
+{
+    try {
+        auto* c = static_cast<RefColor*>(h);
+        if (!c->nano) c->nano = nanovdb::tools::createNanoGrid(*c->grid);
+        if (out) *out = c->nano.data();
+        return c->nano.bufferSize();
+    } catch (std::exception& e) { g_err = e.what(); return 0; }
+}
+
+// tools::rayTrace with one of the colour-grid shaders
+double vdbref_render_levelset_color(void* h, void* color, const vdbref_camera_desc* d, const vdbrt_shader* sh, float iso, uint32_t spp,
+                                    unsigned int seed, int threaded, float* filmRGBA)
+{
+    try {
+        auto* g = static_cast<RefGrid*>(h);
+        auto* c = static_cast<RefColor*>(color);
+        tools::Film film(d->width, d->height);
+        const size_t npx = size_t(d->width) * d->height;
+        std::memcpy(const_cast<tools::Film::RGBA*>(film.pixels()), filmRGBA, npx * 16);
+        auto cam = makeCamera(film, *d);
+        auto shader = makeColorShader(*sh, *c->grid);
+        const auto t0 = std::chrono::steady_clock::now();
+        StockIntersector inter(*g->grid, iso);
+        tools::rayTrace(*g->grid, inter, *shader, *cam, spp, seed, threaded != 0);
+        const auto t1 = std::chrono::steady_clock::now();
+        std::memcpy(filmRGBA, film.pixels(), npx * 16);
+        return std::chrono::duration<double>(t1 - t0).count();
+    } catch (openvdb::ValueError& e) { g_err = std::string("ValueError: ") + e.what(); return -1.0;
+    } catch (openvdb::RuntimeError& e) { g_err = std::string("RuntimeError: ") + e.what(); return -1.0;
+    } catch (std::exception& e) { g_err = e.what(); return -1.0; }
+}
 
 // flatten the reference camera into the product's POD, for checking vdbrt_camera_* bit for bit
 int vdbref_camera_pod(const vdbref_camera_desc* d, vdbrt_camera* out)

@@ -490,8 +490,60 @@ Ray cameraRay(const vdbrt_camera& c, uint32_t i, uint32_t j, double io, double j
 // shaders (tools/RayTracer.h:565-581,614-630,671-690,728-753) and Film::RGBA arithmetic (:231-262)
 // ------------------------------------------------------------------------------------------------------------
 struct RGBA { float r, g, b, a; };
-RGBA shade(const vdbrt_shader& s, const Vec3& xyz, const Vec3& nml, const Vec3& dir)
+} // namespace
+
+// A NanoGrid<Vec3f> for the GridT = Vec3SGrid forms of the shaders (tools/RayTracer.h:542-725).  Vec3f node layout
+// (nanovdb/NanoVDB.h; sizeof/offsetof probe): RootData 96 B + 32 B tiles with the value at +20; internal nodes keep the float
+// build's mask offsets and have 16-byte table entries; leaves: values (12 B each) at +128.
+struct oracle_color {
+    const uint8_t* base = nullptr; const uint8_t* root = nullptr; const uint8_t* tiles = nullptr;
+    uint32_t tableSize = 0; float background[3] = {0.f, 0.f, 0.f};
+    double inv[3], trans[3]; bool hasTranslation = false;
+};
+
+namespace {
+
+// tools::PointSampler::sample(acc, xform.worldToIndex(xyz), v) (tools/Interpolation.h:600-617): probeValue at the voxel
+// ::round()ed from the index position; tile value or background where there is no voxel
+void colorAt(const oracle_color& c, const Vec3& w, float v[3])
 {
+    double p[3];
+    for (int a = 0; a < 3; ++a) p[a] = c.hasTranslation ? (w[a] - c.trans[a]) * c.inv[a] : w[a] * c.inv[a];
+    const int x = int(::round(p[0])), y = int(::round(p[1])), z = int(::round(p[2]));
+    const uint64_t key = uint64_t(uint32_t(z) >> 12) | (uint64_t(uint32_t(y) >> 12) << 21) | (uint64_t(uint32_t(x) >> 12) << 42);
+    const uint8_t* src = nullptr;
+    for (uint32_t i = 0; i < c.tableSize && !src; ++i) {
+        const uint8_t* t = c.tiles + 32 * i;
+        if (rd<uint64_t>(t) != key) continue;
+        const int64_t child = rd<int64_t>(t + 8);
+        if (!child) { src = t + 20; break; }
+        const uint8_t* u = c.root + child;
+        uint32_t n = (((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7);
+        if (!((rd<uint64_t>(u + 32 + 4096 + 8 * (n >> 6)) >> (n & 63)) & 1)) { src = u + 8256 + 16 * n; break; }
+        const uint8_t* l = u + rd<int64_t>(u + 8256 + 16 * n);
+        n = (((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3);
+        if (!((rd<uint64_t>(l + 32 + 512 + 8 * (n >> 6)) >> (n & 63)) & 1)) { src = l + 1088 + 16 * n; break; }
+        const uint8_t* f = l + rd<int64_t>(l + 1088 + 16 * n);
+        src = f + 128 + 12 * (((x & 7) << 6) | ((y & 7) << 3) | (z & 7));
+    }
+    for (int a = 0; a < 3; ++a) v[a] = src ? rd<float>(src + 4 * a) : c.background[a];
+}
+
+RGBA shade(const vdbrt_shader& s, const oracle_color* col, const Vec3& xyz, const Vec3& nml, const Vec3& dir)
+{
+    if (col) {
+        float v[3];
+        colorAt(*col, xyz, v);
+        switch (s.kind) {
+        case VDBRT_SHADER_MATTE: return RGBA{v[0], v[1], v[2], 1.0f};                                              // :549-554
+        case VDBRT_SHADER_NORMAL: return RGBA{float(v[0] * (nml.x + 1.0)), float(v[1] * (nml.y + 1.0)), float(v[2] * (nml.z + 1.0)), 1.0f};   // :598-603
+        case VDBRT_SHADER_POSITION: {                                                                                // :655-661
+            const double rx = (xyz.x - s.bbox_min[0]) * s.inv_dim[0], ry = (xyz.y - s.bbox_min[1]) * s.inv_dim[1], rz = (xyz.z - s.bbox_min[2]) * s.inv_dim[2];
+            return RGBA{v[0] * float(rx), v[1] * float(ry), v[2] * float(rz), 1.0f};
+        }
+        default: { const float f = float(std::fabs(dot(nml, dir))); return RGBA{v[0] * f, v[1] * f, v[2] * f, 1.0f}; }   // :709-717
+        }
+    }
     switch (s.kind) {
     case VDBRT_SHADER_MATTE: return RGBA{s.rgba[0], s.rgba[1], s.rgba[2], s.rgba[3]};
     case VDBRT_SHADER_NORMAL: {   // mRGBA = c*0.5f (alpha -> 1); mRGBA * RGBA(n+1.0) with the doubles cast to float
@@ -634,8 +686,37 @@ static int checkVolume(const oracle_grid* g)
 }
 
 // LevelSetRayTracer::operator() (tools/RayTracer.h:899-918); jitter index n(i,j) = 2*(spp-1)*(j*W+i) (threaded=false order)
+int oracle_color_open(const void* buf, uint64_t bytes, oracle_color** out)
+{
+    if (!buf || !out) return fail(VDBRT_ERR_INVALID_ARG, "null argument");
+    const uint8_t* b = static_cast<const uint8_t*>(buf);
+    if (bytes < GRID_SIZE + TREE_SIZE) return fail(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    const uint64_t magic = rd<uint64_t>(b);
+    if (magic != MAGIC_NUMB && magic != MAGIC_GRID) return fail(VDBRT_ERR_BAD_GRID, "bad magic number");
+    if (rd<uint32_t>(b + OFF_TYPE) != 6) return fail(VDBRT_ERR_NOT_FLOAT, "grid type is not Vec3f");
+    auto* c = new oracle_color;
+    c->base = b; c->root = b + GRID_SIZE + rd<int64_t>(b + GRID_SIZE + 24); c->tiles = c->root + 96;
+    c->tableSize = rd<uint32_t>(c->root + ROOT_TABLESIZE);
+    for (int a = 0; a < 3; ++a) {
+        c->background[a] = rd<float>(c->root + ROOT_BACKGROUND + 4 * a);
+        c->inv[a] = 1.0 / rd<double>(b + OFF_MATD + 8 * 4 * a);
+        c->trans[a] = rd<double>(b + OFF_VECD + 8 * a);
+    }
+    c->hasTranslation = c->trans[0] != 0 || c->trans[1] != 0 || c->trans[2] != 0;
+    *out = c;
+    return VDBRT_OK;
+}
+void oracle_color_close(oracle_color* c) { delete c; }
+
 int oracle_render_levelset(const oracle_grid* g, const vdbrt_camera* cam, const vdbrt_shader* shader, const vdbrt_ls_opts* opts,
                            vdbrt_film* film, vdbrt_aux* aux, vdbrt_counters* ctr, int threads)
+{
+    return oracle_render_levelset_color(g, nullptr, cam, shader, opts, film, aux, ctr, threads);
+}
+
+// the same with a colour grid feeding the shader (shader->color_grid is the PRODUCT's handle and is ignored here)
+int oracle_render_levelset_color(const oracle_grid* g, const oracle_color* color, const vdbrt_camera* cam, const vdbrt_shader* shader,
+                                 const vdbrt_ls_opts* opts, vdbrt_film* film, vdbrt_aux* aux, vdbrt_counters* ctr, int threads)
 {
     if (!g || !cam || !shader || !opts || !film || !film->pixels) return fail(VDBRT_ERR_INVALID_ARG, "null argument");
     if (opts->spp == 0) return fail(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
@@ -662,7 +743,7 @@ int oracle_render_levelset(const oracle_grid* g, const vdbrt_camera* cam, const 
                 Vec3 xi, xw, nml;
                 bool hit = tester.setWorldRay(ray) && LevelSetHDDA<2>::test(tester);
                 RGBA s = bg;
-                if (hit) { tester.getWorldPosAndNml(xi, xw, nml); s = shade(*shader, xw, nml, ray.dir); ++c.hits; }
+                if (hit) { tester.getWorldPosAndNml(xi, xw, nml); s = shade(*shader, color, xw, nml, ray.dir); ++c.hits; }
                 if (k == 0) {
                     col = s;
                     if (aux) {

@@ -34,6 +34,11 @@ int  oracle_intersect_levelset(const oracle_grid* g, const vdbrt_ray* rays, uint
 int  oracle_volume_spans(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, uint32_t max_spans,
                          double* spans, int32_t* counts);
 /* BaseCamera::getRay for pixels ij[2k],ij[2k+1] with offsets (NULL -> 0.5,0.5) */
+typedef struct oracle_color oracle_color;   /* a NanoGrid<Vec3f> feeding the colour-grid shaders */
+int  oracle_color_open(const void* nanovdb_buffer, uint64_t bytes, oracle_color** out);
+void oracle_color_close(oracle_color* c);
+int  oracle_render_levelset_color(const oracle_grid* g, const oracle_color* color, const vdbrt_camera* cam, const vdbrt_shader* shader,
+                                  const vdbrt_ls_opts* opts, vdbrt_film* film, vdbrt_aux* aux, vdbrt_counters* ctr, int threads);
 int  oracle_film_over(float* top, const float* bottom, uint64_t pixels);     /* Film::RGBA::over per pixel, top = top.over(bottom) */
 int  oracle_camera_rays(const vdbrt_camera* cam, const uint32_t* ij, const double* offsets, uint64_t n, vdbrt_ray* rays);
 /* math::DDA<Ray,Log2Dim> trace for the TestRay.testDDA known answers: writes up to max_steps records of

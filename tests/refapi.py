@@ -227,6 +227,30 @@ class Ref:
         self.L.vdbref_jitter_table(seed, out.ctypes.data)
         return out
 
+    # ---- colour grids (GridT = Vec3SGrid forms of the shaders)
+    def color_grid(self, ls, voxel=1.0, translation=(0, 0, 0)):
+        self.L.vdbref_color_grid.restype = C.c_void_p
+        self.L.vdbref_color_grid.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        return self._chk(self.L.vdbref_color_grid(ls, voxel, abi.vec3(translation)))
+
+    def color_nanovdb(self, c):
+        self.L.vdbref_color_nanovdb.restype = C.c_uint64
+        self.L.vdbref_color_nanovdb.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        p = C.c_void_p()
+        n = self.L.vdbref_color_nanovdb(c, C.byref(p))
+        if n == 0:
+            raise RuntimeError("reference: " + self.err())
+        return aligned_copy(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)))
+
+    def render_levelset_color(self, g, c, desc, sh, film, iso=0.0, spp=1, seed=0, threaded=False):
+        self.L.vdbref_render_levelset_color.restype = C.c_double
+        self.L.vdbref_render_levelset_color.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CameraDesc), C.POINTER(abi.Shader), C.c_float,
+                                                        C.c_uint32, C.c_uint, C.c_int, C.c_void_p]
+        t = self.L.vdbref_render_levelset_color(g, c, C.byref(desc), C.byref(sh), iso, spp, seed, int(threaded), film.ctypes.data)
+        if t < 0:
+            raise RuntimeError(self.err())
+        return t
+
     # ---- the path
     def render_levelset(self, g, desc, sh, film, iso=0.0, spp=1, seed=0, threaded=False):
         assert film.dtype == np.float32 and film.flags.c_contiguous
@@ -340,8 +364,16 @@ class Oracle:
         self.L.oracle_grid_probe(g, ijk.ctypes.data, len(ijk), v.ctypes.data, a.ctypes.data)
         return v, a
 
+    def open_color(self, buf):
+        """a serialised NanoGrid<Vec3f> for the colour-grid shaders (the buffer must stay alive)"""
+        self.L.oracle_color_open.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        h = C.c_void_p()
+        self.check(self.L.oracle_color_open(buf.ctypes.data, buf.size, C.byref(h)))
+        self._keep[h.value] = buf
+        return h.value
+
     def render_levelset(self, g, cam, sh, film, iso=0.0, spp=1, jitter=None, part=None, aux=False, counters=False,
-                        threads=1):
+                        threads=1, color=None):
         H, W = film.shape[:2]
         o = abi.LsOpts()
         o.iso, o.spp = iso, spp
@@ -353,9 +385,11 @@ class Oracle:
         ax = AuxArrays(W, H) if aux else None
         pod = ax.pod() if aux else None
         ctr = abi.Counters() if counters else None
-        self.check(self.L.oracle_render_levelset(g, C.byref(cam), C.byref(sh), C.byref(o), C.byref(f),
-                                                 C.byref(pod) if aux else None, C.byref(ctr) if counters else None,
-                                                 threads))
+        self.L.oracle_render_levelset_color.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Shader),
+                                                        C.POINTER(abi.LsOpts), C.POINTER(abi.Film), C.c_void_p, C.c_void_p, C.c_int]
+        self.check(self.L.oracle_render_levelset_color(g, color, C.byref(cam), C.byref(sh), C.byref(o), C.byref(f),
+                                                       C.byref(pod) if aux else None, C.byref(ctr) if counters else None,
+                                                       threads))
         return ax, ctr
 
     def render_volume(self, g, cam, opts, film, counters=False, threads=1):

@@ -90,13 +90,39 @@ def test_fog_volume_from_the_first_float_grid(ctx, oracle, tmp_path):
     assert np.abs(got - want).max() <= 1           # fog colours are double exp() results: 1e-4 relative -> at most one 8-bit step
 
 
+def test_color_option(oracle, tmp_path):
+    """-color Cd: the Vec3f grid named Cd of the same file colours the surface (main.cc:788-795), here through the position shader
+    whose bbox is the world bbox of the active voxels (main.cc:452-458)"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "color_shaders.npz"))
+    scene = tmp_path / "scene.nvdb"
+    z["scene_nvdb"].tofile(str(scene))
+    assert [m.name for m in api.nvdb_list(str(scene))] == [b"surface", b"Cd"]
+    ls, col = api.nvdb_read(str(scene), "surface"), api.nvdb_read(str(scene), "Cd", grid_type=6)
+    assert np.array_equal(col[296:], refapi.aligned_copy(z["color"])[296:])
+    og, oc = oracle.open(ls), oracle.open_color(col)
+    W, H = 160, 120
+    for name, kind in (("diffuse", abi.SHADER_DIFFUSE), ("position", abi.SHADER_POSITION)):
+        out = tmp_path / (name + ".ppm")
+        r = run(scene, out, "-res", "%dx%d" % (W, H), "-t", "18,25,90", "-lookat", "1,2,3", "-color", "Cd", "-shader", name)
+        assert r.returncode == 0, r.stderr
+        info = oracle.info(og)
+        lo = [float(info.index_bbox[a]) for a in range(3)]
+        hi = [float(info.index_bbox[3 + a]) for a in range(3)]
+        sh = api.make_shader(kind, bbox_min=lo, inv_dim=[1.0 / (h - l) for l, h in zip(lo, hi)])
+        film = refapi.new_film(W, H)
+        oracle.render_levelset(og, api.vdb_render_camera(W, H, (18.0, 25.0, 90.0), (1.0, 2.0, 3.0)), sh, film, color=oc)
+        assert np.array_equal(read_ppm(str(out)), to_bits(film)), name
+    assert run(scene, tmp_path / "x.ppm", "-color", "surface").returncode != 0          # "surface is not a vec3s color volume"
+    assert run(scene, tmp_path / "x.ppm", "-color", "nope").returncode != 0
+
+
 def test_generators_and_errors(tmp_path):
     r = run("sphere:30", tmp_path / "s.ppm", "-res", "96x64", "-t", "0,0,100")
     assert r.returncode == 0, r.stderr
     img = read_ppm(str(tmp_path / "s.ppm"))
     assert img.shape == (64, 96, 3) and (img[..., 0] > 0).sum() > 500
     assert run("sphere:30", tmp_path / "s.exr").returncode != 0
-    assert run("sphere:30", tmp_path / "s.ppm", "-color", "Cd").returncode != 0
+    assert run("sphere:30", tmp_path / "s.ppm", "-color", "Cd").returncode != 0          # a generator has no file to read Cd from
     assert run("sphere:30", tmp_path / "s.ppm", "-isovalue", "5").returncode != 0          # outside the narrow band -> ValueError
     assert run("sphere:30", tmp_path / "s.ppm", "-samples", "0").returncode != 0
     assert run(tmp_path / "missing.nvdb", tmp_path / "s.ppm").returncode != 0
