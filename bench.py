@@ -360,20 +360,26 @@ def main():
     host.array[...] = bg
     film_bytes = H * W * 16
 
+    # multi-GPU e2e: ONE host film in POSIX shared memory, mapped and page-locked by every rank; each rank's kernels read the old
+    # pixel of their misses and store the pixels they own over their own PCIe link -- the frame is assembled in host memory with
+    # no gather and no staging copy.  (--gather nccl keeps the copy-in / NCCL gather / copy-out path.)
+    host_shared = None
+    if world > 1 and peer:
+        def exchange_name(n):
+            box = [n]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        host_shared = api.SharedHostFilm(H, W, rank, exchange_name)
+        if rank == 0:
+            host_shared.array[...] = bg
+        dist.barrier()
+
     def e2e_step():
         if world == 1:
-            ctx.render_levelset(grid, cam, sh, host.array, opts=opts_sync)       # H2D film + kernel + D2H film
+            ctx.render_levelset(grid, cam, sh, host.array, opts=opts_sync)       # pinned host film, read and written in place
         elif peer:
-            if rank == 0:
-                api.memcpy(ctx, shared.ptr, host.array.ctypes.data, film_bytes, 0)      # H2D of this step's film into the shared film
-            dist.all_reduce(token)                                                   # peers start after the film is in place
-            step_opts = ctx.ls_opts(part=part)
-            step_opts.flags |= abi.ASYNC
-            ctx.render_levelset(grid, cam, sh, shared.ptr, width=W, height=H, memspace=abi.MEM_DEVICE, opts=step_opts)
-            dist.all_reduce(token)
-            if rank == 0:
-                api.memcpy(ctx, host.array.ctypes.data, shared.ptr, film_bytes, 1)      # D2H of the finished frame
-            torch.cuda.synchronize()
+            ctx.render_levelset(grid, cam, sh, host_shared.array, opts=opts_sync)    # synchronous: returns when this rank's pixels are in the host film
+            dist.barrier()                                                           # the frame is complete when every rank is done
         else:
             film.copy_(torch.from_numpy(host.array), non_blocking=True)          # H2D of this step's film
             step_opts = ctx.ls_opts(part=part)
@@ -396,6 +402,12 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays * args.steps / float(te[0]) / 1e6
+    e2e_match = None
+    if host_shared is not None:
+        if rank == 0:
+            e2e_match = bool(np.array_equal(host_shared.array, film.cpu().numpy()))     # same frame as the peer-store path
+        dist.barrier()
+        host_shared.close()
 
     if rank == 0:
         counters = ctx.count_levelset(grid, cam).as_dict()      # separate instrumented launch, not timed
@@ -426,11 +438,14 @@ def main():
             # single GPU: the pinned host film is read (old pixel of every miss) and written (every pixel) in place by the kernels;
             # multi GPU: the film is copied into and out of rank 0's shared device film
             "e2e": {"value": e2e_value, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": (W * H - hits) * 16 if world == 1 else film_bytes, "d2h_bytes_per_step": film_bytes,
+                    "h2d_bytes_per_step": (W * H - hits) * 16 if (world == 1 or peer) else film_bytes, "d2h_bytes_per_step": film_bytes,
                     "ms_per_step": float(te[0]) * 1e3 / args.steps,
                     "how": ("vdbrt_render_levelset on a pinned host film (tools::Film): misses read their old pixel and all pixels are "
                             "stored over PCIe by the render kernel itself, no staging copies") if world == 1 else
-                           "H2D of the film into rank 0's shared device film, partitioned render with peer stores, D2H of the frame"},
+                           ("one host film in shared memory, page-locked by every rank: each rank's kernels read / store its own pixels over "
+                            "its own PCIe link, a barrier ends the frame; checked against rank 0's device-gathered frame") if peer else
+                           "H2D of the film into rank 0's device film, partitioned render, NCCL gather, D2H of the frame",
+                    "frame_matches_device_path": e2e_match},
             "gpu_launches": args.steps * launches_per_frame,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_render_levelset" + (" + %d long-ray round kernels (k_long_scout/march/finish)" % (launches_per_frame - 1) if launches_per_frame > 1 else ""),

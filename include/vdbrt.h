@@ -200,7 +200,12 @@ int  vdbrt_device_count(void);
 int  vdbrt_set_stream(vdbrt_ctx* ctx, void* cuda_stream);
 int  vdbrt_synchronize(vdbrt_ctx* ctx);
 int  vdbrt_host_alloc(size_t bytes, void** out);         /* pinned host memory (cuda::DeviceBuffer semantics,   */
-int  vdbrt_host_free(void* p);                           /*  nanovdb/cuda/DeviceBuffer.h:316-344)               */
+int  vdbrt_host_free(void* p);
+/* page-lock memory the caller already owns (cudaHostRegister, portable + mapped), e.g. a POSIX shared-memory film that
+ * the processes of all GPUs of a node have mapped: each rank's kernels then store the pixels they own straight into
+ * that one HOST film over their own PCIe link -- the frame is assembled in host memory without any gather.      */
+int  vdbrt_host_register(void* p, size_t bytes);
+int  vdbrt_host_unregister(void* p);                           /*  nanovdb/cuda/DeviceBuffer.h:316-344)               */
 
 /* Device buffers that can be shared between the processes of one node (one process per GPU): rank 0 allocates its film with
  * vdbrt_device_alloc, exports it, every other rank imports the handle and renders the tiles it owns STRAIGHT INTO rank 0's

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("VDBRT_LIBRARY") or os.path.join(os.path.dirname(os.pa
 # every symbol include/vdbrt.h declares
 SYMBOLS = [
     "vdbrt_create", "vdbrt_destroy", "vdbrt_last_error", "vdbrt_device_count", "vdbrt_set_stream", "vdbrt_synchronize",
-    "vdbrt_host_alloc", "vdbrt_host_free", "vdbrt_upload_grid", "vdbrt_free_grid", "vdbrt_grid_get_info",
+    "vdbrt_host_alloc", "vdbrt_host_free", "vdbrt_host_register", "vdbrt_host_unregister", "vdbrt_upload_grid", "vdbrt_free_grid", "vdbrt_grid_get_info",
     "vdbrt_grid_download", "vdbrt_camera_perspective", "vdbrt_camera_orthographic", "vdbrt_camera_look_at",
     "vdbrt_jitter_table", "vdbrt_vol_opts_default", "vdbrt_render_levelset", "vdbrt_render_volume",
     "vdbrt_intersect_levelset", "vdbrt_volume_spans", "vdbrt_count_levelset", "vdbrt_count_volume",
@@ -59,6 +59,8 @@ def load_library():
     L.vdbrt_synchronize.argtypes = [vp]
     L.vdbrt_host_alloc.argtypes = [C.c_size_t, P(vp)]
     L.vdbrt_host_free.argtypes = [vp]
+    L.vdbrt_host_register.argtypes = [vp, C.c_size_t]
+    L.vdbrt_host_unregister.argtypes = [vp]
     L.vdbrt_upload_grid.argtypes = [vp, vp, u64, u32, P(vp)]
     L.vdbrt_free_grid.argtypes = [vp, vp]
     L.vdbrt_upload_color_grid.argtypes = [vp, vp, u64, u32, P(vp)]
@@ -410,6 +412,32 @@ class SharedFilm:
             else:
                 self.ctx.L.vdbrt_ipc_close(self.ctx.handle, self.ptr)
             self.ptr = None
+
+
+class SharedHostFilm:
+    """One HOST film for all ranks of a node: a POSIX shared-memory segment (rank 0 creates it, `exchange` broadcasts its name)
+    that every rank maps and page-locks (vdbrt_host_register).  Each rank renders its tiles with the film as an ordinary host
+    film: its kernels store the pixels it owns over its own PCIe link, nobody copies or gathers anything."""
+
+    def __init__(self, height, width, rank, exchange):
+        from multiprocessing import shared_memory
+        self.rank, self.nbytes = rank, height * width * 16
+        self._creator = shared_memory.SharedMemory(create=True, size=self.nbytes) if rank == 0 else None
+        name = exchange(self._creator.name if rank == 0 else None)
+        self.shm = shared_memory.SharedMemory(name=name)
+        self.array = np.ndarray((height, width, 4), np.float32, buffer=self.shm.buf)
+        self.ptr = self.array.ctypes.data
+        _check(load_library().vdbrt_host_register(self.ptr, self.nbytes))
+
+    def close(self):
+        if self.shm is not None:
+            load_library().vdbrt_host_unregister(self.ptr)
+            self.array = None
+            self.shm.close()
+            if self.rank == 0:
+                self._creator.close()
+                self.shm.unlink()
+            self.shm = None
 
 
 def memcpy(ctx, dst, src, nbytes, kind):

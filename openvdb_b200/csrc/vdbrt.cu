@@ -292,6 +292,13 @@ int vdbrt_host_alloc(size_t bytes, void** out)
     return VDBRT_OK;
 }
 int vdbrt_host_free(void* p) { CUDA_TRY(cudaFreeHost(p)); return VDBRT_OK; }
+int vdbrt_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return VDBRT_OK;
+}
+int vdbrt_host_unregister(void* p) { CUDA_TRY(cudaHostUnregister(p)); return VDBRT_OK; }
 
 int vdbrt_device_alloc(vdbrt_ctx* ctx, size_t bytes, void** out)
 {
