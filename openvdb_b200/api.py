@@ -425,6 +425,11 @@ class SharedHostFilm:
         self._creator = shared_memory.SharedMemory(create=True, size=self.nbytes) if rank == 0 else None
         name = exchange(self._creator.name if rank == 0 else None)
         self.shm = shared_memory.SharedMemory(name=name)
+        try:        # Python < 3.13 also registers ATTACHED segments with the resource tracker, which then unlinks them at exit
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(self.shm._name, "shared_memory")
+        except Exception:
+            pass
         self.array = np.ndarray((height, width, 4), np.float32, buffer=self.shm.buf)
         self.ptr = self.array.ctypes.data
         _check(load_library().vdbrt_host_register(self.ptr, self.nbytes))
@@ -436,7 +441,7 @@ class SharedHostFilm:
             self.shm.close()
             if self.rank == 0:
                 self._creator.close()
-                self.shm.unlink()
+                self._creator.unlink()
             self.shm = None
 
 
