@@ -422,14 +422,16 @@ class SharedHostFilm:
     def __init__(self, height, width, rank, exchange):
         from multiprocessing import shared_memory
         self.rank, self.nbytes = rank, height * width * 16
-        self._creator = shared_memory.SharedMemory(create=True, size=self.nbytes) if rank == 0 else None
-        name = exchange(self._creator.name if rank == 0 else None)
-        self.shm = shared_memory.SharedMemory(name=name)
-        try:        # Python < 3.13 also registers ATTACHED segments with the resource tracker, which then unlinks them at exit
-            from multiprocessing import resource_tracker
-            resource_tracker.unregister(self.shm._name, "shared_memory")
-        except Exception:
-            pass
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            exchange(self.shm.name)
+        else:
+            self.shm = shared_memory.SharedMemory(name=exchange(None))
+            try:    # Python < 3.13 also registers ATTACHED segments with the resource tracker, which would unlink them at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.array = np.ndarray((height, width, 4), np.float32, buffer=self.shm.buf)
         self.ptr = self.array.ctypes.data
         _check(load_library().vdbrt_host_register(self.ptr, self.nbytes))
@@ -440,8 +442,7 @@ class SharedHostFilm:
             self.array = None
             self.shm.close()
             if self.rank == 0:
-                self._creator.close()
-                self._creator.unlink()
+                self.shm.unlink()
             self.shm = None
 
 
