@@ -409,6 +409,17 @@ def main():
         dist.barrier()
         host_shared.close()
 
+    upload = None
+    if rank == 0 and world == 1 and not args.workload.startswith("c4"):
+        # the one-time host -> device upload of the serialised grid (GridHandle::deviceUpload), reported separately
+        hbuf = api.PinnedArray((grid.info.bytes,), np.uint8)
+        ctx.L.vdbrt_grid_download(ctx.handle, grid.handle, hbuf.ptr, grid.info.bytes)
+        t0 = time.perf_counter()
+        g2 = ctx.upload(hbuf.array)
+        ctx.synchronize()
+        upload = {"bytes": int(grid.info.bytes), "ms": (time.perf_counter() - t0) * 1e3, "what": "vdbrt_upload_grid from pinned host memory incl. validation and the node-bbox kernel"}
+        g2.free()
+        hbuf.free()
     if rank == 0:
         counters = ctx.count_levelset(grid, cam).as_dict()      # separate instrumented launch, not timed
         bpr = bytes_per_ray(counters)
@@ -452,6 +463,7 @@ def main():
                          "kernel_ms": kernel_ms_max,
                          "algorithmic_bytes_per_ray": bpr, "rays_per_launch": rays_per_launch, "counters": counters},
             "clocks": clocks,
+            "grid_upload": upload,
         }
         if not args.no_extras and world == 1 and args.workload == "c2":
             try:
