@@ -189,6 +189,9 @@ typedef struct vdbrt_grid_info {
     double   translation[3];
     float    background;
     uint32_t grid_class;      /* VDBRT_GRID_CLASS_*                                                             */
+    uint32_t source_type;     /* nanovdb::GridType of the buffer that was uploaded: 1 Float, 13 Fp4, 14 Fp8, 15 Fp16,
+                               * 16 FpN (quantised leaves are expanded to floats at upload), 6 Vec3f (colour grids)    */
+    uint32_t pad;
 } vdbrt_grid_info;
 
 /* ---- context / memory ------------------------------------------------------------------------------------ */
@@ -223,7 +226,11 @@ int  vdbrt_memcpy(vdbrt_ctx* ctx, void* dst, const void* src, size_t bytes, int 
 /* ---- grids ------------------------------------------------------------------------------------------------
  * replaces nanovdb::GridHandle<cuda::DeviceBuffer>::deviceUpload (nanovdb/cuda/DeviceBuffer.h:411-456) plus the
  * constructor-time work of LinearSearchImpl / VolumeRayIntersector (validation, node-granular bbox:
- * tools/RayIntersector.h:299-319,527-541).  The buffer is a complete NanoGrid<float> (GridData first).        */
+ * tools/RayIntersector.h:299-319,527-541).  The buffer is a complete NanoGrid<float> (GridData first), or a quantised
+ * NanoGrid<Fp4|Fp8|Fp16|FpN> (nanovdb/NanoVDB.h:3752-3980): its leaves are expanded on the device, once, with
+ * LeafData<FpX>::getValue's arithmetic (float(code) * mQuantum + mMinimum) -- what nanovdb::tools::nanoToOpenVDB does before
+ * the reference can ray-trace such a grid (nanovdb/tools/NanoToOpenVDB.h:511-518) -- and the grid then is a NanoGrid<float>
+ * in every respect (vdbrt_grid_info::bytes and vdbrt_grid_download give the expanded buffer).                      */
 int  vdbrt_upload_grid(vdbrt_ctx* ctx, const void* nanovdb_buffer, uint64_t bytes, uint32_t memspace, vdbrt_grid** out);
 /* A NanoGrid<Vec3f> (GridType::Vec3f; createNanoGrid of an openvdb::Vec3SGrid) used as vdbrt_shader::color_grid; replaces
  * the `const GridT& grid` argument of the colour-grid shader constructors.  Scale(+translate) maps only.  Released with
@@ -311,7 +318,8 @@ typedef struct vdbrt_nvdb_meta {   /* io::FileGridMetaData (NanoVDB.h:5913-5929)
 } vdbrt_nvdb_meta;
 /* all grids of all segments of the file (or the one grid of a raw grid buffer); *count = number found           */
 int  vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, uint32_t* count);
-/* grid_name NULL or "": the first float grid (vdb_render's rule, openvdb_cmd/vdb_render/main.cc:771-786).  The buffer
+/* grid_name NULL or "": the first float grid (vdb_render's rule, openvdb_cmd/vdb_render/main.cc:771-786; the quantised
+ * float types Fp4/Fp8/Fp16/FpN count as float: vdbrt_upload_grid takes them).  The buffer
  * is a 32-byte aligned host allocation owned by the caller: pass it to vdbrt_upload_grid, release with vdbrt_buffer_free */
 int  vdbrt_nvdb_read(const char* path, const char* grid_name, void** buffer, uint64_t* bytes);
 /* the same for another value type: grid_type = nanovdb::GridType (1 Float, 6 Vec3f: the colour grid of vdb_render's

@@ -84,6 +84,7 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     info.background = rd<float>(rootHead + kRootBackground);
     for (int i = 0; i < 6; ++i) info.index_bbox[i] = rd<int32_t>(rootHead + 4 * i);
     info.grid_class = rd<uint32_t>(head + OFF_CLASS);
+    info.source_type = 1;                                   // GridType::Float (vdbrt_upload_grid overrides it for quantised sources)
     if (rootOff + 64 + uint64_t(info.root_tiles) * kTileSize > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "root table outside the buffer");
 
     double m[9];
@@ -355,14 +356,39 @@ int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32
     if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (bytes < GRID_SIZE + TREE_SIZE) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
     DeviceGuard guard(ctx->device);
+    const bool onDevice = memspace == VDBRT_MEM_DEVICE;
+    uint8_t head[GRID_SIZE + TREE_SIZE];
+    if (onDevice) {
+        CUDA_TRY(cudaMemcpyAsync(head, buffer, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    } else std::memcpy(head, buffer, sizeof(head));
+    const uint64_t magic = rd<uint64_t>(head);
+    const bool quantised = (magic == MAGIC_NUMB || magic == MAGIC_GRID) && (rd<uint32_t>(head + OFF_VERSION) >> 21) == 32 &&
+                           isQuantisedType(rd<uint32_t>(head + OFF_TYPE));
     auto* g = new vdbrt_grid;
-    g->bytes = bytes; g->device = ctx->device;
-    cudaError_t e = cudaMalloc(&g->dev, bytes);
-    if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
-    e = cudaMemcpyAsync(g->dev, buffer, bytes, memspace == VDBRT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(g->dev); delete g; return cudaFail(e, "cudaMemcpyAsync(grid)"); }
+    g->device = ctx->device;
+    if (quantised) {
+        // NanoGrid<Fp4|Fp8|Fp16|FpN>: the leaves are expanded to floats once, on the device (vdbrt_quant.cu)
+        uint8_t* staged = nullptr;
+        if (!onDevice) {
+            cudaError_t e = cudaMalloc(&staged, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(staged, buffer, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { cudaFree(staged); delete g; return cudaFail(e, "staging the quantised grid"); }
+        }
+        const int rc = expandQuantised(ctx, onDevice ? static_cast<const uint8_t*>(buffer) : staged, bytes, head, &g->dev, &g->bytes);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(staged);
+        if (rc != VDBRT_OK) { delete g; return rc; }
+    } else {
+        g->bytes = bytes;
+        cudaError_t e = cudaMalloc(&g->dev, bytes);
+        if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
+        e = cudaMemcpyAsync(g->dev, buffer, bytes, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(g->dev); delete g; return cudaFail(e, "cudaMemcpyAsync(grid)"); }
+    }
     const int rc = finishGrid(ctx, g);
     if (rc != VDBRT_OK) { cudaFree(g->dev); delete g; return rc; }
+    g->info.source_type = rd<uint32_t>(head + OFF_TYPE);
     *out = g;
     return VDBRT_OK;
 }
@@ -404,6 +430,7 @@ int vdbrt_upload_color_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, 
     info.root_tiles = rd<uint32_t>(rootHead + kRootTableSize);
     info.background = rd<float>(rootHead + kRootBackground);
     info.grid_class = rd<uint32_t>(head + OFF_CLASS);
+    info.source_type = 6;                                   // GridType::Vec3f
     for (int i = 0; i < 6; ++i) info.index_bbox[i] = info.node_bbox[i] = rd<int32_t>(rootHead + 4 * i);
     DevColor& c = g->dcolor;
     std::memset(&c, 0, sizeof(c));

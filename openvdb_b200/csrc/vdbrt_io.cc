@@ -167,17 +167,19 @@ int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridT
     std::rewind(in.f);
     std::vector<Entry> all;
     if (int rc = scan(in, all)) return rc;
+    // "float" includes the quantised float types Fp4/Fp8/Fp16/FpN (GridType 13..16): vdbrt_upload_grid expands them
+    auto matches = [gridType](uint32_t t) { return gridType == 0u || t == gridType || (gridType == 1u && t >= 13u && t <= 16u); };
     const char* what = gridType == 1u ? "scalar, floating-point" : (gridType == 6u ? "vec3s color" : "matching");
     const Entry* pick = nullptr;
     for (const Entry& e : all) {
         if (gridName && *gridName) { if (e.name == gridName) { pick = &e; break; } }
-        else if (gridType == 0u || e.meta.gridType == gridType) { pick = &e; break; }   // vdb_render: the first floating-point volume (main.cc:771-786)
+        else if (matches(e.meta.gridType)) { pick = &e; break; }   // vdb_render: the first floating-point volume (main.cc:771-786)
     }
     if (!pick) {
         if (gridName && *gridName) return setError(VDBRT_ERR_IO, std::string("no grid named \"") + gridName + "\" in file " + path);
         return setError(VDBRT_ERR_NOT_FLOAT, std::string("no ") + what + " volumes in file " + path);
     }
-    if (gridType != 0u && pick->meta.gridType != gridType)
+    if (!matches(pick->meta.gridType))
         return setError(VDBRT_ERR_NOT_FLOAT, std::string(gridName ? gridName : "") + " is not a " + what + " volume");   // main.cc:766-769,790-794
     void* p = alignedAlloc(pick->meta.gridSize);
     if (!p) return setError(VDBRT_ERR_IO, "out of host memory");

@@ -67,6 +67,7 @@ thread_local std::string g_err;
 struct RefGrid {
     FloatGrid::Ptr grid;
     nanovdb::GridHandle<nanovdb::HostBuffer> nano; // lazily created serialisation
+    nanovdb::GridHandle<nanovdb::HostBuffer> quant; // last quantised serialisation (vdbref_grid_nanovdb_quantized)
 };
 
 // Forwarding tester: identical behaviour to the stock LinearSearchImpl, plus bookkeeping.
@@ -238,9 +239,13 @@ void* vdbref_grid_from_nanovdb(const void* buf, uint64_t bytes)
         auto hb = nanovdb::HostBuffer::create(bytes);
         std::memcpy(hb.data(), buf, bytes);
         g->nano = nanovdb::GridHandle<nanovdb::HostBuffer>(std::move(hb));
-        auto* ng = g->nano.grid<float>();
-        if (!ng) { g_err = "not a NanoGrid<float>"; delete g; return nullptr; }
-        g->grid = nanovdb::tools::nanoToOpenVDB(*ng);
+        // float and quantised (Fp4/Fp8/Fp16/FpN) grids: nanoToOpenVDB reads every voxel through the NanoVDB accessors
+        // (LeafData<FpX>::getValue) into a FloatGrid -- the only way the reference ray tracer can be given such a grid
+        const nanovdb::GridType t = g->nano.gridType(0);
+        if (t != nanovdb::GridType::Float && t != nanovdb::GridType::Fp4 && t != nanovdb::GridType::Fp8 &&
+            t != nanovdb::GridType::Fp16 && t != nanovdb::GridType::FpN) { g_err = "not a float-valued NanoGrid"; delete g; return nullptr; }
+        g->grid = gridPtrCast<FloatGrid>(nanovdb::tools::nanoToOpenVDB(g->nano, 0));
+        if (!g->grid) { g_err = "nanoToOpenVDB did not return a FloatGrid"; delete g; return nullptr; }
         return g;
     } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
@@ -255,6 +260,29 @@ uint64_t vdbref_grid_nanovdb(void* h, const void** out)
         if (!g->nano) g->nano = nanovdb::tools::createNanoGrid(*g->grid);
         if (out) *out = g->nano.data();
         return g->nano.bufferSize();
+    } catch (std::exception& e) { g_err = e.what(); return 0; }
+}
+// nanovdb::tools::createNanoGrid<FloatGrid, Fp4|Fp8|Fp16|FpN>: the quantised serialisations (gridType 13..16 = nanovdb::GridType);
+// tolerance < 0 keeps FpN's default oracle (AbsDiff picks its tolerance from the grid class).  The handle is kept by the
+// grid (one quantised serialisation at a time) and *out points into it.
+uint64_t vdbref_grid_nanovdb_quantized(void* h, uint32_t gridType, int dither, float tolerance, const void** out)
+{
+    try {
+        auto* g = static_cast<RefGrid*>(h);
+        namespace nt = nanovdb::tools;
+        using SrcT = openvdb::FloatGrid;
+        const auto sm = nt::StatsMode::Default; const auto cm = nanovdb::CheckMode::Default;
+        const bool d = dither != 0;
+        switch (gridType) {
+        case 13: g->quant = nt::createNanoGrid<SrcT, nanovdb::Fp4>(*g->grid, sm, cm, d); break;
+        case 14: g->quant = nt::createNanoGrid<SrcT, nanovdb::Fp8>(*g->grid, sm, cm, d); break;
+        case 15: g->quant = nt::createNanoGrid<SrcT, nanovdb::Fp16>(*g->grid, sm, cm, d); break;
+        case 16: g->quant = tolerance < 0 ? nt::createNanoGrid<SrcT, nanovdb::FpN>(*g->grid, sm, cm, d)
+                                          : nt::createNanoGrid<SrcT, nanovdb::FpN>(*g->grid, sm, cm, d, 0, nt::AbsDiff(tolerance)); break;
+        default: g_err = "gridType must be 13 (Fp4), 14 (Fp8), 15 (Fp16) or 16 (FpN)"; return 0;
+        }
+        if (out) *out = g->quant.data();
+        return g->quant.bufferSize();
     } catch (std::exception& e) { g_err = e.what(); return 0; }
 }
 // drop the cached serialisation so the next vdbref_grid_nanovdb re-converts from the OpenVDB grid

@@ -57,6 +57,27 @@ inline uint32_t upperOffset(const Coord& c) { return (((c.x & 4095) >> 7) << 10)
 inline uint32_t lowerOffset(const Coord& c) { return (((c.x & 127) >> 3) << 8) | (((c.y & 127) >> 3) << 4) | ((c.z & 127) >> 3); }
 inline uint32_t leafOffset(const Coord& c) { return ((c.x & 7) << 6) | ((c.y & 7) << 3) | (c.z & 7); } // :4516-4519
 
+// Leaf values.  NanoGrid<float>: mValues[n] at +96 (NanoVDB.h:3671-3746).  Quantised grids (GridType 13..16 = Fp4, Fp8, Fp16,
+// FpN) share the 96-byte header LeafFnBase {.. float mMinimum @80, float mQuantum @84 ..} followed by packed codes, and
+// LeafData<FpX>::getValue(n) = float(code_n) * mQuantum + mMinimum (NanoVDB.h:3843, 3876, 3906, 3961); FpN keeps log2 of its bit
+// width in mFlags >> 5 (:3933).  nanovdb::tools::nanoToOpenVDB builds the FloatGrid the reference ray-traces from exactly these
+// values (tools/NanoToOpenVDB.h:511-518).  Compiled with -ffp-contract=off: product and sum round separately.
+inline float leafValue(const uint8_t* lf, uint32_t n, uint32_t gridType) {
+    if (gridType == 1) return rd<float>(lf + LEAF_VALUES + 4 * n);
+    const uint32_t log2w = gridType == 13 ? 2u : gridType == 14 ? 3u : gridType == 15 ? 4u : uint32_t(lf[15] >> 5);
+    const uint8_t* codes = lf + LEAF_VALUES;
+    uint32_t code;
+    switch (log2w) {
+    case 0: code = (codes[n >> 3] >> (n & 7)) & 1u; break;
+    case 1: code = (codes[n >> 2] >> ((n & 3) << 1)) & 3u; break;
+    case 2: code = (codes[n >> 1] >> ((n & 1) << 2)) & 15u; break;
+    case 3: code = codes[n]; break;
+    default: code = rd<uint16_t>(codes + 2 * n); break;
+    }
+    const float product = float(code) * rd<float>(lf + 84);
+    return product + rd<float>(lf + 80);
+}
+
 struct CoordBBox { Coord mn{INT_MAX, INT_MAX, INT_MAX}, mx{INT_MIN, INT_MIN, INT_MIN};
     void expand(const Coord& lo, int dim) { // math::CoordBBox::expand(min, dim)
         for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], lo[a]); mx[a] = std::max(mx[a], lo[a] + dim - 1); } }
@@ -68,7 +89,7 @@ struct oracle_grid {
     const uint8_t* base = nullptr; uint64_t bytes = 0;
     const uint8_t* tree = nullptr; const uint8_t* root = nullptr; const uint8_t* tiles = nullptr;
     const uint8_t* firstLeaf = nullptr; const uint8_t* firstLower = nullptr; const uint8_t* firstUpper = nullptr;
-    uint32_t tableSize = 0, leafCount = 0, lowerCount = 0, upperCount = 0, gridClass = 0;
+    uint32_t tableSize = 0, leafCount = 0, lowerCount = 0, upperCount = 0, gridClass = 0, gridType = 1;
     uint64_t activeVoxels = 0;
     float background = 0.f;
     double scale[3], inv[3], trans[3], voxelSize[3];
@@ -123,7 +144,7 @@ struct Access {
     }
     // ValueAccessor::probeValue: value + active state of voxel or covering tile, background/inactive outside the root table
     bool probeValue(const Coord& c, float& v) {
-        if (const uint8_t* lf = leaf(c)) { const uint32_t n = leafOffset(c); v = rd<float>(lf + LEAF_VALUES + 4 * n); return maskBit(lf + LEAF_VMASK, n); }
+        if (const uint8_t* lf = leaf(c)) { const uint32_t n = leafOffset(c); v = leafValue(lf, n, g.gridType); return maskBit(lf + LEAF_VMASK, n); }
         if (const uint8_t* l = lower(c)) { const uint32_t n = lowerOffset(c); v = rd<float>(l + LOWER_TABLE + 8 * n); return maskBit(l + LOWER_VMASK, n); }
         if (const uint8_t* u = upper(c)) { const uint32_t n = upperOffset(c); v = rd<float>(u + UPPER_TABLE + 8 * n); return maskBit(u + UPPER_VMASK, n); }
         if (const uint8_t* t = findTile(c)) { v = rd<float>(t + 20); return rd<uint32_t>(t + 16) != 0; }
@@ -618,8 +639,10 @@ int oracle_grid_open(const void* buf, uint64_t bytes, oracle_grid** out)
     if (magic != MAGIC_NUMB && magic != MAGIC_GRID) return fail(VDBRT_ERR_BAD_GRID, "bad magic number");
     if ((rd<uint32_t>(b + OFF_VERSION) >> 21) != 32) return fail(VDBRT_ERR_BAD_GRID, "incompatible NanoVDB major version");
     if (rd<uint64_t>(b + OFF_GRIDSIZE) > bytes) return fail(VDBRT_ERR_BAD_GRID, "grid size exceeds buffer");
-    if (rd<uint32_t>(b + OFF_TYPE) != 1) return fail(VDBRT_ERR_NOT_FLOAT, "grid type is not Float");
+    const uint32_t gridType = rd<uint32_t>(b + OFF_TYPE);
+    if (gridType != 1 && !(gridType >= 13 && gridType <= 16)) return fail(VDBRT_ERR_NOT_FLOAT, "grid type is not Float");
     auto* g = new oracle_grid;
+    g->gridType = gridType;
     g->base = b; g->bytes = bytes; g->tree = b + GRID_SIZE;
     g->firstLeaf = g->tree + rd<int64_t>(g->tree + 0); g->firstLower = g->tree + rd<int64_t>(g->tree + 8);
     g->firstUpper = g->tree + rd<int64_t>(g->tree + 16); g->root = g->tree + rd<int64_t>(g->tree + 24);
@@ -653,7 +676,7 @@ int oracle_grid_get_info(const oracle_grid* g, vdbrt_grid_info* info)
     for (int i = 0; i < 6; ++i) info->index_bbox[i] = g->indexBBox[i];
     for (int a = 0; a < 3; ++a) { info->node_bbox[a] = g->nodeBBox.mn[a]; info->node_bbox[3 + a] = g->nodeBBox.mx[a];
         info->voxel_size[a] = g->voxelSize[a]; info->translation[a] = g->trans[a]; }
-    info->background = g->background; info->grid_class = g->gridClass;
+    info->background = g->background; info->grid_class = g->gridClass; info->source_type = g->gridType;
     return VDBRT_OK;
 }
 

@@ -126,6 +126,8 @@ class Ref:
         L.vdbref_grid_free.argtypes = [vp]
         L.vdbref_grid_nanovdb.restype = C.c_uint64
         L.vdbref_grid_nanovdb.argtypes = [vp, C.POINTER(vp)]
+        L.vdbref_grid_nanovdb_quantized.restype = C.c_uint64
+        L.vdbref_grid_nanovdb_quantized.argtypes = [vp, C.c_uint32, C.c_int, C.c_float, C.POINTER(vp)]
         L.vdbref_grid_stats.argtypes = [vp, vp, vp, vp, vp]
         L.vdbref_grid_probe.argtypes = [vp, vp, C.c_uint64, vp, vp]
         L.vdbref_camera_pod.argtypes = [C.POINTER(CameraDesc), C.POINTER(abi.Camera)]
@@ -192,6 +194,14 @@ class Ref:
         """serialised NanoGrid<float> as a 32-byte aligned uint8 array (a copy)"""
         p = C.c_void_p()
         n = self.L.vdbref_grid_nanovdb(g, C.byref(p))
+        if n == 0:
+            raise RuntimeError("reference: " + self.err())
+        return aligned_copy(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)))
+
+    def nanovdb_quantized(self, g, grid_type, dither=False, tolerance=-1.0):
+        """createNanoGrid<FloatGrid, Fp4|Fp8|Fp16|FpN> (grid_type 13..16) as a 32-byte aligned uint8 array (a copy)"""
+        p = C.c_void_p()
+        n = self.L.vdbref_grid_nanovdb_quantized(g, grid_type, 1 if dither else 0, tolerance, C.byref(p))
         if n == 0:
             raise RuntimeError("reference: " + self.err())
         return aligned_copy(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)))
