@@ -56,6 +56,14 @@ template<typename T> T rd(const uint8_t* p) { T v; std::memcpy(&v, p, sizeof(T))
 // ---------------------------------------------------------------------------------------------------------------
 // grid registration: header parsing (host) + node-granular bbox (device)
 // ---------------------------------------------------------------------------------------------------------------
+void vdbrt::destroyGrid(vdbrt_grid* grid)
+{
+    if (!grid) return;
+    cudaFree(grid->dev);
+    cudaFree(grid->halo);
+    delete grid;
+}
+
 int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
 {
     // header: GridData + TreeData, then RootData
@@ -112,6 +120,22 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
         const unsigned long long threads = (unsigned long long)info.root_tiles << 15;
         k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch));
         CUDA_TRY(cudaGetLastError());
+    }
+    // halo blocks of a level set's leaves (DevGrid::halo): an acceleration structure like the node bbox, built once here.
+    // Needs 2944 B per leaf next to the grid; without the memory (or with VDBRT_HALO=0) the stencil walks the leaves instead.
+    const uint64_t leafOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 0));
+    static const bool useHalo = [] { const char* e = std::getenv("VDBRT_HALO"); return !(e && *e == '0'); }();
+    cudaFree(grid->halo); grid->halo = nullptr;
+    if (useHalo && info.grid_class == VDBRT_GRID_CLASS_LEVEL_SET && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
+        leafOff + uint64_t(info.leaf_count) * 2144ull <= grid->bytes) {
+        if (cudaMalloc(&grid->halo, sizeof(float) * size_t(kHaloStride) * size_t(info.leaf_count)) != cudaSuccess) { cudaGetLastError(); grid->halo = nullptr; }
+        else {
+            d.leaf0 = uint32_t(leafOff >> 5); d.leaf_count = info.leaf_count;
+            const unsigned blocks = info.leaf_count < 148u * 32u ? info.leaf_count : 148u * 32u;
+            k_build_halo<<<blocks, 256, 0, ctx->stream>>>(d, leafOff, grid->halo);
+            CUDA_TRY(cudaGetLastError());
+            d.halo = grid->halo;
+        }
     }
     CUDA_TRY(cudaMemcpyAsync(init, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -387,7 +411,7 @@ int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32
         if (e != cudaSuccess) { cudaFree(g->dev); delete g; return cudaFail(e, "cudaMemcpyAsync(grid)"); }
     }
     const int rc = finishGrid(ctx, g);
-    if (rc != VDBRT_OK) { cudaFree(g->dev); delete g; return rc; }
+    if (rc != VDBRT_OK) { destroyGrid(g); return rc; }
     g->info.source_type = rd<uint32_t>(head + OFF_TYPE);
     *out = g;
     return VDBRT_OK;
@@ -453,8 +477,7 @@ int vdbrt_free_grid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     if (!grid) return VDBRT_OK;
     DeviceGuard guard(grid->device);
     if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(grid->dev);
-    delete grid;
+    destroyGrid(grid);
     return VDBRT_OK;
 }
 

@@ -356,7 +356,7 @@ int buildLevelSet(vdbrt_ctx* ctx, const P& prim, const int lo[3], const int hi[3
     g->bytes = total; g->device = ctx->device;
     cudaError_t e = cudaMalloc(&g->dev, total);
     if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
-    auto failGrid = [&](int rc) { cudaFree(g->dev); delete g; return rc; };
+    auto failGrid = [&](int rc) { destroyGrid(g); return rc; };
     cudaMemsetAsync(g->dev, 0, total, st);                    // padding bytes are defined: the buffer is reproducible byte for byte
     DevBuf dLowers, dUppers, dChild, dBlockOf, dLeafOrg, dStats;
     if (cudaMalloc(&dLowers.p, nLower * sizeof(LowerDesc)) != cudaSuccess || cudaMalloc(&dUppers.p, nUpper * sizeof(UpperDesc)) != cudaSuccess ||
@@ -705,7 +705,7 @@ extern "C" int vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* l
     g->bytes = total; g->device = ctx->device;
     cudaError_t e = cudaMalloc(&g->dev, total);
     if (e != cudaSuccess) { delete g; return cudaFail(e, "cudaMalloc(grid)"); }
-    auto failGrid = [&](int rc) { cudaFree(g->dev); delete g; return rc; };
+    auto failGrid = [&](int rc) { destroyGrid(g); return rc; };
     cudaMemsetAsync(g->dev, 0, total, st);                    // padding bytes are defined: the buffer is reproducible byte for byte
     DevBuf dLowers, dUpperSrc, dMap, dLeafSrc, dStats;
     if (cudaMalloc(&dLowers.p, nLower * sizeof(FogLower)) != cudaSuccess || cudaMalloc(&dUpperSrc.p, nUpper * 4) != cudaSuccess ||

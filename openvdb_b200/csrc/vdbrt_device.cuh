@@ -42,7 +42,16 @@ struct DevGrid {
     uint32_t has_translation;
     uint32_t grid_class;
     double   voxel_size0;
+    // Halo blocks (level sets only; null = none): for leaf i, the 9x9x9 values getValue() returns at origin + (0..8)^3 -- the
+    // leaf's own 512 values plus the +x/+y/+z faces, edges and corner taken from whatever lies there (neighbour leaf, tile,
+    // background) -- at halo + 736 * i floats, index 81 x + 9 y + z.  Built once when the grid is registered (k_build_halo).
+    // A BoxStencil cell (tools: math/Stencils.h:414-423) whose base voxel lies in a leaf reads its 8 corners from that
+    // leaf's block with 8 loads off one pointer: no walk over the up to 8 leaves the cell touches.
+    const float* halo;
+    uint32_t leaf0;           // handle (byte offset >> 5) of leaf 0; leaves are 2144 B = 67 handles apart
+    uint32_t leaf_count;
 };
+constexpr uint32_t kHaloStride = 736;   // floats per halo block (729 used; 2944 B keeps blocks 32-byte aligned)
 
 struct RootSmem {
     unsigned long long key[kMaxSmemTiles];
@@ -190,6 +199,19 @@ struct TreeCursor {
     template<bool KEEP>
     __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
     {
+        if (!KEEP && g.halo) {
+            // the level-set path: base voxel inside a leaf (92 % of the stencil moves) -> that leaf's halo block
+            TreeCursor probe = *this;
+            if (probe.descend(g, s, x, y, z) == 0) {
+                const uint32_t i = (probe.n0 - g.leaf0) / 67u;
+                if (i < g.leaf_count) {
+                    const float* b = g.halo + size_t(i) * kHaloStride + (uint32_t(x & 7) * 81u + uint32_t(y & 7) * 9u + uint32_t(z & 7));
+                    v[0] = __ldg(b); v[1] = __ldg(b + 1); v[2] = __ldg(b + 10); v[3] = __ldg(b + 9);
+                    v[4] = __ldg(b + 81); v[5] = __ldg(b + 82); v[6] = __ldg(b + 91); v[7] = __ldg(b + 90);
+                    return;
+                }
+            }
+        }
         const int fmask = (((x & 7) == 7) ? 4 : 0) | (((y & 7) == 7) ? 2 : 0) | (((z & 7) == 7) ? 1 : 0);
         const uint32_t ox0 = uint32_t(x & 7) << 6, ox1 = uint32_t((x + 1) & 7) << 6, oy0 = uint32_t(y & 7) << 3, oy1 = uint32_t((y + 1) & 7) << 3;
         const uint32_t oz0 = uint32_t(z & 7), oz1 = uint32_t((z + 1) & 7);

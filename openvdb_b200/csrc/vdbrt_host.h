@@ -27,6 +27,7 @@ struct vdbrt_grid {
     int device = 0;
     vdbrt_grid_info info;
     vdbrt::DevGrid dgrid;
+    float* halo = nullptr;                      // DevGrid::halo (9^3 values per leaf, level sets only)
     bool is_color = false;                      // a NanoGrid<Vec3f> for the colour-grid shaders (dcolor instead of dgrid)
     vdbrt::DevColor dcolor;
 };
@@ -36,6 +37,8 @@ int setError(int code, const std::string& msg);
 int cudaFail(cudaError_t e, const char* what);
 // parse the header of grid->dev, validate it, fill info/dgrid and compute the node-granular bbox on the device
 int finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid);
+// cudaFree of everything a grid owns on the device + delete
+void destroyGrid(vdbrt_grid* grid);
 // quantised grids (vdbrt_quant.cu): NanoGrid<Fp4|Fp8|Fp16|FpN> in device memory -> freshly allocated NanoGrid<float>
 bool isQuantisedType(uint32_t gridType);
 int expandQuantised(vdbrt_ctx* ctx, const uint8_t* src, uint64_t srcBytes, const uint8_t* head, uint8_t** outDev, uint64_t* outBytes);

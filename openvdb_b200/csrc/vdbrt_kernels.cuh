@@ -873,6 +873,27 @@ __device__ __forceinline__ void expandBox(int* out, int x, int y, int z, int dim
     atomicMax(out + 3, x + dim - 1); atomicMax(out + 4, y + dim - 1); atomicMax(out + 5, z + dim - 1);
 }
 
+// DevGrid::halo: one 256-thread block per leaf (grid-stride), three of the 729 values per thread.  Values outside the leaf are
+// what ValueAccessor::getValue returns there (neighbour leaf, tile of any level, background): a full descent from the root.
+__global__ void __launch_bounds__(256) k_build_halo(const __grid_constant__ DevGrid g, unsigned long long leafOff, float* __restrict__ out)
+{
+    __shared__ RootSmem root;
+    stageRoot(g, root);
+    __syncthreads();
+    for (uint32_t leaf = blockIdx.x; leaf < g.leaf_count; leaf += gridDim.x) {
+        const uint8_t* lf = g.base + leafOff + (unsigned long long)leaf * 2144ull;
+        const int ox = int(ldg32(lf)) & ~7, oy = int(ldg32(lf + 4)) & ~7, oz = int(ldg32(lf + 8)) & ~7;   // mBBoxMin -> origin (NanoVDB.h:4489)
+        float* dst = out + size_t(leaf) * kHaloStride;
+        for (uint32_t t = threadIdx.x; t < 729u; t += 256u) {
+            const uint32_t lx = t / 81u, ly = (t / 9u) % 9u, lz = t % 9u;
+            float v;
+            if (lx < 8u && ly < 8u && lz < 8u) v = ldgf(lf + kLeafValues + 4u * ((lx << 6) | (ly << 3) | lz));
+            else { TreeCursor c; c.reset(); v = c.getValue(g, root, ox + int(lx), oy + int(ly), oz + int(lz)); }
+            dst[t] = v;
+        }
+    }
+}
+
 __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long rootOff, uint32_t tableSize, int* out)
 {
     const unsigned long long gid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
