@@ -202,7 +202,8 @@ struct TreeCursor {
         if (!KEEP && g.halo) {
             // the level-set path: base voxel inside a leaf (92 % of the stencil moves) -> that leaf's halo block
             TreeCursor probe = *this;
-            if (probe.descend(g, s, x, y, z) == 0) {
+            const int depth = probe.descend(g, s, x, y, z);
+            if (depth == 0) {
                 const uint32_t i = (probe.n0 - g.leaf0) / 67u;
                 if (i < g.leaf_count) {
                     const float* b = g.halo + size_t(i) * kHaloStride + (uint32_t(x & 7) * 81u + uint32_t(y & 7) * 9u + uint32_t(z & 7));
@@ -210,6 +211,14 @@ struct TreeCursor {
                     v[4] = __ldg(b + 81); v[5] = __ldg(b + 82); v[6] = __ldg(b + 91); v[7] = __ldg(b + 90);
                     return;
                 }
+            } else if (((x & 7) != 7) && ((y & 7) != 7) && ((z & 7) != 7)) {
+                // no leaf at the base voxel and the cell stays inside its 8^3 block (a ray entering the band through a high
+                // face: tester.init's position lies in the empty block it came from): one tile / the background covers all 8
+                float tile;
+                probe.valueAt(g, s, depth, x, y, z, tile);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = tile;
+                return;
             }
         }
         const int fmask = (((x & 7) == 7) ? 4 : 0) | (((y & 7) == 7) ? 2 : 0) | (((z & 7) == 7) ? 1 : 0);
@@ -505,7 +514,16 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
                 if (COUNT) ++c.voxel;
                 float V;
-                if (acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V) && V > vmin && V < vmax) { w.pendInterp = 2; w.tq = cur.next(); }
+                bool on;
+                // a voxel of a leaf: the value comes from the leaf's halo block when there is one (the same values; the stencil
+                // reads them from there too, so the leaf's own value array stays out of the caches), the active bit from the leaf
+                uint32_t hi = 0xffffffffu;
+                if (depth == 0 && g.halo) hi = (acc.n0 - g.leaf0) / 67u;
+                if (hi < g.leaf_count) {
+                    V = __ldg(g.halo + size_t(hi) * kHaloStride + (uint32_t(cur.vx & 7) * 81u + uint32_t(cur.vy & 7) * 9u + uint32_t(cur.vz & 7)));
+                    on = maskBit(TreeCursor::node(g, acc.n0) + kLeafVMask, leafOffset(cur.vx, cur.vy, cur.vz));
+                } else on = acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V);
+                if (on && V > vmin && V < vmax) { w.pendInterp = 2; w.tq = cur.next(); }
                 w.pendStep = true;
             }
         }
