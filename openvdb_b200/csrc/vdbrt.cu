@@ -121,12 +121,12 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
         k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch));
         CUDA_TRY(cudaGetLastError());
     }
-    // halo blocks of a level set's leaves (DevGrid::halo): an acceleration structure like the node bbox, built once here.
+    // halo blocks of the leaves (DevGrid::halo): an acceleration structure like the node bbox, built once here.
     // Needs 2944 B per leaf next to the grid; without the memory (or with VDBRT_HALO=0) the stencil walks the leaves instead.
     const uint64_t leafOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 0));
     static const bool useHalo = [] { const char* e = std::getenv("VDBRT_HALO"); return !(e && *e == '0'); }();
     cudaFree(grid->halo); grid->halo = nullptr;
-    if (useHalo && info.grid_class == VDBRT_GRID_CLASS_LEVEL_SET && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
+    if (useHalo && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
         leafOff + uint64_t(info.leaf_count) * 2144ull <= grid->bytes) {
         if (cudaMalloc(&grid->halo, sizeof(float) * size_t(kHaloStride) * size_t(info.leaf_count)) != cudaSuccess) { cudaGetLastError(); grid->halo = nullptr; }
         else {

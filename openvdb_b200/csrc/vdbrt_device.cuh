@@ -42,7 +42,7 @@ struct DevGrid {
     uint32_t has_translation;
     uint32_t grid_class;
     double   voxel_size0;
-    // Halo blocks (level sets only; null = none): for leaf i, the 9x9x9 values getValue() returns at origin + (0..8)^3 -- the
+    // Halo blocks (null = none): for leaf i, the 9x9x9 values getValue() returns at origin + (0..8)^3 -- the
     // leaf's own 512 values plus the +x/+y/+z faces, edges and corner taken from whatever lies there (neighbour leaf, tile,
     // background) -- at halo + 736 * i floats, index 81 x + 9 y + z.  Built once when the grid is registered (k_build_halo).
     // A BoxStencil cell (tools: math/Stencils.h:414-423) whose base voxel lies in a leaf reads its 8 corners from that
@@ -199,9 +199,10 @@ struct TreeCursor {
     template<bool KEEP>
     __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
     {
-        if (!KEEP && g.halo) {
-            // the level-set path: base voxel inside a leaf (92 % of the stencil moves) -> that leaf's halo block
-            TreeCursor probe = *this;
+        if (g.halo) {
+            // base voxel inside a leaf (92 % of a level set's stencil moves) -> that leaf's halo block
+            TreeCursor copy = *this;
+            TreeCursor& probe = KEEP ? *this : copy;
             const int depth = probe.descend(g, s, x, y, z);
             if (depth == 0) {
                 const uint32_t i = (probe.n0 - g.leaf0) / 67u;

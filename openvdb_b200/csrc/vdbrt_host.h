@@ -27,7 +27,7 @@ struct vdbrt_grid {
     int device = 0;
     vdbrt_grid_info info;
     vdbrt::DevGrid dgrid;
-    float* halo = nullptr;                      // DevGrid::halo (9^3 values per leaf, level sets only)
+    float* halo = nullptr;                      // DevGrid::halo (9^3 values per leaf)
     bool is_color = false;                      // a NanoGrid<Vec3f> for the colour-grid shaders (dcolor instead of dgrid)
     vdbrt::DevColor dcolor;
 };
