@@ -417,7 +417,7 @@ def main():
         t0 = time.perf_counter()
         g2 = ctx.upload(hbuf.array)
         ctx.synchronize()
-        upload = {"bytes": int(grid.info.bytes), "ms": (time.perf_counter() - t0) * 1e3, "what": "vdbrt_upload_grid from pinned host memory incl. validation and the node-bbox kernel"}
+        upload = {"bytes": int(grid.info.bytes), "ms": (time.perf_counter() - t0) * 1e3, "what": "vdbrt_upload_grid from pinned host memory incl. validation, the node-bbox kernel and the halo-block kernel (2944 B per leaf next to the grid)"}
         g2.free()
         hbuf.free()
     if rank == 0:
