@@ -61,6 +61,7 @@ void vdbrt::destroyGrid(vdbrt_grid* grid)
     if (!grid) return;
     cudaFree(grid->dev);
     cudaFree(grid->halo);
+    cudaFree(grid->lowmask);
     delete grid;
 }
 
@@ -120,6 +121,19 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
         const unsigned long long threads = (unsigned long long)info.root_tiles << 15;
         k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch));
         CUDA_TRY(cudaGetLastError());
+    }
+    // "leaf or active tile" masks of the lower nodes (DevGrid::lowmask), for the volume walk; VDBRT_LOWMASK=0 keeps them off
+    const uint64_t lowerOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 8));
+    static const bool useLowmask = [] { const char* e = std::getenv("VDBRT_LOWMASK"); return !(e && *e == '0'); }();
+    cudaFree(grid->lowmask); grid->lowmask = nullptr;
+    if (useLowmask && info.lower_count && info.root_tiles && !(lowerOff & 31) && lowerOff + uint64_t(info.lower_count) * 33856ull <= grid->bytes) {
+        if (cudaMalloc(&grid->lowmask, 512 * size_t(info.lower_count)) != cudaSuccess) { cudaGetLastError(); grid->lowmask = nullptr; }
+        else {
+            const unsigned long long words = (unsigned long long)info.lower_count << 6;
+            k_build_lowmask<<<unsigned((words + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, lowerOff, info.lower_count, grid->lowmask);
+            CUDA_TRY(cudaGetLastError());
+            d.lowmask = grid->lowmask; d.lower0 = uint32_t(lowerOff >> 5); d.lower_count = info.lower_count;
+        }
     }
     // halo blocks of the leaves (DevGrid::halo): an acceleration structure like the node bbox, built once here.
     // Needs 2944 B per leaf next to the grid; without the memory (or with VDBRT_HALO=0) the stencil walks the leaves instead.

@@ -50,6 +50,12 @@ struct DevGrid {
     const float* halo;
     uint32_t leaf0;           // handle (byte offset >> 5) of leaf 0; leaves are 2144 B = 67 handles apart
     uint32_t leaf_count;
+    // "leaf or active tile" masks of the lower nodes (null = none): lowmask[64 i + w] = child-mask word w | value-mask word w of
+    // lower node i (512 B per node, built by k_build_lowmask).  The volume walk only needs this one bit per 8^3 cell: at the
+    // leaf level VolumeHDDA counts any existing leaf as active, otherwise the tile's state (math/DDA.h:308-309,326-327).
+    const unsigned long long* lowmask;
+    uint32_t lower0;          // handle of lower node 0; lower nodes are 33856 B = 1058 handles apart
+    uint32_t lower_count;
 };
 constexpr uint32_t kHaloStride = 736;   // floats per halo block (729 used; 2944 B keeps blocks 32-byte aligned)
 
@@ -659,16 +665,25 @@ struct SpanWalk {
         }
         needStep = true;
         bound = cur.t0;
-        const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
-        if (COUNT) { if (lvl == 0) ++c.root; else if (lvl == 1) ++c.upper; else ++c.lower; }
-        if (lvl < 2 && depth <= 2 - lvl) {              // child node: walk it
-            c0 = cur.t0; c1 = cur.next();
-            sm.park(slotBase + lvl, cur);
-            ++lvl; pendLevel = true; needStep = false;
-            return kSpanContinue;
+        bool active;
+        if (lvl == 2 && g.lowmask && acc.n1 && !(uint32_t((cur.vx ^ acc.kx) | (cur.vy ^ acc.ky) | (cur.vz ^ acc.kz)) & ~127u)) {
+            // a cell of the lower node the cursor is in (the usual case; rounding can push a cell outside): one mask word
+            if (COUNT) ++c.lower;
+            const uint32_t n = lowerOffset(cur.vx, cur.vy, cur.vz);
+            const uint32_t i = min((acc.n1 - g.lower0) / 1058u, g.lower_count - 1u);
+            active = (__ldg(g.lowmask + ((size_t(i) << 6) | (n >> 6))) >> (n & 63u)) & 1ull;
+        } else {
+            const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
+            if (COUNT) { if (lvl == 0) ++c.root; else if (lvl == 1) ++c.upper; else ++c.lower; }
+            if (lvl < 2 && depth <= 2 - lvl) {              // child node: walk it
+                c0 = cur.t0; c1 = cur.next();
+                sm.park(slotBase + lvl, cur);
+                ++lvl; pendLevel = true; needStep = false;
+                return kSpanContinue;
+            }
+            // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state
+            active = (lvl == 2 && depth == 0) ? true : acc.activeAt(g, s, depth, cur.vx, cur.vy, cur.vz);
         }
-        // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state
-        const bool active = (lvl == 2 && depth == 0) ? true : acc.activeAt(g, s, depth, cur.vx, cur.vy, cur.vz);
         if (active) {
             if (ts0 < 0.0) ts0 = cur.t0;
         } else if (ts0 >= 0.0) {

@@ -28,6 +28,7 @@ struct vdbrt_grid {
     vdbrt_grid_info info;
     vdbrt::DevGrid dgrid;
     float* halo = nullptr;                      // DevGrid::halo (9^3 values per leaf)
+    unsigned long long* lowmask = nullptr;      // DevGrid::lowmask (512 B per lower node)
     bool is_color = false;                      // a NanoGrid<Vec3f> for the colour-grid shaders (dcolor instead of dgrid)
     vdbrt::DevColor dcolor;
 };

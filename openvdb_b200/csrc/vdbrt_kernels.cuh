@@ -873,6 +873,16 @@ __device__ __forceinline__ void expandBox(int* out, int x, int y, int z, int dim
     atomicMax(out + 3, x + dim - 1); atomicMax(out + 4, y + dim - 1); atomicMax(out + 5, z + dim - 1);
 }
 
+// DevGrid::lowmask: one thread per mask word of every lower node
+__global__ void k_build_lowmask(const uint8_t* __restrict__ base, unsigned long long lowerOff, uint32_t lowerCount, unsigned long long* __restrict__ out)
+{
+    const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const uint32_t node = uint32_t(t >> 6), w = uint32_t(t & 63u);
+    if (node >= lowerCount) return;
+    const uint8_t* l = base + lowerOff + (unsigned long long)node * 33856ull;
+    out[t] = ldg64(l + kLowerCMask + 8u * w) | ldg64(l + kLowerVMask + 8u * w);
+}
+
 // DevGrid::halo: one 256-thread block per leaf (grid-stride), three of the 729 values per thread.  Values outside the leaf are
 // what ValueAccessor::getValue returns there (neighbour leaf, tile of any level, background): a full descent from the root.
 __global__ void __launch_bounds__(256) k_build_halo(const __grid_constant__ DevGrid g, unsigned long long leafOff, float* __restrict__ out)
