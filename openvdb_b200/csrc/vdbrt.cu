@@ -145,7 +145,8 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
         if (cudaMalloc(&grid->halo, sizeof(float) * size_t(kHaloStride) * size_t(info.leaf_count)) != cudaSuccess) { cudaGetLastError(); grid->halo = nullptr; }
         else {
             d.leaf0 = uint32_t(leafOff >> 5); d.leaf_count = info.leaf_count;
-            const unsigned blocks = info.leaf_count < 148u * 32u ? info.leaf_count : 148u * 32u;
+            const unsigned cap = unsigned(ctx->sm_count > 0 ? ctx->sm_count : 148) * 32u;          // a multiple of the SM count, grid-stride loop
+            const unsigned blocks = info.leaf_count < cap ? info.leaf_count : cap;
             k_build_halo<<<blocks, 256, 0, ctx->stream>>>(d, leafOff, grid->halo);
             CUDA_TRY(cudaGetLastError());
             d.halo = grid->halo;
