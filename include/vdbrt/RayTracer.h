@@ -54,7 +54,8 @@ class FloatGrid
 {
 public:
     using Ptr = std::shared_ptr<FloatGrid>;
-    /// upload a serialised grid (nanovdb::GridHandle<HostBuffer>::data(), size())
+    /// upload a serialised grid (nanovdb::GridHandle<HostBuffer>::data(), size()): NanoGrid<float>, or a quantised
+    /// NanoGrid<Fp4|Fp8|Fp16|FpN> (createNanoGrid<openvdb::FloatGrid, nanovdb::Fp8>(grid) ...), whose leaves are expanded on the device
     static Ptr upload(Context& ctx, const void* nanovdbBuffer, uint64_t bytes)
     {
         vdbrt_grid* g = nullptr;
