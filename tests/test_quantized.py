@@ -95,6 +95,29 @@ def test_oracle_dequantises_like_the_reference(ref, oracle, name, gtype, tol):
     ref.free(rq); ref.free(g); oracle.close(og)
 
 
+@pytest.mark.parametrize("gtype", [13, 14, 16])
+def test_dithered_quantisation(ref, oracle, gtype):
+    """createNanoGrid(.., ditherOn = true) chooses other codes (DitherLUT); the leaves decode the same way"""
+    g = golden_sphere(ref)
+    plain = ref.nanovdb_quantized(g, gtype)
+    q = ref.nanovdb_quantized(g, gtype, dither=True)
+    assert (q.size == plain.size or gtype == 16) and not np.array_equal(q, plain)        # FpN may also pick other bit widths
+    og = oracle.open(q)
+    rq = ref.from_nanovdb(q)
+    ijk = probe_points()
+    rv, ra = ref.probe(rq, ijk)
+    ov, oa = oracle.probe(og, ijk)
+    assert np.array_equal(rv.view(np.uint32), ov.view(np.uint32)) and np.array_equal(ra, oa)
+    cam, d = ls_camera()
+    sh = api.make_shader(abi.SHADER_NORMAL)
+    rfilm = refapi.new_film(W, H)
+    ref.render_levelset(rq, d, sh, rfilm)
+    ofilm = refapi.new_film(W, H)
+    oracle.render_levelset(og, cam, sh, ofilm)
+    assert np.array_equal(rfilm, ofilm)
+    ref.free(rq); ref.free(g); oracle.close(og)
+
+
 def test_fpn_fixture_mixes_bit_widths(gold):
     hist, end = fpn_widths(gold["ls_fpn_loose"])
     assert len(hist) >= 3, hist                   # 1-, 2-, 4-bit leaves ...
