@@ -117,6 +117,12 @@ typedef struct vdbrt_ls_opts {
  * the slowest tile bounds the frame time), off otherwise; one sample per pixel only.                            */
 #define VDBRT_LS_ROUNDS_ON  4u
 #define VDBRT_LS_ROUNDS_OFF 8u
+/* Heavy tiles first (csrc/vdbrt_kernels.cuh, k_probe_levelset): one budgeted probe ray per 8x4 tile estimates its cost and
+ * the work queue hands out the expensive strips of tiles before the rest, so that no silhouette tile (every ray grazing
+ * the surface) starts when the queue is nearly empty.  Same pixels either way.  Default: on when a resident warp gets
+ * two tiles or more.                                                                                            */
+#define VDBRT_LS_ORDER_ON   16u
+#define VDBRT_LS_ORDER_OFF  32u
 
 /* VolumeRender parameters (tools/RayTracer.h:162-207; defaults :929-936).                                      */
 typedef struct vdbrt_vol_opts {
@@ -286,6 +292,11 @@ int  vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
 /* device time (ms, CUDA events on the context's stream) of the kernel(s) of the last render call, and how many
  * kernels of this library that call launched                                                                   */
 int  vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches);
+/* Scheduling knobs of one context (the environment variables VDBRT_LS_* / VDBRT_FOG_* set the same values when the
+ * context is created; this call is for tests and for measuring one setting against another in one process).  Keys:
+ * "ls_strip", "ls_strip_ratio", "ls_refill", "ls_eager", "ls_order", "ls_probe_cap", "ls_probe_b", "ls_tail", "ls_budget", "ls_factor", "ls_rounds", "ls_leaves0" .. "ls_leaves7".
+ * None of them changes a pixel.  Unknown key -> VDBRT_ERR_INVALID_ARG.                                           */
+int  vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value);
 
 /* ---- grid construction on the GPU (inputs for benches) ------------------------------------
  * Same voxel values/topology as nanovdb::tools::createLevelSetSphere/Torus (nanovdb/tools/CreatePrimitives.h:

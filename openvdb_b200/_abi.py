@@ -13,6 +13,8 @@ LS_UNIFORM_BG = 1
 ASYNC = 2
 LS_ROUNDS_ON = 4
 LS_ROUNDS_OFF = 8
+LS_ORDER_ON = 16
+LS_ORDER_OFF = 32
 
 ERR_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "BAD_GRID", 3: "NOT_FLOAT", 4: "NOT_LEVELSET", 5: "NONUNIFORM",

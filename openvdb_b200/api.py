@@ -24,7 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
-    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over",
+    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over", "vdbrt_set_tuning",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library():
     L.vdbrt_count_levelset.argtypes = [vp, vp, P(abi.Camera), P(abi.LsOpts), P(abi.Counters)]
     L.vdbrt_count_volume.argtypes = [vp, vp, P(abi.Camera), P(abi.VolOpts), P(abi.Counters)]
     L.vdbrt_last_kernel_ms.argtypes = [vp, P(C.c_float), P(u32)]
+    L.vdbrt_set_tuning.argtypes = [vp, C.c_char_p, u32]
     L.vdbrt_build_levelset_sphere.argtypes = [vp, dbl, P(dbl), dbl, dbl, P(vp)]
     L.vdbrt_build_levelset_torus.argtypes = [vp, dbl, dbl, P(dbl), dbl, dbl, P(vp)]
     L.vdbrt_build_levelset_spheres.argtypes = [vp, vp, u32, dbl, dbl, P(vp)]
@@ -283,7 +284,7 @@ class Context:
         f.bg_rgba = (C.c_float * 4)(*bg)
         return f
 
-    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None, rounds=None):
+    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None, rounds=None, order=None):
         o = abi.LsOpts()
         o.iso, o.spp = iso, spp
         if spp > 1:
@@ -294,6 +295,8 @@ class Context:
         o.flags = abi.LS_UNIFORM_BG if uniform_bg else 0
         if rounds is not None:      # long-ray rounds: None = library default (on for partitioned frames)
             o.flags |= abi.LS_ROUNDS_ON if rounds else abi.LS_ROUNDS_OFF
+        if order is not None:       # heavy tiles first: None = library default (on when a warp gets two tiles or more)
+            o.flags |= abi.LS_ORDER_ON if order else abi.LS_ORDER_OFF
         return o
 
     def render_levelset(self, grid, cam, shader, film, iso=0.0, spp=1, seed=0, part=None, aux=None, uniform_bg=False,
@@ -337,6 +340,11 @@ class Context:
         c = abi.Counters()
         _check(self.L.vdbrt_count_volume(self.handle, grid.handle, C.byref(cam), C.byref(opts), C.byref(c)))
         return c
+
+    def set_tuning(self, **kw):
+        """scheduling knobs (vdbrt_set_tuning): ls_strip, ls_refill, ls_eager, ls_order, ls_probe_cap, ls_probe_b, ..."""
+        for k, v in kw.items():
+            _check(self.L.vdbrt_set_tuning(self.handle, k.encode(), int(v)))
 
     def last_kernel_ms(self):
         ms, n = C.c_float(), C.c_uint32()

@@ -271,11 +271,16 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ctx->stream = ctx->own_stream;
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    if (std::getenv("VDBRT_TIME_PROBE")) CUDA_TRY(cudaEventCreate(&ctx->evp));
     CUDA_TRY(cudaMalloc(&ctx->scratch, 4096));
     CUDA_TRY(cudaMemset(ctx->scratch, 0, 4096));
     // tuning knobs of the long-ray rounds (see vdbrt_kernels.cuh); the defaults were measured on the B200
     const char* ev = std::getenv("VDBRT_LS_BUDGET");
     ctx->ls_budget = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultBudget;
+    ev = std::getenv("VDBRT_LS_TAIL");
+    ctx->ls_tail = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultTail;
+    ev = std::getenv("VDBRT_LS_VOXEL_ONLY");
+    ctx->ls_voxel_only = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : 0u;
     ev = std::getenv("VDBRT_LS_FACTOR");
     ctx->ls_factor = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultFactor;
     ev = std::getenv("VDBRT_LS_ROUNDS");
@@ -286,6 +291,16 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     // 1.00 -> 0.83 ms per rank at 1/8 of C2 against the six rounds 2,4,12,32,64,128)
     static const uint32_t kLeaves[kMaxRounds] = {8, 128, 128, 128, 128, 128, 128, 128};
     for (int r = 0; r < kMaxRounds; ++r) ctx->ls_leaves[r] = kLeaves[r];
+    // feeding of the render warps (Sched, vdbrt_kernels.cuh); defaults measured on the B200 (profiles/r02_summary.md)
+    auto envU = [](const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? uint32_t(std::strtoul(e, nullptr, 10)) : dflt; };
+    ctx->ls_strip = envU("VDBRT_LS_STRIP", 1);            // 8x4 tiles per strip (measured: anything above 1 costs L2 locality)
+    ctx->ls_strip_ratio = envU("VDBRT_LS_STRIP_RATIO", 4);  // ... but at least this many strips per resident warp (0: no such rule)
+    ctx->ls_refill = envU("VDBRT_LS_REFILL", 32);         // idle lanes that trigger a refill from the strip (32: whole tiles)
+    ctx->ls_affine = envU("VDBRT_LS_AFFINE", 0);          // SM-affine queues: strips per chunk (0: one global queue)
+    ctx->ls_eager = envU("VDBRT_LS_EAGER", 0);            // take the next strip while lanes of the old one are still running
+    ctx->ls_order = envU("VDBRT_LS_ORDER", 0);            // heavy strips first: 0 off, 1 on, 2 when a warp gets >= 2 tiles
+    ctx->ls_probe_cap = envU("VDBRT_LS_PROBE_CAP", 128);  // steps a probe ray may take; unfinished = list A
+    ctx->ls_probe_b = envU("VDBRT_LS_PROBE_B", 64);       // steps from which a strip goes to list B
     if ((ev = std::getenv("VDBRT_LS_LEAVES"))) {
         int r = 0;
         for (const char* q = ev; *q && r < kMaxRounds; ++r) { ctx->ls_leaves[r] = uint32_t(std::strtoul(q, const_cast<char**>(&q), 10)); if (*q == ',') ++q; }
@@ -304,6 +319,7 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->lng) cudaFree(ctx->lng);
+    if (ctx->ord) cudaFree(ctx->ord);
     cudaFree(ctx->scratch);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->own_stream);
@@ -520,14 +536,18 @@ int vdbrt_grid_download(vdbrt_ctx* ctx, const vdbrt_grid* grid, void* dst, uint6
 static int longBuffers(vdbrt_ctx* ctx, size_t slots, LongBufs& lb)
 {
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
-    const size_t capLong = std::max<size_t>(slots / 4, 65536), capSeg = capLong * 16;
+    static const size_t capDiv = [] { const char* e = std::getenv("VDBRT_LS_CAPDIV"); const long v = e ? std::atol(e) : 4; return size_t(v < 1 ? 1 : v); }();
+    // tail rule: only rays that are in flight when the queue runs dry can be suspended (32 per resident warp)
+    const size_t inFlight = size_t(ctx->sm_count) * VDBRT_MINBLOCKS * kBlockThreads;
+    const size_t capLong = ctx->ls_tail ? std::max<size_t>(std::min(slots, 2 * inFlight), 65536) : std::max<size_t>(slots / capDiv, 65536);
+    const size_t capSeg = capLong * (ctx->ls_tail ? 32 : 16);
     const size_t oCtl = 0, oA = up(sizeof(LongCtl)), oB = oA + up(capLong * 4), oR = oB + up(capLong * 4), oI = oR + up(capLong * sizeof(LongRay));
     const size_t oO = oI + up(capSeg * sizeof(SegIn)), total = oO + up(capSeg * sizeof(SegOut));
     if (int rc = ensureBuffer(&ctx->lng, &ctx->lng_cap, total)) return rc;
     uint8_t* b = static_cast<uint8_t*>(ctx->lng);
     lb.ctl = reinterpret_cast<LongCtl*>(b + oCtl); lb.liveA = reinterpret_cast<uint32_t*>(b + oA); lb.liveB = reinterpret_cast<uint32_t*>(b + oB);
     lb.rays = reinterpret_cast<LongRay*>(b + oR); lb.segIn = reinterpret_cast<SegIn*>(b + oI); lb.segOut = reinterpret_cast<SegOut*>(b + oO);
-    lb.capLong = uint32_t(capLong); lb.capSeg = uint32_t(capSeg); lb.budget = ctx->ls_budget; lb.factor = ctx->ls_factor;
+    lb.capLong = uint32_t(capLong); lb.capSeg = uint32_t(capSeg); lb.budget = ctx->ls_budget; lb.factor = ctx->ls_factor; lb.tail = ctx->ls_tail; lb.voxel_only = ctx->ls_voxel_only;
     return VDBRT_OK;
 }
 
@@ -545,35 +565,89 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     if (shader->color_grid) sh.col = shader->color_grid->dcolor;
     const DevCamera dc = toDev(*cam);
     unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
-    // long-ray rounds: one sample per pixel only (with more, the samples of a pixel are accumulated in order by one thread)
-    // They pay when ONE slow tile is long against everything else a warp has to do, i.e. when this launch has few tiles
-    // per resident warp -- a small share of a frame that is split over several GPUs (measured on C2, 1/8 of the frame:
-    // 1.9 -> 1.0 ms per rank).  With many tiles per warp the work queue balances the frame by itself and the rounds only
-    // cost (C2 whole frame 3.75 -> 3.9 ms, C4 at 1/8: 6.8 -> 8.3 ms), so the default is: partitioned frame AND fewer than
-    // kRoundsMaxTilesPerWarp tiles per warp.  VDBRT_LS_ROUNDS_ON / _OFF override.
+    // long-ray rounds: one sample per pixel only (with more, the samples of a pixel are accumulated in order by one thread).
+    // They pay when the launch is bounded by its slowest tile, i.e. when it has few tiles per resident warp -- a small frame, or a
+    // small share of a frame that is split over several GPUs (C2 at 1/8 of the frame: 1.22 -> 0.68 ms per rank, 1/4: 1.41 -> 0.95).
+    // With many tiles per warp the tail is a small part of the launch and the rounds cost about what they save (C2 whole frame
+    // 2.72 -> 2.63 ms), and where the long rays cross empty space rather than graze a surface they lose outright (C4: 34.4 -> 36.7 ms,
+    // 1/8 share 5.2 -> 5.5 ms: the scout walks empty cells no faster than the render kernel): profiles/r02_summary.md.  Default: fewer
+    // than kRoundsMaxTilesPerWarp tiles per warp.  VDBRT_LS_ROUNDS_ON / _OFF override.  WHICH rays are suspended is the tail rule
+    // (ctx->ls_tail, vdbrt_kernels.cuh) unless VDBRT_LS_TAIL=0 selects round 1's per-tile budget.
     const double tilesPerWarp = double(tm.items) / (double(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32));
-    const bool automatic = opts->part.count > 1 && tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
-    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && ctx->ls_budget != 0 && ctx->ls_rounds != 0;
+    const bool automatic = tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
+    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
     LongBufs lb = {};
     lb.budget = 0xffffffffu;
     if (rounds) {
         if (int rc = longBuffers(ctx, size_t(tm.items) * 32, lb)) return rc;
         CUDA_TRY(cudaMemsetAsync(lb.ctl, 0, sizeof(LongCtl), ctx->stream));
     }
+    // how the warps are fed (Sched, vdbrt_kernels.cuh): strips of 8x4 tiles, lanes re-fed from the warp's own strip, heavy strips first
+    Sched sc = {};
+    // strips as long as the launch still has at least four of them per resident warp (a small share of a partitioned frame gets single tiles)
+    const uint32_t residentWarps = uint32_t(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32);
+    sc.strip_tiles = ctx->ls_strip ? ctx->ls_strip : 1u;
+    if (ctx->ls_strip_ratio) sc.strip_tiles = std::max(1u, std::min(sc.strip_tiles, tm.items / (ctx->ls_strip_ratio * residentWarps)));
+    sc.refill = ctx->ls_refill; sc.eager = ctx->ls_eager;
+    if (sc.refill < 1u || sc.refill > 32u) sc.refill = 32u;
+    const uint32_t nStrips = (tm.items + sc.strip_tiles - 1u) / sc.strip_tiles;
+    // heavy strips first: worth a probe launch when a warp gets more than a couple of tiles (otherwise everything starts at once anyway)
+    const bool orderAuto = ctx->ls_order == 1u || (ctx->ls_order == 2u && tilesPerWarp >= 2.0);
+    const bool order = !dCounters && nStrips > 1u && !(opts->flags & VDBRT_LS_ORDER_OFF) && ((opts->flags & VDBRT_LS_ORDER_ON) || orderAuto);
     CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
+    if (ctx->ls_affine && !order) {
+        sc.affine = ctx->ls_affine; sc.nq = uint32_t(ctx->sm_count > 0 ? std::min(ctx->sm_count, 256) : 1);
+        sc.smq = reinterpret_cast<unsigned int*>(ctx->scratch + 1024);               // 256 x 4 bytes of the 4 KB scratch block
+        CUDA_TRY(cudaMemsetAsync(sc.smq, 0, sizeof(unsigned int) * sc.nq, ctx->stream));
+    }
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    // LONG = true compiles the suspension of over-budget rays into the kernel
-    const void* kern = dCounters ? (const void*)k_render_levelset<false, true, false>
-                     : wantAux ? (rounds ? (const void*)k_render_levelset<true, false, true> : (const void*)k_render_levelset<true, false, false>)
-                               : (rounds ? (const void*)k_render_levelset<false, false, true> : (const void*)k_render_levelset<false, false, false>);
-    const int blocks = persistentGrid(ctx, kern, tm.items);
-    if (dCounters) k_render_levelset<false, true, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters, lb);
-    else if (wantAux && rounds) k_render_levelset<true, false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
-    else if (wantAux) k_render_levelset<true, false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
-    else if (rounds) k_render_levelset<false, false, true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
-    else k_render_levelset<false, false, false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, nullptr, lb);
+    uint32_t launches = 0;
+    if (order) {
+        auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+        const size_t n = nStrips, oCost = 256, oDone = oCost + up(4 * n), oCls = oDone + up(4 * n), oA = oCls + up(n), oB = oA + up(4 * n), totalB = oB + up(4 * n);
+        if (int rc = ensureBuffer(&ctx->ord, &ctx->ord_cap, totalB)) return rc;
+        uint8_t* b = static_cast<uint8_t*>(ctx->ord);
+        OrderBufs ob;
+        ob.ctl = reinterpret_cast<uint32_t*>(b); ob.cost = reinterpret_cast<uint32_t*>(b + oCost); ob.done = reinterpret_cast<uint32_t*>(b + oDone);
+        ob.cls = b + oCls; ob.listA = reinterpret_cast<uint32_t*>(b + oA); ob.listB = reinterpret_cast<uint32_t*>(b + oB);
+        CUDA_TRY(cudaMemsetAsync(b, 0, oA, ctx->stream));
+        const unsigned cap = unsigned(ctx->sm_count) * 16u, need = (tm.items + kBlockThreads - 1) / kBlockThreads;
+        k_probe_levelset<<<need < cap ? need : cap, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, ob, sc.strip_tiles, ctx->ls_probe_cap,
+                                                                                     ctx->ls_probe_cap, ctx->ls_probe_b);
+        CUDA_TRY(cudaGetLastError());
+        sc.ctl = ob.ctl; sc.listA = ob.listA; sc.listB = ob.listB; sc.cls = ob.cls;
+        ++launches;
+        if (ctx->evp) CUDA_TRY(cudaEventRecord(ctx->evp, ctx->stream));
+    }
+    // LONG = true compiles the suspension of over-budget rays into the kernel; MULTI = more than one sample per pixel
+    const bool multi = opts->spp > 1;
+    void (*kern)(DevGrid, DevCamera, DevShader, LsParams, TileMap, float4*, AuxOut, unsigned int*, unsigned long long*, LongBufs, Sched) =
+        dCounters ? k_render_levelset<false, true, false, true>
+        : wantAux ? (rounds ? k_render_levelset<true, false, true, false> : multi ? k_render_levelset<true, false, false, true> : k_render_levelset<true, false, false, false>)
+                  : (rounds ? k_render_levelset<false, false, true, false> : multi ? k_render_levelset<false, false, false, true> : k_render_levelset<false, false, false, false>);
+    const int blocks = persistentGrid(ctx, (const void*)kern, nStrips);
+    static const bool debugExit = std::getenv("VDBRT_DEBUG_EXIT") != nullptr;
+    const size_t nWarps = size_t(blocks) * (kBlockThreads / 32);
+    if (debugExit) {
+        if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, 8 * (nWarps + 1))) return rc;
+        sc.warp_exit = static_cast<unsigned long long*>(ctx->io);
+    }
+    kern<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters, lb, sc);
+    if (debugExit) {
+        // when did the warps leave?  (the tail of the frame: time between the mean and the last exit)
+        std::vector<unsigned long long> t(nWarps + 1);
+        CUDA_TRY(cudaMemcpyAsync(t.data(), ctx->io, 8 * (nWarps + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        std::vector<double> us(nWarps);
+        for (size_t i = 0; i < nWarps; ++i) us[i] = double(t[i + 1] - t[0]) * 1e-3;
+        std::sort(us.begin(), us.end());
+        double mean = 0; for (double v : us) mean += v; mean /= double(nWarps);
+        std::fprintf(stderr, "[vdbrt] warp exits (us after launch): first %.0f  p10 %.0f  median %.0f  mean %.0f  p90 %.0f  p99 %.0f  last %.0f  (%zu warps, %u tiles)\n",
+                     us.front(), us[nWarps / 10], us[nWarps / 2], mean, us[nWarps * 9 / 10], us[nWarps * 99 / 100], us.back(), nWarps, tm.items);
+    }
     CUDA_TRY(cudaGetLastError());
-    ctx->last_launches = 1;
+    ++launches;
+    ctx->last_launches = launches;
     if (rounds) {
         // K leaf visits per ray and round: small first (most suspended rays hit soon), then growing
         const uint32_t* kLeaves = ctx->ls_leaves;
@@ -587,7 +661,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
         if (wantAux) k_long_finish<true><<<wide, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, nr);
         else k_long_finish<false><<<wide, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, sh, p, dFilm, aux, lb, nr);
         CUDA_TRY(cudaGetLastError());
-        ctx->last_launches = 2 + 2 * uint32_t(nr);
+        ctx->last_launches = launches + 1 + 2 * uint32_t(nr);
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     if (rounds && std::getenv("VDBRT_DEBUG_LONG")) {
@@ -862,11 +936,36 @@ int vdbrt_volume_spans(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* 
     return VDBRT_OK;
 }
 
+int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
+{
+    if (!ctx || !key) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    const std::string k(key);
+    struct { const char* name; uint32_t* field; } table[] = {
+        {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order},
+        {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
+        {"ls_rounds", &ctx->ls_rounds},
+    };
+    for (auto& t : table) if (k == t.name) {
+        if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;
+        *t.field = value;
+        return VDBRT_OK;
+    }
+    if (k.size() == 10 && k.compare(0, 9, "ls_leaves") == 0 && k[9] >= '0' && k[9] < '0' + kMaxRounds) {      // leaf visits per ray in round r
+        ctx->ls_leaves[k[9] - '0'] = value ? value : 1u;
+        return VDBRT_OK;
+    }
+    return setError(VDBRT_ERR_INVALID_ARG, "unknown tuning key: " + k);
+}
+
 int vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches)
 {
     if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");
     DeviceGuard guard(ctx->device);
     if (ms) { CUDA_TRY(cudaEventSynchronize(ctx->ev1)); CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1)); }
+    if (ms && ctx->evp && std::getenv("VDBRT_TIME_PROBE")) {      // diagnostics: the probe launch alone (only valid right after an ordered level-set render)
+        float pm = 0.f;
+        if (cudaEventElapsedTime(&pm, ctx->ev0, ctx->evp) == cudaSuccess) std::fprintf(stderr, "[vdbrt] probe %.3f ms of %.3f ms\n", pm, *ms); else cudaGetLastError();
+    }
     if (launches) *launches = ctx->last_launches;
     return VDBRT_OK;
 }

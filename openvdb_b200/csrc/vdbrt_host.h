@@ -8,13 +8,17 @@
 struct vdbrt_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the kernel(s) of the last call on `stream`
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;   // bracket the kernel(s) of the last call on `stream`
     uint32_t last_launches = 0;
     uint8_t* scratch = nullptr;                 // 4 KB: [0,64) bbox reduction, [64,128) work queue, [128,..) counters
     void* film = nullptr;  size_t film_cap = 0; // device staging for host films
     void* aux = nullptr;   size_t aux_cap = 0;  // device staging for per-pixel records
     void* io = nullptr;    size_t io_cap = 0;   // device staging for ray batches / scratch films
     void* lng = nullptr;   size_t lng_cap = 0;  // long-ray records, segment lists and their control block (vdbrt_kernels.cuh)
+    void* ord = nullptr;   size_t ord_cap = 0;  // tile-ordering buffers of the level-set render (OrderBufs, vdbrt_kernels.cuh)
+    uint32_t ls_strip = 1, ls_strip_ratio = 4, ls_refill = 32, ls_eager = 0, ls_affine = 0, ls_order = 0, ls_probe_cap = 128, ls_probe_b = 64;   // Sched (vdbrt_kernels.cuh)
+    uint32_t ls_voxel_only = 0;                 // tail rule: only rays that are marching voxels are suspended
+    uint32_t ls_tail = 0;                       // tail rule: iterations a tile may still spend once the work queue has run dry (0: per-tile rule below)
     uint32_t ls_budget = 0;                     // warp iterations a tile may spend before its running rays are suspended (0 = never)
     uint32_t ls_factor = 0;                     // ... or this many percent of a warp's share of the launch, if that is more
     uint32_t ls_rounds = 0;                     // long-ray rounds per frame

@@ -79,15 +79,34 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 // are re-fed from the atomic queue in batches (one atomicAdd per refill, tickets numbered in tile order so a warp's
 // lanes stay spatially coherent), instead of idling until the slowest ray of a fixed tile is done.
 // ------------------------------------------------------------------------------------------------------------
-#ifndef VDBRT_REFILL
-#define VDBRT_REFILL 32
-#endif
 #ifndef VDBRT_MINBLOCKS
 #define VDBRT_MINBLOCKS 4
 #endif
-// measured on the B200 (C2 workload): re-feeding single lanes costs more (ray set-up for a few lanes at a time, lost
-// coherence) than it gains; a warp takes a fresh 8x4 tile when all its lanes are done (profiles/r01_tuning.md)
-constexpr int kRefillThreshold = VDBRT_REFILL;   // refill when at least this many lanes are idle
+// How a warp is fed (all run-time, warp-uniform; launchLevelSet fills it in):
+//   * the queue hands out STRIPS of `strip_tiles` consecutive 8x4 tiles (consecutive tiles of a macro-tile row are neighbours in x);
+//   * a warp feeds its lanes from its own strip: when at least `refill` lanes have finished their pixel they get the next
+//     pixels of the strip, so lanes whose rays ended early do not idle until the slowest ray of a fixed tile is done -- and
+//     the new rays start right next to the ones still running (same leaves, same tree path).  Round 1 measured per-lane
+//     refill from the GLOBAL queue as slower: there the next tickets belong to whatever tile the other 2 367 warps have
+//     reached, and the lanes of a warp end up in different parts of the tree.  refill = 32: a fresh tile when all lanes are done;
+//   * heavy strips first: k_probe_levelset traces one ray per tile with a budget and sorts the strips into two "heavy" lists;
+//     the queue's first tickets walk those lists, the rest walk all strips in order and skip the ones already handed out.
+//     A silhouette tile (every ray grazes the surface, ~10x the mean tile) that starts when the queue is nearly empty was the
+//     tail of the frame: 0.6 of 2.75 ms on C2 with one GPU, half of the frame time of a 1/8 share.
+//   * SM-affine queues (`affine` > 0): the strips are dealt out in chunks of `affine` consecutive strips, chunk c to SM c mod #SMs, and
+//     every SM drains its own queue (one counter per SM) before it steals from the others: the 16 warps of an SM then work
+//     on neighbouring tiles and share their L1 lines (node tables, leaf headers, halo blocks) instead of 16 unrelated tiles.
+struct Sched {
+    uint32_t strip_tiles, refill, eager;
+    uint32_t affine;             // strips per chunk (0: one global queue)
+    unsigned int* smq;           // affine: one counter per SM (zeroed before the launch), nq of them
+    uint32_t nq;
+    unsigned long long* warp_exit;   // diagnostics (VDBRT_DEBUG_EXIT): %globaltimer of every warp when it leaves the kernel, [0] = launch start
+    const uint32_t* ctl;         // [0], [1]: strips in the two heavy lists (null: no ordering)
+    const uint32_t* listA; const uint32_t* listB;
+    const uint8_t* cls;          // per strip: 0 = not in a list
+};
+struct OrderBufs { uint32_t* cost; uint32_t* done; uint32_t* ctl; uint32_t* listA; uint32_t* listB; uint8_t* cls; };
 
 __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket, uint32_t& px, uint32_t& py)
 {
@@ -136,7 +155,8 @@ __device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kNoHit = 0xffffffffu;
 constexpr int kMaxRounds = 8;
-constexpr uint32_t kDefaultBudget = 160;  // warp iterations per 8x4 tile before its running rays are suspended ...
+constexpr uint32_t kDefaultTail = 48;     // tail rule: warp iterations a tile may still spend once the queue has run dry
+constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
 constexpr int kDefaultRounds = 2;
 constexpr double kRoundsMaxTilesPerWarp = 12.0;   // rounds are on by default only below this (see launchLevelSet)
@@ -154,7 +174,8 @@ struct LongRay {
 struct SegIn { double t0, t1; int kx, ky, kz; uint32_t n2, n1, n0; };
 struct SegOut { double time, px, py, pz; float gx, gy, gz; int ix, iy, iz; };
 struct LongCtl { uint32_t nLong, tiles; unsigned long long spent; uint32_t segCount[kMaxRounds]; uint32_t live[kMaxRounds + 1]; };   // live[r]: rays that walked in round r; spent/tiles: iterations of the finished tiles
-struct LongBufs { LongRay* rays; uint32_t* liveA; uint32_t* liveB; SegIn* segIn; SegOut* segOut; LongCtl* ctl; uint32_t capLong, capSeg, budget, factor; };
+struct LongBufs { LongRay* rays; uint32_t* liveA; uint32_t* liveB; SegIn* segIn; SegOut* segOut; LongCtl* ctl; uint32_t capLong, capSeg, budget, factor;
+                  uint32_t tail, voxel_only; };   // tail > 0: suspend only once the work queue has run dry, `tail` warp iterations after a warp has seen that
 
 // Writes the record of a suspended ray.  Nothing of the caller's state is modified (the record is built from copies), so
 // the cold suspension path adds no merges to the registers the render loop carries from iteration to iteration.
@@ -202,11 +223,13 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
     w.skip = (r.flags & 1u) != 0u; w.pendLevel = (r.flags & 2u) != 0u; w.pendStep = (r.flags & 4u) != 0u;
 }
 
-template<bool AUX, bool COUNT, bool LONG>
+// MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
+template<bool AUX, bool COUNT, bool LONG, bool MULTI>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
-                  AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb)
+                  AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb,
+                  const __grid_constant__ Sched sc)
 {
     __shared__ RootSmem root;
     __shared__ WalkSmem<kBlockThreads> wsm;
@@ -214,7 +237,20 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned total = tm.items * 32u;            // tickets: 32 pixel slots per warp tile
+    if (sc.warp_exit && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        sc.warp_exit[0] = now;
+    }
+    const unsigned total = tm.items * 32u;            // pixel slots: 32 per warp tile
+    const unsigned stripSlots = sc.strip_tiles * 32u;
+    const unsigned nStrips = (tm.items + sc.strip_tiles - 1u) / sc.strip_tiles;
+    const unsigned nA = sc.ctl ? sc.ctl[0] : 0u, nB = sc.ctl ? sc.ctl[1] : 0u;      // written by k_probe_levelset before this launch
+    const unsigned nTickets = nA + nB + nStrips;
+    const unsigned thr = LONG ? 32u : sc.refill;      // the tile budget of the long-ray rounds counts whole tiles
+    unsigned mySm = 0;
+    asm("mov.u32 %0, %%smid;" : "=r"(mySm));
+    mySm %= (sc.nq ? sc.nq : 1u);
     TreeCursor acc; acc.reset();
     Stencil st; st.reset();
     Counters c = {};
@@ -229,26 +265,37 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray);
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
+    unsigned sNext = 0, sEnd = 0;                       // pixel slots of the warp's strip that are still to be handed out (warp-uniform)
 
     long long tileStart = 0; unsigned long long tileIters = 0, tileActive = 0;
     // warp iterations spent on the current tile, and what a tile may spend: at least lb.budget, and lb.factor percent of
     // a warp's fair share of the whole launch (tiles per warp x the mean of the tiles the grid has finished so far, two
     // atomics per tile).  Suspending pays when ONE tile is long against everything else a warp has to do -- a small
     // partition of a frame; a launch with plenty of tiles per warp balances itself and suspends next to nothing.
+    // Tail rule (lb.tail > 0, the default): nothing is suspended while the queue still has tiles -- a heavy tile that starts early
+    // overlaps with everything else and costs nothing.  Once the queue has run dry (every warp polls the ticket counter every 16
+    // iterations) the rest of the launch is only as fast as its slowest ray: rays still running `tail` iterations later are
+    // suspended and finished by the rounds, which spread one ray's leaf visits over the idle machine.  Measured on the B200
+    // (VDBRT_DEBUG_EXIT): the last warp of the C2 frame leaves 0.66 ms after the first (24 % of the frame), of a 1/8 share of
+    // the C4 frame 1.2 ms after the first (24 %).
     const float tilesPerWarp = float(tm.items) / float(gridDim.x * (kBlockThreads / 32));
-    uint32_t spent = 0, limit = lb.budget;
+    uint32_t spent = 0, limit = lb.tail ? lb.tail : lb.budget;
+    bool tail = false;                  // the queue has run dry
     bool longFull = false;              // no room left for suspended rays: finish everything in line
-    // Two nested loops.  The OUTER one runs once per refill: it takes tickets from the queue and sets up the next ray of
-    // every lane that needs one (the only place the ray registers are written).  The INNER one advances the running rays
-    // and finishes the ones that end, until a lane wants its next ray or no lane is running: nothing of the outer loop's
-    // bookkeeping is executed per traversal step.
+    // Two nested loops.  The OUTER one runs once per refill: it feeds idle lanes the next pixels of the warp's strip and sets
+    // up the next ray of every lane that needs one (the only place the ray registers are written).  The INNER one advances
+    // the running rays and finishes the ones that end, until enough lanes are idle (or one wants its next sample) or no lane
+    // is running: nothing of the outer loop's bookkeeping is executed per traversal step.
     for (;;) {
         __syncwarp();
         // (0) the tile has used up its budget (the inner loop leaves when that happens): suspend the rays that are still running,
         // they continue in the long-ray rounds.  Kept out of the inner loop so that the hot loop is the same with and without it.
-        if (LONG && spent > limit && !longFull) {
-            const bool sus = rayOn && walk.pendInterp != 3;         // a ray that already found its crossing just finishes
+        if (LONG && spent > limit && !longFull && (!lb.tail || tail)) {
+            // a ray that already found its crossing just finishes; tail rule with lb.voxel_only: only rays that are marching voxels go
+            // to the rounds (the rounds parallelise leaf marches; a ray that is crossing empty nodes is walked by the scout no faster)
+            const bool sus = rayOn && walk.pendInterp != 3 && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
             const unsigned m = __ballot_sync(0xffffffffu, sus);
+            if (lb.tail) spent = 0;                                 // the lanes that stay are looked at again `tail` iterations later
             if (m) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
@@ -261,8 +308,9 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 }
             }
         }
-        // (1) refill idle lanes from the queue
+        // (1) feed idle lanes
         const unsigned idle = __ballot_sync(0xffffffffu, !hasPix);
+        const unsigned nIdle = __popc(idle);
         if (COUNT && idle == 0xffffffffu && lane == 0) {
             const long long now = clock64();
             if (tileStart) {
@@ -271,8 +319,8 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             }
             tileStart = now; tileIters = 0; tileActive = 0;
         }
-        if (idle == 0xffffffffu && drained) break;
-        if (LONG && idle == 0xffffffffu) {
+        if (idle == 0xffffffffu && drained && sNext >= sEnd) break;
+        if (LONG && idle == 0xffffffffu && !lb.tail) {
             unsigned m = 0;
             if (lane == 0) {
                 if (spent > 1u) { atomicAdd(&lb.ctl->spent, (unsigned long long)(spent < limit ? spent : limit)); atomicAdd(&lb.ctl->tiles, 1u); }
@@ -284,27 +332,56 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             limit = m > lb.budget ? m : lb.budget;
             spent = 0;
         }
-        if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillThreshold)) {
-            const unsigned want = __popc(idle);
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(queue, want);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + want >= total) drained = true;
-            if (!hasPix) {
-                const unsigned ticket = base + __popc(idle & ((1u << lane) - 1u));
-                if (ticket < total && ticketToPixel(tm, ticket, px, py)) {
-                    hasPix = true; rayOn = false; k = 0;
-                    pix = size_t(py) * tm.width + px;
-                    n = 2ull * p.sub * pix;
+        // the warp's strip is used up: the next one comes from the queue -- when every lane is idle, or (eager) as soon as a refill is due
+        if (sNext >= sEnd && !drained && (idle == 0xffffffffu || (sc.eager && nIdle >= thr))) {
+            unsigned s = 0xffffffffu;
+            if (lane == 0 && sc.affine) {
+                // own queue first, then the other SMs' (a queue that is used up is skipped after one plain load)
+                const unsigned chunk = sc.affine, perRound = chunk * sc.nq;
+                for (unsigned v = 0; v < sc.nq && s == 0xffffffffu; ++v) {
+                    const unsigned q = (mySm + v) % sc.nq;
+                    for (;;) {
+                        // position p of queue q is strip (p / chunk) * perRound + q * chunk + p % chunk; the queue is used up when its chunk starts past the end
+                        const unsigned seen = *reinterpret_cast<volatile unsigned int*>(sc.smq + q);
+                        if ((seen / chunk) * perRound + q * chunk >= nStrips) break;
+                        const unsigned pos = atomicAdd(sc.smq + q, 1u);
+                        const unsigned start = (pos / chunk) * perRound + q * chunk;
+                        if (start >= nStrips) break;
+                        if (start + pos % chunk < nStrips) { s = start + pos % chunk; break; }
+                    }
+                }
+            } else if (lane == 0) {
+                for (;;) {
+                    const unsigned t = atomicAdd(queue, 1u);
+                    if (t >= nTickets) break;
+                    if (t < nA) { s = sc.listA[t]; break; }                   // heavy strips first (k_probe_levelset)
+                    if (t < nA + nB) { s = sc.listB[t - nA]; break; }
+                    const unsigned u = t - nA - nB;
+                    if (!sc.cls || !sc.cls[u]) { s = u; break; }              // everything else in tile order
                 }
             }
+            s = __shfl_sync(0xffffffffu, s, 0);
+            if (s == 0xffffffffu) { drained = true; tail = true; }
+            else { sNext = s * stripSlots; sEnd = sNext + stripSlots < total ? sNext + stripSlots : total; }
+        }
+        if (sNext < sEnd && (idle == 0xffffffffu || nIdle >= thr)) {
+            if (!hasPix) {
+                const unsigned ticket = sNext + __popc(idle & ((1u << lane) - 1u));
+                if (ticket < sEnd && ticketToPixel(tm, ticket, px, py)) {
+                    hasPix = true; rayOn = false; k = 0;
+                    pix = size_t(py) * tm.width + px;
+                    if (MULTI) n = 2ull * p.sub * pix;
+                }
+            }
+            sNext += nIdle;
+            if (!__any_sync(0xffffffffu, hasPix)) continue;                    // slots outside the film (edge tiles)
         }
         // (2) start the next ray of the lane's pixel
         int status = kWalkContinue;
         if (hasPix && !rayOn) {
-            const bool first = k == 0;
+            const bool first = !MULTI || k == 0;
             cameraRay(cam, px, py, first ? 0.5 : p.jitter[n & 15], first ? 0.5 : p.jitter[(n + 1) & 15], ray);
-            if (!first) n += 2;
+            if (MULTI && !first) n += 2;
             wdx = ray.dx; wdy = ray.dy; wdz = ray.dz;               // world direction for the shader
             if (COUNT) ++c.rays;
             // intersectsWS: setWorldRay = worldToIndex + clip (tools/RayIntersector.h:558-562)
@@ -312,11 +389,18 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (clipRay(ray, g, 0)) { walk.begin(ray); rayOn = true; }
             else status = kWalkMiss;
         }
+        const bool canRefill = thr < 32u && (sNext < sEnd || (sc.eager && !drained));
 #pragma unroll 1
         for (;;) {
             __syncwarp();
             if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
-            if (LONG) ++spent;
+            if (LONG) {
+                ++spent;
+                if (lb.tail && !tail && (spent & 15u) == 0u) {
+                    tail = *reinterpret_cast<volatile unsigned int*>(queue) >= nTickets;
+                    if (tail) spent = 0;
+                }
+            }
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
@@ -330,25 +414,76 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 float4 s;
                 if (hit) {
                     if (COUNT) ++c.hits;
-                    s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, k == 0);
+                    s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, !MULTI || k == 0);
                 } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
-                if (AUX && k == 0 && aux.hit) aux.hit[pix] = hit ? 1 : 0;
-                if (k == 0) col = s;
-                else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+                if (AUX && (!MULTI || k == 0) && aux.hit) aux.hit[pix] = hit ? 1 : 0;
                 rayOn = false;
-                if (++k > p.sub) {
-                    film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+                if (MULTI) {
+                    if (k == 0) col = s;
+                    else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+                    if (++k > p.sub) {
+                        film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+                        hasPix = false;
+                    }
+                } else {
+                    film[pix] = make_float4(s.x * p.frac, s.y * p.frac, s.z * p.frac, 1.0f);
                     hasPix = false;
                 }
                 status = kWalkContinue;
             }
-            // back to the outer loop when a lane wants its next ray (or fresh pixels), or when nothing is running any more
+            // back to the outer loop when a lane wants its next ray, when enough lanes are idle and the strip has pixels for them,
+            // or when nothing is running any more
             const unsigned running = __ballot_sync(0xffffffffu, rayOn);
-            if (running == 0u || (kRefillThreshold < 32 && __popc(running) <= 32 - kRefillThreshold) || __any_sync(0xffffffffu, hasPix && !rayOn)) break;
-            if (LONG && spent > limit && !longFull) break;
+            if (running == 0u || (canRefill && 32u - (unsigned)__popc(running) >= thr) || (MULTI && __any_sync(0xffffffffu, hasPix && !rayOn))) break;
+            if (LONG && spent > limit && !longFull && (!lb.tail || tail)) break;
         }
     }
     if (COUNT) flushCounters(c, counters);
+    if (sc.warp_exit && lane == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        sc.warp_exit[1 + blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)] = now;
+    }
+}
+
+// One ray per 8x4 tile (the pixel in its middle), traced for at most `cap` steps: the number of steps is the tile's cost
+// estimate.  The last tile of a strip to finish sorts the strip into list A (cost >= thrA) or B (>= thrB) -- see Sched.
+// Plain per-thread loop (a launch of tiles/32 warps, ~3 % of the frame's rays); nothing it computes reaches the film.
+__global__ void __launch_bounds__(kBlockThreads)
+k_probe_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ LsParams p,
+                 const __grid_constant__ TileMap tm, const __grid_constant__ OrderBufs ob, uint32_t stripTiles, uint32_t cap, uint32_t thrA, uint32_t thrB)
+{
+    __shared__ RootSmem root;
+    __shared__ WalkSmem<kBlockThreads> wsm;
+    stageRoot(g, root);
+    __syncthreads();
+    Counters c = {};
+    for (uint32_t item = blockIdx.x * kBlockThreads + threadIdx.x; item < tm.items; item += gridDim.x * kBlockThreads) {
+        uint32_t px, py, it = 0;
+        if (ticketToPixel(tm, item * 32u + 20u, px, py)) {
+            Ray ray;
+            cameraRay(cam, px, py, 0.5, 0.5, ray);
+            worldToIndex(g, ray);
+            if (clipRay(ray, g, 0)) {
+                TreeCursor acc; acc.reset();
+                Stencil st; st.reset();
+                LsWalk w; w.begin(ray);
+                LsHit h = {};
+#pragma unroll 1
+                for (; it < cap; ++it)
+                    if (lsAdvance<false, false, kBlockThreads>(true, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, w, h, c) != kWalkContinue) break;
+            }
+        }
+        const uint32_t strip = item / stripTiles;
+        const uint32_t first = strip * stripTiles, nTiles = tm.items - first < stripTiles ? tm.items - first : stripTiles;
+        atomicMax(ob.cost + strip, it);
+        __threadfence();
+        if (atomicAdd(ob.done + strip, 1u) == nTiles - 1u) {
+            const uint32_t cost = atomicMax(ob.cost + strip, 0u);
+            if (cost >= thrA) { ob.cls[strip] = 1; ob.listA[atomicAdd(ob.ctl + 0, 1u)] = strip; }
+            else if (cost >= thrB) { ob.cls[strip] = 2; ob.listB[atomicAdd(ob.ctl + 1, 1u)] = strip; }
+        }
+    }
 }
 
 // Round r works on the rays that walked in round r-1 (list r-1; all suspended rays for r = 0).  Its scout first RESOLVES

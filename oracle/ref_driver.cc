@@ -207,6 +207,47 @@ void* vdbref_grid_spheres_union(const double* spheres, uint32_t n, double voxel,
     } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
 
+// The same union folded by `threads` workers: worker w unions the spheres w, w+threads, ... into its own grid, then the
+// partial grids are unioned in worker order.  csgUnion keeps min(a,b) with the minimum's active state (ties keep a's; equal
+// values of these spheres have equal states), so the fold order does not change the result -- asserted against the
+// sequential fold in tests/test_oracle_vs_reference.py.  Only used to build BASELINE config 4's grid for the timed
+// reference arm in seconds instead of minutes; the render that is timed is the stock one.
+void* vdbref_grid_spheres_union_mt(const double* spheres, uint32_t n, double voxel, double halfWidth, int threads)
+{
+    try {
+        ensureInit();
+        if (threads < 1) threads = 1;
+        if (uint32_t(threads) > n) threads = int(n ? n : 1);
+        std::vector<FloatGrid::Ptr> part(threads);
+        std::vector<std::string> errs(threads);
+        const int saved = tbb_shim::num_threads();
+        tbb_shim::set_num_threads(1);                       // the library's own parallel_for stays serial inside the workers
+        auto work = [&](int w) {
+            try {
+                for (uint32_t s = uint32_t(w); s < n; s += uint32_t(threads)) {
+                    const double* p = spheres + 4 * s;
+                    auto sph = tools::createLevelSetSphere<FloatGrid>(float(p[3]), Vec3f(float(p[0]), float(p[1]), float(p[2])),
+                                                                      float(voxel), float(halfWidth));
+                    if (!part[w]) part[w] = sph; else tools::csgUnion(*part[w], *sph);
+                }
+            } catch (std::exception& e) { errs[w] = e.what(); }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < threads; ++w) pool.emplace_back(work, w);
+        work(0);
+        for (auto& t : pool) t.join();
+        tbb_shim::set_num_threads(saved);
+        for (auto& e : errs) if (!e.empty()) { g_err = e; return nullptr; }
+        auto* g = new RefGrid;
+        for (int w = 0; w < threads; ++w) {
+            if (!part[w]) continue;
+            if (!g->grid) g->grid = part[w]; else tools::csgUnion(*g->grid, *part[w]);
+            part[w].reset();
+        }
+        return g;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
 // hand-made grid for the known-answer tests: setValue(ijk, v) for n voxels, then Grid::fill(bbox, value, active) for
 // nb boxes {min xyz, max xyz} (a node-aligned active box becomes an active tile)
 void* vdbref_grid_custom(float background, uint32_t gridClass, double voxelSize, const double* translation,

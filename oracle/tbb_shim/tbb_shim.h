@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstddef>
 #include <deque>
 #include <functional>
@@ -257,13 +258,76 @@ private:
     std::function<T()> mMake; std::list<T> mItems; std::map<std::thread::id, T*> mIdx; std::mutex mMx;
 };
 
+// concurrent_vector: segmented storage (segment k holds 16 << k elements, elements never move), so that push_back /
+// grow_by from several threads and element access by index or iterator can run at the same time, as with TBB's own.
+// Growth is serialised by a mutex; the segment table is a fixed array of atomic pointers, reads take no lock.
 template<typename T, typename A = std::allocator<T>>
-class concurrent_vector : public std::deque<T> {   // deque: push_back keeps references valid
+class concurrent_vector {
+    static constexpr int kSegs = 48, kLog0 = 4;
+    static int segOf(std::size_t i) { int k = 0; std::size_t n = (i >> kLog0) + 1; while (n >>= 1) ++k; return k; }
+    static std::size_t segBase(int k) { return ((std::size_t(1) << k) - 1) << kLog0; }
+    static std::size_t segSize(int k) { return std::size_t(1) << (k + kLog0); }
+    T* slot(std::size_t i) const { const int k = segOf(i); return mSeg[k].load(std::memory_order_acquire) + (i - segBase(k)); }
+    template<typename VecT, typename RefT>
+    class iter {
+    public:
+        using iterator_category = std::random_access_iterator_tag; using value_type = T; using difference_type = std::ptrdiff_t;
+        using pointer = typename std::remove_reference<RefT>::type*; using reference = RefT;
+        iter() = default; iter(VecT* v, std::size_t i) : mV(v), mI(i) {}
+        template<typename V2, typename R2> iter(const iter<V2, R2>& o) : mV(o.mV), mI(o.mI) {}
+        reference operator*() const { return *mV->slot(mI); } pointer operator->() const { return mV->slot(mI); }
+        reference operator[](difference_type d) const { return *mV->slot(mI + d); }
+        iter& operator++() { ++mI; return *this; } iter operator++(int) { iter t(*this); ++mI; return t; }
+        iter& operator--() { --mI; return *this; } iter operator--(int) { iter t(*this); --mI; return t; }
+        iter& operator+=(difference_type d) { mI += d; return *this; } iter& operator-=(difference_type d) { mI -= d; return *this; }
+        friend iter operator+(iter a, difference_type d) { a.mI += d; return a; } friend iter operator+(difference_type d, iter a) { a.mI += d; return a; }
+        friend iter operator-(iter a, difference_type d) { a.mI -= d; return a; }
+        friend difference_type operator-(const iter& a, const iter& b) { return difference_type(a.mI) - difference_type(b.mI); }
+        friend bool operator==(const iter& a, const iter& b) { return a.mI == b.mI; } friend bool operator!=(const iter& a, const iter& b) { return a.mI != b.mI; }
+        friend bool operator<(const iter& a, const iter& b) { return a.mI < b.mI; } friend bool operator>(const iter& a, const iter& b) { return a.mI > b.mI; }
+        friend bool operator<=(const iter& a, const iter& b) { return a.mI <= b.mI; } friend bool operator>=(const iter& a, const iter& b) { return a.mI >= b.mI; }
+        VecT* mV = nullptr; std::size_t mI = 0;
+    };
 public:
-    using std::deque<T>::deque;
-    typename std::deque<T>::iterator push_back(const T& v) { std::deque<T>::push_back(v); return std::prev(this->end()); }
-    typename std::deque<T>::iterator push_back(T&& v) { std::deque<T>::push_back(std::move(v)); return std::prev(this->end()); }
-    typename std::deque<T>::iterator grow_by(std::size_t n) { auto s = this->size(); this->resize(s + n); return this->begin() + s; }
+    using value_type = T; using size_type = std::size_t; using reference = T&; using const_reference = const T&;
+    using iterator = iter<concurrent_vector, T&>; using const_iterator = iter<const concurrent_vector, const T&>;
+    concurrent_vector() { for (auto& s : mSeg) s.store(nullptr, std::memory_order_relaxed); }
+    explicit concurrent_vector(size_type n, const T& v = T()) : concurrent_vector() { grow_to(n, &v); }
+    concurrent_vector(const concurrent_vector& o) : concurrent_vector() { for (size_type i = 0; i < o.size(); ++i) push_back(o[i]); }
+    concurrent_vector& operator=(const concurrent_vector& o) { if (this != &o) { clear(); for (size_type i = 0; i < o.size(); ++i) push_back(o[i]); } return *this; }
+    ~concurrent_vector() { clear(); for (auto& s : mSeg) { ::operator delete(static_cast<void*>(s.load())); } }
+    iterator push_back(const T& v) { std::lock_guard<std::mutex> g(mMx); const size_type i = mSize.load(std::memory_order_relaxed); reserve_locked(i + 1); new (slot(i)) T(v); mSize.store(i + 1, std::memory_order_release); return iterator(this, i); }
+    iterator push_back(T&& v) { std::lock_guard<std::mutex> g(mMx); const size_type i = mSize.load(std::memory_order_relaxed); reserve_locked(i + 1); new (slot(i)) T(std::move(v)); mSize.store(i + 1, std::memory_order_release); return iterator(this, i); }
+    template<typename... Args> iterator emplace_back(Args&&... a) { std::lock_guard<std::mutex> g(mMx); const size_type i = mSize.load(std::memory_order_relaxed); reserve_locked(i + 1); new (slot(i)) T(std::forward<Args>(a)...); mSize.store(i + 1, std::memory_order_release); return iterator(this, i); }
+    iterator grow_by(size_type n) { std::lock_guard<std::mutex> g(mMx); const size_type s = mSize.load(std::memory_order_relaxed); reserve_locked(s + n); for (size_type i = s; i < s + n; ++i) new (slot(i)) T(); mSize.store(s + n, std::memory_order_release); return iterator(this, s); }
+    iterator grow_by(size_type n, const T& v) { std::lock_guard<std::mutex> g(mMx); const size_type s = mSize.load(std::memory_order_relaxed); reserve_locked(s + n); for (size_type i = s; i < s + n; ++i) new (slot(i)) T(v); mSize.store(s + n, std::memory_order_release); return iterator(this, s); }
+    void resize(size_type n) { grow_to(n, nullptr); }
+    void reserve(size_type n) { std::lock_guard<std::mutex> g(mMx); reserve_locked(n); }
+    void clear() { std::lock_guard<std::mutex> g(mMx); const size_type n = mSize.load(); for (size_type i = 0; i < n; ++i) slot(i)->~T(); mSize.store(0); }
+    size_type size() const { return mSize.load(std::memory_order_acquire); }
+    bool empty() const { return size() == 0; }
+    reference operator[](size_type i) { return *slot(i); } const_reference operator[](size_type i) const { return *slot(i); }
+    reference at(size_type i) { return *slot(i); } const_reference at(size_type i) const { return *slot(i); }
+    reference front() { return *slot(0); } reference back() { return *slot(size() - 1); }
+    const_reference front() const { return *slot(0); } const_reference back() const { return *slot(size() - 1); }
+    iterator begin() { return iterator(this, 0); } iterator end() { return iterator(this, size()); }
+    const_iterator begin() const { return const_iterator(this, 0); } const_iterator end() const { return const_iterator(this, size()); }
+    const_iterator cbegin() const { return begin(); } const_iterator cend() const { return end(); }
+private:
+    void reserve_locked(size_type n) {
+        if (n == 0) return;
+        for (int k = 0, last = segOf(n - 1); k <= last; ++k)
+            if (!mSeg[k].load(std::memory_order_relaxed)) mSeg[k].store(static_cast<T*>(::operator new(segSize(k) * sizeof(T))), std::memory_order_release);
+    }
+    void grow_to(size_type n, const T* v) {
+        std::lock_guard<std::mutex> g(mMx);
+        const size_type s = mSize.load(std::memory_order_relaxed);
+        if (n <= s) { for (size_type i = n; i < s; ++i) slot(i)->~T(); mSize.store(n, std::memory_order_release); return; }
+        reserve_locked(n);
+        for (size_type i = s; i < n; ++i) { if (v) new (slot(i)) T(*v); else new (slot(i)) T(); }
+        mSize.store(n, std::memory_order_release);
+    }
+    std::atomic<T*> mSeg[kSegs]; std::atomic<size_type> mSize{0}; mutable std::mutex mMx;
 };
 
 template<typename K> struct tbb_hash_compare {
@@ -271,38 +335,103 @@ template<typename K> struct tbb_hash_compare {
     static bool equal(const K& a, const K& b) { return a == b; }
 };
 
+// concurrent_hash_map with TBB's locking contract: find / insert / erase may be called from any number of threads; an
+// `accessor` holds a WRITE lock on its element and a `const_accessor` a READ lock until it is released or destroyed;
+// erase(key) waits for the element's lock.  The table itself is guarded by one mutex (the registry of a tree's value
+// accessors -- tree/Tree.h:1081-1082,1423-1450 -- sees one insert and one erase per task, so a single lock is enough).
+// Iteration is not safe against concurrent modification, exactly as in TBB.
 template<typename K, typename V, typename HC = tbb_hash_compare<K>>
 class concurrent_hash_map {
     struct H { std::size_t operator()(const K& k) const { return HC().hash(k); } };
     struct E { bool operator()(const K& a, const K& b) const { return HC().equal(a, b); } };
-    using MapT = std::unordered_map<K, V, H, E>;
 public:
-    using value_type = typename MapT::value_type; using iterator = typename MapT::iterator;
-    using const_iterator = typename MapT::const_iterator; using key_type = K; using mapped_type = V;
+    using value_type = std::pair<const K, V>; using key_type = K; using mapped_type = V;
+private:
+    struct Node {
+        value_type kv; std::mutex mx; std::condition_variable cv; int readers = 0; bool writer = false;
+        explicit Node(const K& k) : kv(k, V()) {} explicit Node(const value_type& v) : kv(v) {}
+        void lock(bool write) { std::unique_lock<std::mutex> l(mx); if (write) { cv.wait(l, [&] { return !writer && readers == 0; }); writer = true; } else { cv.wait(l, [&] { return !writer; }); ++readers; } }
+        void unlock(bool write) { { std::lock_guard<std::mutex> l(mx); if (write) writer = false; else --readers; } cv.notify_all(); }
+    };
+    using NodeP = std::shared_ptr<Node>;
+    using MapT = std::unordered_map<K, NodeP, H, E>;
+    template<typename MapIt, typename RefT>
+    class iter {
+    public:
+        using iterator_category = std::forward_iterator_tag; using value_type = typename concurrent_hash_map::value_type;
+        using difference_type = std::ptrdiff_t; using pointer = typename std::remove_reference<RefT>::type*; using reference = RefT;
+        iter() = default; explicit iter(MapIt it) : mIt(it) {}
+        reference operator*() const { return mIt->second->kv; } pointer operator->() const { return &mIt->second->kv; }
+        iter& operator++() { ++mIt; return *this; } iter operator++(int) { iter t(*this); ++mIt; return t; }
+        friend bool operator==(const iter& a, const iter& b) { return a.mIt == b.mIt; } friend bool operator!=(const iter& a, const iter& b) { return a.mIt != b.mIt; }
+        MapIt mIt;
+    };
+public:
+    using iterator = iter<typename MapT::iterator, value_type&>; using const_iterator = iter<typename MapT::const_iterator, const value_type&>;
     class const_accessor {
     public:
-        const value_type& operator*() const { return *mP; } const value_type* operator->() const { return mP; }
-        bool empty() const { return !mP; } void release() { mP = nullptr; }
-    protected: friend class concurrent_hash_map; value_type* mP = nullptr;
+        const_accessor() = default; const_accessor(const const_accessor&) = delete; const_accessor& operator=(const const_accessor&) = delete;
+        ~const_accessor() { release(); }
+        const value_type& operator*() const { return mN->kv; } const value_type* operator->() const { return &mN->kv; }
+        bool empty() const { return !mN; }
+        void release() { if (mN) { mN->unlock(mWrite); mN.reset(); } }
+    protected:
+        friend class concurrent_hash_map;
+        void hold(const NodeP& n, bool write) { release(); n->lock(write); mN = n; mWrite = write; }
+        NodeP mN; bool mWrite = false;
     };
     class accessor : public const_accessor {
     public:
-        value_type& operator*() const { return *this->mP; } value_type* operator->() const { return this->mP; }
+        value_type& operator*() const { return this->mN->kv; } value_type* operator->() const { return &this->mN->kv; }
     };
-    bool find(const_accessor& a, const K& k) const { auto it = const_cast<MapT&>(mM).find(k); if (it == mM.end()) { a.mP = nullptr; return false; } a.mP = &*it; return true; }
-    bool find(accessor& a, const K& k) { auto it = mM.find(k); if (it == mM.end()) { a.mP = nullptr; return false; } a.mP = &*it; return true; }
-    bool insert(const_accessor& a, const K& k) { auto r = mM.emplace(k, V()); a.mP = &*r.first; return r.second; }
-    bool insert(accessor& a, const K& k) { auto r = mM.emplace(k, V()); a.mP = &*r.first; return r.second; }
-    bool insert(const value_type& v) { return mM.insert(v).second; }
-    bool insert(accessor& a, const value_type& v) { auto r = mM.insert(v); a.mP = &*r.first; return r.second; }
-    bool erase(const K& k) { return mM.erase(k) > 0; }
-    bool erase(const_accessor& a) { if (!a.mP) return false; K k = a.mP->first; a.mP = nullptr; return mM.erase(k) > 0; }
-    bool erase(accessor& a) { if (!a.mP) return false; K k = a.mP->first; a.mP = nullptr; return mM.erase(k) > 0; }
-    std::size_t size() const { return mM.size(); } bool empty() const { return mM.empty(); } void clear() { mM.clear(); }
-    std::size_t count(const K& k) const { return mM.count(k); }
-    iterator begin() { return mM.begin(); } iterator end() { return mM.end(); }
-    const_iterator begin() const { return mM.begin(); } const_iterator end() const { return mM.end(); }
-private: MapT mM;
+    concurrent_hash_map() = default;
+    bool find(const_accessor& a, const K& k) const { return lookup(a, k, false); }
+    bool find(accessor& a, const K& k) { return lookup(a, k, true); }
+    bool insert(const_accessor& a, const K& k) { return emplace(&a, false, k, nullptr); }
+    bool insert(accessor& a, const K& k) { return emplace(&a, true, k, nullptr); }
+    bool insert(const value_type& v) { return emplace(nullptr, false, v.first, &v); }
+    bool insert(const_accessor& a, const value_type& v) { return emplace(&a, false, v.first, &v); }
+    bool insert(accessor& a, const value_type& v) { return emplace(&a, true, v.first, &v); }
+    bool erase(const K& k) {
+        NodeP n;
+        { std::lock_guard<std::mutex> g(mMx); auto it = mM.find(k); if (it == mM.end()) return false; n = it->second; mM.erase(it); }
+        n->lock(true); n->unlock(true);       // wait for the holders of the element, as TBB does
+        return true;
+    }
+    bool erase(const_accessor& a) { return eraseHeld(a); }
+    bool erase(accessor& a) { return eraseHeld(a); }
+    std::size_t size() const { std::lock_guard<std::mutex> g(mMx); return mM.size(); }
+    bool empty() const { return size() == 0; }
+    void clear() { std::lock_guard<std::mutex> g(mMx); mM.clear(); }
+    std::size_t count(const K& k) const { std::lock_guard<std::mutex> g(mMx); return mM.count(k); }
+    iterator begin() { return iterator(mM.begin()); } iterator end() { return iterator(mM.end()); }
+    const_iterator begin() const { return const_iterator(mM.begin()); } const_iterator end() const { return const_iterator(mM.end()); }
+private:
+    bool lookup(const_accessor& a, const K& k, bool write) const {
+        a.release();
+        NodeP n;
+        { std::lock_guard<std::mutex> g(mMx); auto it = mM.find(k); if (it == mM.end()) return false; n = it->second; }
+        a.hold(n, write);
+        return true;
+    }
+    bool emplace(const_accessor* a, bool write, const K& k, const value_type* v) {
+        if (a) a->release();
+        NodeP n; bool fresh;
+        { std::lock_guard<std::mutex> g(mMx);
+          auto it = mM.find(k);
+          fresh = it == mM.end();
+          if (fresh) { n = v ? std::make_shared<Node>(*v) : std::make_shared<Node>(k); mM.emplace(k, n); } else n = it->second; }
+        if (a) a->hold(n, write);
+        return fresh;
+    }
+    bool eraseHeld(const_accessor& a) {
+        if (a.empty()) return false;
+        const K k = a.mN->kv.first; NodeP n = a.mN; bool gone = false;
+        { std::lock_guard<std::mutex> g(mMx); auto it = mM.find(k); if (it != mM.end() && it->second == n) { mM.erase(it); gone = true; } }
+        a.release();
+        return gone;
+    }
+    MapT mM; mutable std::mutex mMx;
 };
 
 class task_group_context {

@@ -119,6 +119,8 @@ class Ref:
         L.vdbref_grid_fog_from_levelset.argtypes = [vp]
         L.vdbref_grid_spheres_union.restype = vp
         L.vdbref_grid_spheres_union.argtypes = [vp, C.c_uint32, C.c_double, C.c_double]
+        L.vdbref_grid_spheres_union_mt.restype = vp
+        L.vdbref_grid_spheres_union_mt.argtypes = [vp, C.c_uint32, C.c_double, C.c_double, C.c_int]
         L.vdbref_grid_custom.restype = vp
         L.vdbref_grid_custom.argtypes = [C.c_float, C.c_uint32, C.c_double, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64]
         L.vdbref_grid_from_nanovdb.restype = vp
@@ -171,6 +173,11 @@ class Ref:
     def spheres_union(self, spheres, voxel=1.0, half_width=3.0):
         s = np.ascontiguousarray(spheres, np.float64).reshape(-1, 4)
         return self._chk(self.L.vdbref_grid_spheres_union(s.ctypes.data, len(s), voxel, half_width))
+
+    def spheres_union_mt(self, spheres, threads, voxel=1.0, half_width=3.0):
+        """the same union folded by `threads` workers (order-independent; builds BASELINE config 4 in seconds)"""
+        s = np.ascontiguousarray(spheres, np.float64).reshape(-1, 4)
+        return self._chk(self.L.vdbref_grid_spheres_union_mt(s.ctypes.data, len(s), voxel, half_width, int(threads)))
 
     def custom(self, background=0.0, grid_class=abi.GRID_CLASS_FOG_VOLUME, voxel=1.0, translation=(0, 0, 0), voxels=(), boxes=()):
         """voxels: [((i,j,k), value)], boxes: [((min xyz),(max xyz), value, active)]"""

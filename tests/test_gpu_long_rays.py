@@ -26,8 +26,8 @@ def render(ctx, grid, cam, sh, W, H, bg=(0, 0, 0, 1), want_aux=True, **opts):
 @pytest.fixture(scope="module")
 def tiny_budget_ctx():
     """a context whose tiles may spend only a handful of iterations: nearly every ray that enters the grid is suspended"""
-    old = {k: os.environ.get(k) for k in ("VDBRT_LS_BUDGET", "VDBRT_LS_FACTOR", "VDBRT_LS_LEAVES")}
-    os.environ.update(VDBRT_LS_BUDGET="6", VDBRT_LS_FACTOR="0", VDBRT_LS_LEAVES="2,4,12")
+    old = {k: os.environ.get(k) for k in ("VDBRT_LS_BUDGET", "VDBRT_LS_FACTOR", "VDBRT_LS_LEAVES", "VDBRT_LS_TAIL")}
+    os.environ.update(VDBRT_LS_BUDGET="6", VDBRT_LS_FACTOR="0", VDBRT_LS_LEAVES="2,4,12", VDBRT_LS_TAIL="0")    # the per-tile rule
     c = api.Context(0)
     for k, v in old.items():
         if v is None:
@@ -81,6 +81,35 @@ def test_every_ray_suspended_few_rounds(tiny_budget_ctx, oracle, torus_small, sp
         assert_records_equal(aux, oaux)
         assert np.array_equal(film, ofilm)
         g.free()
+
+
+def test_tail_rule_any_budget(ctx, oracle, torus_small):
+    """the default rule: rays are suspended only once the queue has run dry, `ls_tail` iterations later -- from 'everything that
+    is in flight at that moment' (1) to 'next to nothing' (4096), whole and partitioned frames give the oracle's frame and records"""
+    g = ctx.upload(torus_small.buf)
+    W, H = 400, 240
+    cam = api.vdb_render_camera(W, H, (0.0, 90.0, 255.0), (0, 0, 0))
+    sh = api.make_shader(abi.SHADER_DIFFUSE)
+    rng = np.random.default_rng(11)
+    old = rng.random((H, W, 4)).astype(np.float32)
+    ofilm = old.copy()
+    oaux, _ = oracle.render_levelset(torus_small.oracle_handle, cam, sh, ofilm, aux=True, threads=4)
+    try:
+        for tail in (1, 7, 48, 4096):
+            ctx.set_tuning(ls_tail=tail)
+            film = old.copy()
+            aux = refapi.AuxArrays(W, H)
+            ctx.render_levelset(g, cam, sh, film, aux=aux.pod(), opts=ctx.ls_opts())
+            assert ctx.last_kernel_ms()[1] > 1          # rounds are on by default
+            assert_records_equal(aux, oaux)
+            assert np.array_equal(film, ofilm), tail
+            film = old.copy()
+            for r in range(3):
+                ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(part=api.partition(r, 3, 32, 32)))
+            assert np.array_equal(film, ofilm), ("partitioned", tail)
+    finally:
+        ctx.set_tuning(ls_tail=48)
+    g.free()
 
 
 def test_partitioned_frame_uses_rounds_by_default(ctx, oracle, torus_small):
