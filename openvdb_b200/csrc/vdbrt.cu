@@ -5,6 +5,7 @@
 // implementation of the hot path in this library: without a CUDA device vdbrt_create() fails.
 #include "../../include/vdbrt.h"
 #include "vdbrt_kernels.cuh"
+#include "vdbrt_fog.cuh"
 #include "vdbrt_host.h"
 
 #include <algorithm>
@@ -301,6 +302,9 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ctx->ls_order = envU("VDBRT_LS_ORDER", 0);            // heavy strips first: 0 off, 1 on, 2 when a warp gets >= 2 tiles
     ctx->ls_probe_cap = envU("VDBRT_LS_PROBE_CAP", 128);  // steps a probe ray may take; unfinished = list A
     ctx->ls_probe_b = envU("VDBRT_LS_PROBE_B", 64);       // steps from which a strip goes to list B
+    ctx->fog_wave = envU("VDBRT_FOG_WAVE", 1);            // VolumeRender as a wavefront of three kernels (vdbrt_fog.cuh); 0: the one-loop kernel
+    ctx->fog_rec_per_ray = envU("VDBRT_FOG_REC_PER_RAY", 12);   // record budget per primary ray (average over a batch of tiles)
+    ctx->fog_cap_mb = envU("VDBRT_FOG_CAP_MB", 4096);     // device memory for the records of one batch
     if ((ev = std::getenv("VDBRT_LS_LEAVES"))) {
         int r = 0;
         for (const char* q = ev; *q && r < kMaxRounds; ++r) { ctx->ls_leaves[r] = uint32_t(std::strtoul(q, const_cast<char**>(&q), 10)); if (*q == ',') ++q; }
@@ -320,6 +324,7 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->lng) cudaFree(ctx->lng);
     if (ctx->ord) cudaFree(ctx->ord);
+    if (ctx->fog) cudaFree(ctx->fog);
     cudaFree(ctx->scratch);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->own_stream);
@@ -785,16 +790,64 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
     CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    const VolTiles all = {0u, tm.items, nullptr, nullptr};
     if (dCounters) {
         const int blocks = persistentGrid(ctx, (const void*)k_render_volume<true>, tm.items);
-        k_render_volume<true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, dCounters);
-    } else {
+        k_render_volume<true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, dCounters, all);
+        ctx->last_launches = 1;
+    } else if (!ctx->fog_wave || tm.items == 0) {
         const int blocks = persistentGrid(ctx, (const void*)k_render_volume<false>, tm.items);
-        k_render_volume<false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr);
+        k_render_volume<false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr, all);
+        ctx->last_launches = 1;
+    } else {
+        // Wavefront (vdbrt_fog.cuh): primary rays -> records of the dense samples -> shadow rays -> pixels, in batches of tiles whose
+        // records fit the buffer (fog_rec_per_ray records per primary ray on average; a tile that runs out is re-rendered by the
+        // one-loop kernel, so the budget is a performance knob, not a limit).
+        auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+        const uint32_t spp = p.sub + 1u;
+        const size_t raysPerTile = 32u * size_t(spp);
+        const size_t perRay = ctx->fog_rec_per_ray ? ctx->fog_rec_per_ray : 12u;
+        const size_t budget = size_t(ctx->fog_cap_mb ? ctx->fog_cap_mb : 4096u) << 20;
+        const size_t bytesPerTile = raysPerTile * (perRay * sizeof(FogRec) + sizeof(FogRayRec)) + 1;
+        const uint32_t batchTiles = uint32_t(std::max<size_t>(1, std::min<size_t>(tm.items, budget / bytesPerTile)));
+        const size_t cap = std::min<size_t>(size_t(batchTiles) * raysPerTile * perRay, 0xfffffff0u);
+        const size_t oCtl = 0, oFlag = 256, oRays = oFlag + up(batchTiles), oRecs = oRays + up(size_t(batchTiles) * raysPerTile * sizeof(FogRayRec));
+        const size_t total = oRecs + up(cap * sizeof(FogRec));
+        if (int rc = ensureBuffer(&ctx->fog, &ctx->fog_cap, total)) return rc;
+        uint8_t* b = static_cast<uint8_t*>(ctx->fog);
+        FogWave fw;
+        fw.ctl = reinterpret_cast<unsigned int*>(b + oCtl); fw.tileFlag = b + oFlag; fw.rays = reinterpret_cast<FogRayRec*>(b + oRays);
+        fw.recs = reinterpret_cast<FogRec*>(b + oRecs); fw.cap = uint32_t(cap);
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fog_shadow, kBlockThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
+        const int shadowBlocks = ctx->sm_count * perSm;
+        uint32_t launches = 0;
+        for (uint32_t t0 = 0; t0 < tm.items; t0 += batchTiles) {
+            fw.tile0 = t0; fw.tile1 = std::min(tm.items, t0 + batchTiles);
+            CUDA_TRY(cudaMemsetAsync(b, 0, oRays, ctx->stream));                       // queue words, counters, tile flags
+            const int blocks = persistentGrid(ctx, (const void*)k_fog_primary, fw.tile1 - fw.tile0);
+            k_fog_primary<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, fw);
+            k_fog_shadow<<<shadowBlocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, p, fw);
+            const unsigned long long slots = (unsigned long long)(fw.tile1 - fw.tile0) * 32ull;
+            k_fog_resolve<<<unsigned(std::min<unsigned long long>((slots + 255) / 256, (unsigned long long)ctx->sm_count * 32ull)), 256, 0, ctx->stream>>>(p, tm, fw, dFilm);
+            // tiles that ran out of record space: the one-loop kernel (returns at once when there is none)
+            CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
+            const VolTiles flagged = {fw.tile0, fw.tile1, fw.tileFlag, fw.ctl + 2};
+            k_render_volume<false><<<persistentGrid(ctx, (const void*)k_render_volume<false>, fw.tile1 - fw.tile0), kBlockThreads, 0, ctx->stream>>>(
+                grid->dgrid, dc, p, tm, dFilm, queue, nullptr, flagged);
+            launches += 4;
+        }
+        ctx->last_launches = launches;
+        if (std::getenv("VDBRT_DEBUG_FOG")) {
+            unsigned int h[4];
+            CUDA_TRY(cudaMemcpyAsync(h, fw.ctl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            std::fprintf(stderr, "[vdbrt] fog wavefront: %u tiles in batches of %u, last batch: %u records of %zu (%.2f per ray), %u tiles flagged\n", tm.items, batchTiles,
+                         h[1], cap, double(h[1]) / double((fw.tile1 - fw.tile0) * raysPerTile), h[2]);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->last_launches = 1;
     return VDBRT_OK;
 }
 
@@ -943,7 +996,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     struct { const char* name; uint32_t* field; } table[] = {
         {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
-        {"ls_rounds", &ctx->ls_rounds},
+        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };
     for (auto& t : table) if (k == t.name) {
         if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;

@@ -791,13 +791,17 @@ struct VolParams {
 // taken right away -- same samples, same order, same arithmetic.  A ray that saturates (|T|^2 < cutoff) after a few
 // samples never walks the rest of its chord (for shadow rays inside the fog that is > 90 % of the node probes).
 enum { kFogIdle = 0, kFogPrimary = 1, kFogShadow = 2 };
+struct VolTiles { uint32_t tile0, tile1; const uint8_t* only; const unsigned int* gate; };   // work items [tile0, tile1); only[t - tile0] != 0 if given; *gate != 0 if given
 constexpr int kFogBatch = 8;             // a phase runs when this many lanes want it, or when the other phases are starved
 
 template<bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, 3)
 k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
-                const __grid_constant__ TileMap tm, float4* __restrict__ film, unsigned int* queue, unsigned long long* counters)
+                const __grid_constant__ TileMap tm, float4* __restrict__ film, unsigned int* queue, unsigned long long* counters,
+                const __grid_constant__ VolTiles vt)
 {
+    // as the fall-back of the wavefront path (vdbrt_fog.cuh): only the flagged tiles of one batch, and nothing at all when none is flagged
+    if (vt.gate && *vt.gate == 0u) return;
     __shared__ RootSmem root;
     __shared__ FogSmem<kBlockThreads> sm;
     stageRoot(g, root);
@@ -844,9 +848,10 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
         if (idle == 0xffffffffu) {
             if (drained) break;
             unsigned item = 0;
-            if (lane == 0) item = atomicAdd(queue, 1u);
+            if (lane == 0) item = vt.tile0 + atomicAdd(queue, 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= tm.items) { drained = true; continue; }
+            if (item >= vt.tile1) { drained = true; continue; }
+            if (vt.only && !vt.only[item - vt.tile0]) continue;
             uint32_t px, py;
             if (ticketToPixel(tm, item * 32u + lane, px, py)) {
                 pix = size_t(py) * tm.width + px;
