@@ -9,6 +9,7 @@
 #include "vdbrt_host.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -303,6 +304,7 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ctx->ls_probe_cap = envU("VDBRT_LS_PROBE_CAP", 128);  // steps a probe ray may take; unfinished = list A
     ctx->ls_probe_b = envU("VDBRT_LS_PROBE_B", 64);       // steps from which a strip goes to list B
     ctx->fog_wave = envU("VDBRT_FOG_WAVE", 1);            // VolumeRender as a wavefront of three kernels (vdbrt_fog.cuh); 0: the one-loop kernel
+    ctx->fog_refill = envU("VDBRT_FOG_REFILL", 8);        // shadow kernel: idle lanes that trigger a refill from the record queue
     ctx->fog_rec_per_ray = envU("VDBRT_FOG_REC_PER_RAY", 12);   // record budget per primary ray (average over a batch of tiles)
     ctx->fog_cap_mb = envU("VDBRT_FOG_CAP_MB", 4096);     // device memory for the records of one batch
     if ((ev = std::getenv("VDBRT_LS_LEAVES"))) {
@@ -785,6 +787,13 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
                         uint32_t width, uint32_t height, float4* dFilm, unsigned long long* dCounters)
 {
     VolParams p; vol_params(opts, p);
+    {
+        const DevGrid& g = grid->dgrid;
+        const double jx = p.light[0] * g.inv[0], jy = p.light[1] * g.inv[1], jz = p.light[2] * g.inv[2];
+        const double len = std::sqrt(jx * jx + jy * jy + jz * jz);
+        const double dx = jx / len, dy = jy / len, dz = jz / len;
+        p.sb[0] = dx; p.sb[1] = dy; p.sb[2] = dz; p.sb[3] = 1 / dx; p.sb[4] = 1 / dy; p.sb[5] = 1 / dz; p.sb[6] = len * 1e-9; p.sb[7] = len * DBL_MAX;
+    }
     const TileMap tm = makeTileMap(width, height, opts->part.tile_w, opts->part.tile_h, opts->part.rank, opts->part.count);
     const DevCamera dc = toDev(*cam);
     unsigned int* queue = reinterpret_cast<unsigned int*>(ctx->scratch + 64);
@@ -818,6 +827,7 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
         FogWave fw;
         fw.ctl = reinterpret_cast<unsigned int*>(b + oCtl); fw.tileFlag = b + oFlag; fw.rays = reinterpret_cast<FogRayRec*>(b + oRays);
         fw.recs = reinterpret_cast<FogRec*>(b + oRecs); fw.cap = uint32_t(cap);
+        fw.refill = ctx->fog_refill >= 1u && ctx->fog_refill <= 32u ? ctx->fog_refill : 32u;
         int perSm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fog_shadow, kBlockThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
         const int shadowBlocks = ctx->sm_count * perSm;
@@ -996,7 +1006,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     struct { const char* name; uint32_t* field; } table[] = {
         {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
-        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
+        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };
     for (auto& t : table) if (k == t.name) {
         if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;

@@ -16,6 +16,12 @@
 // efficiency and occupancy; what it costs is ~100 bytes of HBM traffic per dense sample -- on a path whose kernels leave HBM idle.
 #pragma once
 #include "vdbrt_kernels.cuh"
+#ifndef VDBRT_FOG_SHADOW_BLOCKS
+#define VDBRT_FOG_SHADOW_BLOCKS 6
+#endif
+#ifndef VDBRT_FOG_PRIMARY_BLOCKS
+#define VDBRT_FOG_PRIMARY_BLOCKS 4
+#endif
 
 namespace vdbrt {
 
@@ -33,6 +39,7 @@ struct FogWave {
     unsigned int* ctl;                                     // [0] tile queue, [1] records used, [2] flagged tiles, [3] shadow queue
     uint32_t cap;                                          // records available
     uint32_t tile0, tile1;                                 // this batch: work items [tile0, tile1) of the launch's TileMap
+    uint32_t refill;                                       // shadow kernel: idle lanes that trigger a refill from the record queue (32: whole tickets)
 };
 
 // Parking area for the suspended parent levels of ONE span walk per lane (two slots: root level, upper level)
@@ -40,7 +47,6 @@ template<int THREADS>
 struct FogPark {
     double t1[2][THREADS], nx[2][THREADS], ny[2][THREADS], nz[2][THREADS];
     int vx[2][THREADS], vy[2][THREADS], vz[2][THREADS];
-    double sbase[8];
     __device__ __forceinline__ void park(int slot, const Dda& d)
     {
         const int t = threadIdx.x;
@@ -52,18 +58,6 @@ struct FogPark {
         d.t1 = t1[slot][t]; d.nx = nx[slot][t]; d.ny = ny[slot][t]; d.nz = nz[slot][t]; d.vx = vx[slot][t]; d.vy = vy[slot][t]; d.vz = vz[slot][t];
     }
 };
-
-// the shadow ray's direction is the same for every sample: sRay(Vec3R(0), mLightDir) through worldToIndex
-// (tools/RayTracer.h:1017,1039-1040; Ray ctor defaults t0 = 1e-9, t1 = max, math/Ray.h:57-63)
-__device__ __forceinline__ void shadowBase(const DevGrid& g, const VolParams& p, double* sbase)
-{
-    const double jx = p.light[0] * g.inv[0], jy = p.light[1] * g.inv[1], jz = p.light[2] * g.inv[2];
-    const double len = vlength(jx, jy, jz);
-    const double dx = jx / len, dy = jy / len, dz = jz / len;
-    sbase[0] = dx; sbase[1] = dy; sbase[2] = dz;
-    sbase[3] = 1 / dx; sbase[4] = 1 / dy; sbase[5] = 1 / dz;
-    sbase[6] = len * 1e-9; sbase[7] = len * DBL_MAX;
-}
 
 // One lane's march along one ray: the lazy span walk of k_render_volume (vdbrt_kernels.cuh) -- a sample is taken as soon as the
 // entry time of the last probed cell proves that it lies inside the still-open span.
@@ -106,20 +100,24 @@ constexpr int kFogWaveBatch = 8;       // a phase runs when this many lanes want
 // ---------------------------------------------------------------------------------------------------------------------------
 // 1. primary rays
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads, 4)
+__global__ void __launch_bounds__(kBlockThreads, VDBRT_FOG_PRIMARY_BLOCKS)
 k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
               const __grid_constant__ TileMap tm, const __grid_constant__ FogWave fw)
 {
     __shared__ RootSmem root;
     __shared__ FogPark<kBlockThreads> sm;
     stageRoot(g, root);
-    if (threadIdx.x == 0) shadowBase(g, p, sm.sbase);
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t spp = p.sub + 1u;
+#ifdef VDBRT_FOG_PRIMARY_TWO_CURSORS
     TreeCursor accW, accV;               // walker cursor, sampler cursor (the reference keeps separate accessors too)
     accW.reset(); accV.reset();
+#else
+    TreeCursor accW; accW.reset();       // one cursor for both (see k_fog_shadow)
+    TreeCursor& accV = accW;
+#endif
     Counters c = {};
     bool busy = false, pendExp = false, needRay = false, drained = false;
     size_t pix = 0;
@@ -195,9 +193,9 @@ k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCame
                 worldToIndexPos(g, wx, wy, wz);
                 Ray sRay;
                 sRay.ex = wx; sRay.ey = wy; sRay.ez = wz;
-                sRay.dx = sm.sbase[0]; sRay.dy = sm.sbase[1]; sRay.dz = sm.sbase[2];
-                sRay.ix = sm.sbase[3]; sRay.iy = sm.sbase[4]; sRay.iz = sm.sbase[5];
-                sRay.t0 = sm.sbase[6]; sRay.t1 = sm.sbase[7];
+                sRay.dx = p.sb[0]; sRay.dy = p.sb[1]; sRay.dz = p.sb[2];
+                sRay.ix = p.sb[3]; sRay.iy = p.sb[4]; sRay.iz = p.sb[5];
+                sRay.t0 = p.sb[6]; sRay.t1 = p.sb[7];
                 if (!clipRay(sRay, g, 1)) m.tcur += p.pstep;                              // `continue`: no luminance, pTrans unchanged
                 else { emit = true; sx = wx; sy = wy; sz = wz; s0 = sRay.t0; s1 = sRay.t1; }
             }
@@ -244,39 +242,45 @@ k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCame
 // ---------------------------------------------------------------------------------------------------------------------------
 // 2. shadow rays: one lane per record, 32 consecutive records per warp ticket
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads, 4)
+__global__ void __launch_bounds__(kBlockThreads, VDBRT_FOG_SHADOW_BLOCKS)
 k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParams p, const __grid_constant__ FogWave fw)
 {
     __shared__ RootSmem root;
     __shared__ FogPark<kBlockThreads> sm;
     stageRoot(g, root);
-    if (threadIdx.x == 0) shadowBase(g, p, sm.sbase);
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t nRec = min(fw.ctl[1], fw.cap);
-    TreeCursor accW, accV;
-    accW.reset(); accV.reset();
+    // ONE tree cursor for the span walk and the sampler (the reference keeps two accessors): a cursor is only a cache, and the samples
+    // lie in the span the walk has just crossed, mostly in the same lower node -- six registers less buy a sixth CTA per SM
+    TreeCursor accW; accW.reset();
+    TreeCursor& accV = accW;
     Counters c = {};
+    // every ray of this kernel has the direction p.sb (kernel parameters): the six direction registers of a lane are never anything else
     FogMarch m; m.idle();
+    m.ray.dx = p.sb[0]; m.ray.dy = p.sb[1]; m.ray.dz = p.sb[2]; m.ray.ix = p.sb[3]; m.ray.iy = p.sb[4]; m.ray.iz = p.sb[5];
     bool busy = false, pendExp = false, drained = false;
     uint32_t rec = 0;
     double dens = 0.0, Sx = 1.0, Sy = 1.0, Sz = 1.0;
 
+    // Lanes are re-fed one by one: a shadow ray is set up by loading its record (no camera arithmetic), and the records a warp
+    // draws next lie right behind the ones it is working on -- they were appended by the same primary warps -- so, unlike in the
+    // level-set kernel, feeding single lanes costs neither set-up time nor locality (fw.refill idle lanes trigger a refill).
     for (;;) {
         __syncwarp();
-        if (!__any_sync(0xffffffffu, busy)) {
-            if (drained) break;
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle == 0xffffffffu && drained) break;
+        if (!drained && (idle == 0xffffffffu || (unsigned)__popc(idle) >= fw.refill)) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(fw.ctl + 3, 32u);
+            if (lane == 0) base = atomicAdd(fw.ctl + 3, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= nRec) { drained = true; continue; }
-            rec = base + lane;
-            if (rec < nRec) {
+            if (base + (unsigned)__popc(idle) >= nRec) drained = true;
+            const unsigned mine = base + __popc(idle & ((1u << lane) - 1u));
+            if (!busy && mine < nRec) {
+                rec = mine;
                 const FogRec* r = fw.recs + rec;
                 m.ray.ex = r->eye[0]; m.ray.ey = r->eye[1]; m.ray.ez = r->eye[2];
-                m.ray.dx = sm.sbase[0]; m.ray.dy = sm.sbase[1]; m.ray.dz = sm.sbase[2];
-                m.ray.ix = sm.sbase[3]; m.ray.iy = sm.sbase[4]; m.ray.iz = sm.sbase[5];
                 m.ray.t0 = r->t0; m.ray.t1 = r->t1;
                 m.begin();
                 Sx = Sy = Sz = 1.0; busy = true; pendExp = false;
@@ -322,7 +326,8 @@ k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParam
                 r->a[0] = ax; r->a[1] = ay; r->a[2] = az;
                 busy = false; pendExp = false;
             }
-            if (!__any_sync(0xffffffffu, busy)) break;
+            const unsigned running = __ballot_sync(0xffffffffu, busy);
+            if (running == 0u || (!drained && 32u - (unsigned)__popc(running) >= fw.refill)) break;
         }
     }
 }

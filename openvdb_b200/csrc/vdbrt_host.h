@@ -18,7 +18,7 @@ struct vdbrt_ctx {
     void* ord = nullptr;   size_t ord_cap = 0;  // tile-ordering buffers of the level-set render (OrderBufs, vdbrt_kernels.cuh)
     uint32_t ls_strip = 1, ls_strip_ratio = 4, ls_refill = 32, ls_eager = 0, ls_affine = 0, ls_order = 0, ls_probe_cap = 128, ls_probe_b = 64;   // Sched (vdbrt_kernels.cuh)
     void* fog = nullptr;   size_t fog_cap = 0;  // records / ray table of the fog wavefront (vdbrt_fog.cuh)
-    uint32_t fog_wave = 1, fog_rec_per_ray = 12, fog_cap_mb = 4096;
+    uint32_t fog_wave = 1, fog_refill = 8, fog_rec_per_ray = 12, fog_cap_mb = 4096;
     uint32_t ls_voxel_only = 0;                 // tail rule: only rays that are marching voxels are suspended
     uint32_t ls_tail = 0;                       // tail rule: iterations a tile may still spend once the work queue has run dry (0: per-tile rule below)
     uint32_t ls_budget = 0;                     // warp iterations a tile may spend before its running rays are suspended (0 = never)

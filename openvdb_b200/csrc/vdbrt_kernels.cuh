@@ -779,6 +779,10 @@ struct VolParams {
     double ext[3], albedo[3];   // extinction = -scattering-absorption; albedo = lightColor*scattering/(scattering+absorption)
     uint32_t sub; float frac;   // samples per pixel - 1, 1/samples (EXTENSION: the reference's VolumeRender has one sample per pixel)
     double jitter[16];
+    // the shadow ray's index-space direction, 1/direction and times -- sRay(Vec3R(0), mLightDir) through worldToIndex (tools/RayTracer.h:1017,
+    // 1039-1040; Ray ctor defaults t0 = 1e-9, t1 = max, math/Ray.h:57-63) -- the same for every sample, evaluated once on the host with
+    // the device's arithmetic (IEEE division and sqrt, no contraction): as kernel parameters they cost the shadow kernel no registers
+    double sb[8];
 };
 
 // Per-lane state machine, warp-synchronous like the level-set kernel.  A lane works on its primary ray or on a shadow

@@ -15,7 +15,7 @@ RTOL, ATOL = 1e-4, 1e-3
 @pytest.fixture()
 def tuned(ctx):
     yield ctx
-    ctx.set_tuning(fog_wave=1, fog_rec_per_ray=12, fog_cap_mb=4096)
+    ctx.set_tuning(fog_wave=1, fog_refill=8, fog_rec_per_ray=12, fog_cap_mb=4096)
 
 
 @pytest.fixture(scope="module")
@@ -54,13 +54,13 @@ def test_wavefront_equals_one_loop_kernel_and_oracle(tuned, oracle, fog_union, s
     assert (want[..., 3] > 0).sum() > 5000
     assert np.array_equal(base[..., 3] > 0, want[..., 3] > 0) and np.allclose(base, want, rtol=RTOL, atol=ATOL)
     # (records per ray, MB per batch): plenty / several batches / starved (most tiles fall back) / one record for the whole batch
-    for per_ray, cap_mb in ((12, 4096), (12, 1), (2, 4096), (1, 1)):
-        ctx.set_tuning(fog_wave=1, fog_rec_per_ray=per_ray, fog_cap_mb=cap_mb)
+    for per_ray, cap_mb, refill in ((12, 4096, 8), (12, 1, 32), (2, 4096, 1), (1, 1, 8), (12, 4096, 16)):
+        ctx.set_tuning(fog_wave=1, fog_rec_per_ray=per_ray, fog_cap_mb=cap_mb, fog_refill=refill)
         film, _ = render(ctx, fog, cam, W, H, spp)
         assert ctx.last_kernel_ms()[1] >= 4
-        assert np.array_equal(film, base), (per_ray, cap_mb)
+        assert np.array_equal(film, base), (per_ray, cap_mb, refill)
     # three ranks, one after the other, into one film
-    ctx.set_tuning(fog_wave=1, fog_rec_per_ray=12, fog_cap_mb=4096)
+    ctx.set_tuning(fog_wave=1, fog_refill=8, fog_rec_per_ray=12, fog_cap_mb=4096)
     film = refapi.new_film(W, H, (0.5, 0.25, 0.125, 0.75))
     for r in range(3):
         vo = api.vol_opts_default(spp=spp, seed=2)

@@ -29,7 +29,7 @@ def main():
     lines = sass_lines(lib, kern)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, data = rows[1], rows[2:]
+    hdr, data = (rows[1], rows[2:]) if "Address" in rows[1] else (rows[0], rows[1:])
     iA, iE, iT, iS = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed'), hdr.index('# Samples')
     assert len(data) == len(lines), (len(data), len(lines))
     per = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0, 0]
