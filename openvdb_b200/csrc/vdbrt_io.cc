@@ -15,8 +15,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
+#include <sys/types.h>
 #include <zlib.h>
 
 namespace vdbrt {
@@ -49,13 +52,32 @@ static_assert(sizeof(FileHeader) == 16 && sizeof(FileMetaData) == 176, "NanoVDB 
 
 struct File {
     std::FILE* f = nullptr;
-    explicit File(const char* path, const char* mode) : f(std::fopen(path, mode)) {}
+    int64_t size = 0;                                              // length of the file (input files)
+    explicit File(const char* path, const char* mode) : f(std::fopen(path, mode))
+    {
+        if (f && mode[0] == 'r' && fseeko(f, 0, SEEK_END) == 0) { size = int64_t(ftello(f)); fseeko(f, 0, SEEK_SET); }
+    }
     ~File() { if (f) std::fclose(f); }
     bool read(void* dst, size_t n) { return std::fread(dst, 1, n, f) == n; }
     bool write(const void* src, size_t n) { return std::fwrite(src, 1, n, f) == n; }
+    int64_t tell() { return int64_t(ftello(f)); }
+    bool seek(int64_t at) { return at >= 0 && at <= size && fseeko(f, off_t(at), SEEK_SET) == 0; }
 };
 
-struct Entry { FileMetaData meta; std::string name; long payload; };   // payload: file offset of the grid's bytes
+struct Entry { FileMetaData meta; std::string name; int64_t payload; };   // payload: file offset of the grid's bytes
+
+// Nothing a file says about sizes is trusted before it has been checked against the length of the file: a grid name is at most
+// kMaxName bytes, a payload lies inside the file, an uncompressed grid is as long as its payload, a ZIP stream is shorter than it.
+constexpr uint32_t kMaxName = 4096;
+constexpr uint64_t kMaxGrid = 1ull << 40;                         // 1 TiB: more than any GPU holds; bounds the allocation for a ZIP payload
+
+// every extern "C" body runs inside this: no C++ exception may cross the C ABI
+template<class F> int guarded(F&& body)
+{
+    try { return body(); }
+    catch (const std::bad_alloc&) { return setError(VDBRT_ERR_IO, "out of host memory"); }
+    catch (const std::exception& e) { return setError(VDBRT_ERR_BAD_GRID, std::string("malformed NanoVDB file: ") + e.what()); }
+}
 
 // io::stringHash (nanovdb/io/IO.h:718-729): the name key stored in FileMetaData (readers compare it before the name)
 uint64_t nameHash(const char* s)
@@ -75,7 +97,7 @@ int scan(File& in, std::vector<Entry>& out)
 {
     for (;;) {
         FileHeader h;
-        const long at = std::ftell(in.f);
+        const int64_t at = in.tell();
         const size_t got = std::fread(&h, 1, sizeof(h), in.f);
         if (got == 0) break;                                        // clean end of file
         if (got != sizeof(h)) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB file header");
@@ -88,13 +110,21 @@ int scan(File& in, std::vector<Entry>& out)
         std::vector<Entry> seg(h.gridCount);
         for (auto& e : seg) {
             if (!in.read(&e.meta, sizeof(FileMetaData))) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB grid meta data");
-            std::vector<char> name(e.meta.nameSize + 1, '\0');
+            if (e.meta.nameSize > kMaxName || int64_t(e.meta.nameSize) > in.size - in.tell())
+                return setError(VDBRT_ERR_BAD_GRID, "NanoVDB grid name longer than the file allows");
+            std::vector<char> name(size_t(e.meta.nameSize) + 1, '\0');
             if (e.meta.nameSize && !in.read(name.data(), e.meta.nameSize)) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB grid name");
             e.name = name.data();
         }
-        long pos = std::ftell(in.f);
-        for (auto& e : seg) { e.payload = pos; pos += long(e.meta.fileSize); out.push_back(e); }
-        if (std::fseek(in.f, pos, SEEK_SET) != 0) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB file");
+        int64_t pos = in.tell();
+        for (auto& e : seg) {
+            const uint64_t left = uint64_t(in.size - pos);
+            if (e.meta.fileSize > left) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB file (a grid payload ends beyond the end of the file)");
+            if (e.meta.gridSize > kMaxGrid || (e.meta.codec == CODEC_NONE && e.meta.gridSize != e.meta.fileSize) || (e.meta.codec == CODEC_ZIP && e.meta.fileSize < 8))
+                return setError(VDBRT_ERR_BAD_GRID, "inconsistent sizes in the NanoVDB grid meta data");
+            e.payload = pos; pos += int64_t(e.meta.fileSize); out.push_back(e);
+        }
+        if (!in.seek(pos)) return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB file");
     }
     return VDBRT_OK;
 }
@@ -107,6 +137,7 @@ extern "C" {
 
 int vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, uint32_t* count)
 {
+  return guarded([&]() -> int {
     if (!path || !count) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     File in(path, "rb");
     if (!in.f) return setError(VDBRT_ERR_IO, std::string("Unable to open file named \"") + path + "\" for input");
@@ -140,6 +171,7 @@ int vdbrt_nvdb_list(const char* path, vdbrt_nvdb_meta* out, uint32_t capacity, u
         for (int k = 0; k < 3; ++k) out[i].voxel_size[k] = m.voxelSize[k];
     }
     return VDBRT_OK;
+  });
 }
 
 int vdbrt_nvdb_read(const char* path, const char* gridName, void** buffer, uint64_t* bytes)
@@ -149,17 +181,29 @@ int vdbrt_nvdb_read(const char* path, const char* gridName, void** buffer, uint6
 
 int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridType, void** buffer, uint64_t* bytes)
 {
+  return guarded([&]() -> int {
     if (!path || !buffer || !bytes) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     *buffer = nullptr; *bytes = 0;
     File in(path, "rb");
     if (!in.f) return setError(VDBRT_ERR_IO, std::string("Unable to open file named \"") + path + "\" for input");
     uint64_t first = 0;
-    if (in.read(&first, 8) && first == MAGIC_GRID) {               // raw grid buffer
-        std::fseek(in.f, 0, SEEK_END);
-        const long size = std::ftell(in.f);
+    // "float" includes the quantised float types Fp4/Fp8/Fp16/FpN (GridType 13..16): vdbrt_upload_grid expands them
+    auto matches = [gridType](uint32_t t) { return gridType == 0u || t == gridType || (gridType == 1u && t >= 13u && t <= 16u); };
+    const char* what = gridType == 1u ? "scalar, floating-point" : (gridType == 6u ? "vec3s color" : "matching");
+    if (in.read(&first, 8) && first == MAGIC_GRID) {               // raw grid buffer: one grid, described by its own GridData
+        const int64_t size = in.size;
+        uint8_t head[736];
         std::rewind(in.f);
+        if (size < int64_t(sizeof(head)) || !in.read(head, sizeof(head))) return setError(VDBRT_ERR_BAD_GRID, "truncated raw NanoVDB grid");
+        uint64_t gridSize; uint32_t type;
+        std::memcpy(&gridSize, head + 32, 8); std::memcpy(&type, head + 636, 4);
+        if (gridSize > uint64_t(size)) return setError(VDBRT_ERR_BAD_GRID, "truncated raw NanoVDB grid (grid size exceeds the file)");
+        char name[257]; std::memcpy(name, head + 40, 256); name[256] = 0;
+        if (gridName && *gridName && std::strcmp(name, gridName) != 0) return setError(VDBRT_ERR_IO, std::string("no grid named \"") + gridName + "\" in file " + path);
+        if (!matches(type)) return setError(VDBRT_ERR_NOT_FLOAT, std::string(gridName && *gridName ? gridName : "the grid") + " is not a " + what + " volume");
         void* p = alignedAlloc(uint64_t(size));
         if (!p) return setError(VDBRT_ERR_IO, "out of host memory");
+        std::rewind(in.f);
         if (!in.read(p, size_t(size))) { std::free(p); return setError(VDBRT_ERR_BAD_GRID, "truncated raw NanoVDB grid"); }
         *buffer = p; *bytes = uint64_t(size);
         return VDBRT_OK;
@@ -167,9 +211,6 @@ int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridT
     std::rewind(in.f);
     std::vector<Entry> all;
     if (int rc = scan(in, all)) return rc;
-    // "float" includes the quantised float types Fp4/Fp8/Fp16/FpN (GridType 13..16): vdbrt_upload_grid expands them
-    auto matches = [gridType](uint32_t t) { return gridType == 0u || t == gridType || (gridType == 1u && t >= 13u && t <= 16u); };
-    const char* what = gridType == 1u ? "scalar, floating-point" : (gridType == 6u ? "vec3s color" : "matching");
     const Entry* pick = nullptr;
     for (const Entry& e : all) {
         if (gridName && *gridName) { if (e.name == gridName) { pick = &e; break; } }
@@ -183,13 +224,14 @@ int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridT
         return setError(VDBRT_ERR_NOT_FLOAT, std::string(gridName ? gridName : "") + " is not a " + what + " volume");   // main.cc:766-769,790-794
     void* p = alignedAlloc(pick->meta.gridSize);
     if (!p) return setError(VDBRT_ERR_IO, "out of host memory");
-    std::fseek(in.f, pick->payload, SEEK_SET);
+    if (!in.seek(pick->payload)) { std::free(p); return setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB file"); }
     int rc = VDBRT_OK;
     if (pick->meta.codec == CODEC_NONE) {
         if (!in.read(p, size_t(pick->meta.gridSize))) rc = setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB grid payload");
     } else if (pick->meta.codec == CODEC_ZIP) {
         uint64_t csize = 0;
         if (!in.read(&csize, 8)) rc = setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB grid payload");
+        else if (csize > pick->meta.fileSize - 8) rc = setError(VDBRT_ERR_BAD_GRID, "ZIP stream longer than its payload");
         else {
             std::vector<unsigned char> tmp(csize);
             if (!in.read(tmp.data(), size_t(csize))) rc = setError(VDBRT_ERR_BAD_GRID, "truncated NanoVDB grid payload");
@@ -203,10 +245,12 @@ int vdbrt_nvdb_read_typed(const char* path, const char* gridName, uint32_t gridT
     if (rc != VDBRT_OK) { std::free(p); return rc; }
     *buffer = p; *bytes = pick->meta.gridSize;
     return VDBRT_OK;
+  });
 }
 
 int vdbrt_nvdb_write(const char* path, const void* buffer, uint64_t bytes, uint32_t codec)
 {
+  return guarded([&]() -> int {
     if (!path || !buffer) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (bytes < 736) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
     if (codec != CODEC_NONE && codec != CODEC_ZIP) return setError(VDBRT_ERR_UNSUPPORTED, "only the NONE and ZIP codecs are built in");
@@ -249,6 +293,7 @@ int vdbrt_nvdb_write(const char* path, const void* buffer, uint64_t bytes, uint3
     else ok = ok && out.write(g, size_t(gridSize));
     if (!ok) return setError(VDBRT_ERR_IO, "Failed writing NanoVDB file");
     return VDBRT_OK;
+  });
 }
 
 int vdbrt_buffer_free(void* buffer) { std::free(buffer); return VDBRT_OK; }
@@ -257,6 +302,7 @@ int vdbrt_buffer_free(void* buffer) { std::free(buffer); return VDBRT_OK; }
 // every channel is static_cast<unsigned char>(255.0f * value)
 int vdbrt_film_save_ppm(const char* fileName, const float* rgba, uint32_t width, uint32_t height)
 {
+  return guarded([&]() -> int {
     if (!fileName || !rgba) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     std::string name(fileName);
     if (name.find_last_of(".") == std::string::npos) name.append(".ppm");
@@ -269,6 +315,7 @@ int vdbrt_film_save_ppm(const char* fileName, const float* rgba, uint32_t width,
     std::fprintf(out.f, "P6\n%u %u\n255\n", width, height);
     if (!out.write(buf.data(), buf.size())) return setError(VDBRT_ERR_IO, "Failed writing PPM file");
     return VDBRT_OK;
+  });
 }
 
 } // extern "C"

@@ -112,3 +112,66 @@ def test_save_ppm(tmp_path):
     px = np.frombuffer(raw[len(head):], np.uint8).reshape(5, 7, 3)
     assert np.array_equal(px, (np.float32(255.0) * film[..., :3]).astype(np.uint8))
     assert tuple(px[0, 0]) == (255, 0, 254)
+
+
+def _patched(src, tmp_path, name, edits):
+    """a copy of a reference-written file with some header bytes overwritten: edits = [(offset, bytes)]"""
+    raw = bytearray(open(src, "rb").read())
+    for off, b in edits:
+        raw[off:off + len(b)] = b
+    p = str(tmp_path / name)
+    open(p, "wb").write(bytes(raw))
+    return p
+
+
+def test_malformed_files_are_rejected_not_trusted(tmp_path):
+    """every size a file states is checked against the length of the file before anything is allocated or read:
+    FileHeader 16 B, then FileMetaData 176 B with gridSize @0, fileSize @8, nameSize @136, codec @168"""
+    import struct
+    none, zipf = golden("io_none.nvdb"), golden("io_zip.nvdb")
+    meta = 16
+    cases = [
+        ("name_wraps.nvdb", none, [(meta + 136, struct.pack("<I", 0xFFFFFFFF))]),          # nameSize + 1 wrapped to 0 in round 1
+        ("name_huge.nvdb", none, [(meta + 136, struct.pack("<I", 1 << 20))]),
+        ("payload_beyond_eof.nvdb", none, [(meta + 8, struct.pack("<Q", 1 << 40))]),
+        ("grid_size_mismatch.nvdb", none, [(meta + 0, struct.pack("<Q", 1 << 50))]),
+        ("zip_grid_size_huge.nvdb", zipf, [(meta + 0, struct.pack("<Q", 1 << 62))]),
+        ("zip_payload_tiny.nvdb", zipf, [(meta + 8, struct.pack("<Q", 4))]),
+    ]
+    for name, src, edits in cases:
+        p = _patched(src, tmp_path, name, edits)
+        for call in (lambda: api.nvdb_read(p), lambda: api.nvdb_list(p)):
+            with pytest.raises(api.VdbrtError) as e:
+                call()
+            assert e.value.code in (abi.ERR_BAD_GRID, abi.ERR_IO), name
+    # a ZIP stream that claims to be longer than its payload (the uint64 in front of the stream)
+    raw = open(zipf, "rb").read()
+    name_size = struct.unpack_from("<I", raw, meta + 136)[0]
+    p = _patched(zipf, tmp_path, "zip_stream_long.nvdb", [(16 + 176 + name_size, struct.pack("<Q", 1 << 40))])
+    with pytest.raises(api.VdbrtError) as e:
+        api.nvdb_read(p)
+    assert e.value.code == abi.ERR_BAD_GRID
+    # truncated file
+    p = str(tmp_path / "cut.nvdb")
+    open(p, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(api.VdbrtError):
+        api.nvdb_read(p)
+
+
+def test_raw_grid_buffer_honours_name_and_type(tmp_path):
+    raw = golden("io_sphere.raw")
+    got = api.nvdb_read(raw)
+    assert np.array_equal(got, np.fromfile(raw, np.uint8))
+    name = bytes(got[40:40 + 256]).split(b"\0")[0].decode()
+    assert np.array_equal(api.nvdb_read(raw, name=name), got)
+    with pytest.raises(api.VdbrtError) as e:
+        api.nvdb_read(raw, name="no_such_grid")
+    assert e.value.code == abi.ERR_IO
+    with pytest.raises(api.VdbrtError) as e:
+        api.nvdb_read(raw, grid_type=6)                      # a float grid is not a Vec3f colour grid
+    assert e.value.code == abi.ERR_NOT_FLOAT
+    cut = str(tmp_path / "cut.raw")
+    open(cut, "wb").write(open(raw, "rb").read()[:5000])
+    with pytest.raises(api.VdbrtError) as e:
+        api.nvdb_read(cut)
+    assert e.value.code == abi.ERR_BAD_GRID
