@@ -20,7 +20,7 @@ ERR_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "BAD_GRID", 3: "NOT_FLOAT", 4: "NOT_LEVELSET", 5: "NONUNIFORM",
     6: "EMPTY_GRID", 7: "ISO_RANGE", 8: "SPP_ZERO", 9: "CUDA", 10: "UNSUPPORTED", 11: "NOMEM", 12: "IO",
 }
-ERR_BAD_GRID, ERR_NOT_FLOAT, ERR_UNSUPPORTED, ERR_IO = 2, 3, 10, 12
+ERR_INVALID_ARG, ERR_BAD_GRID, ERR_NOT_FLOAT, ERR_UNSUPPORTED, ERR_IO = 1, 2, 3, 10, 12
 
 
 class Ray(C.Structure):

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -116,16 +117,25 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     d.has_translation = (d.trans[0] != 0 || d.trans[1] != 0 || d.trans[2] != 0) ? 1u : 0u;
     d.voxel_size0 = info.voxel_size[0];
 
-    // node-granular bbox on the device
-    int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    // node-granular bbox on the device; the same pass checks that every child offset lands on a node of the right level inside the
+    // buffer (counted in init[6]) -- the derived structures below and the render kernels follow those links without looking again
+    const uint64_t leafOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 0)), lowerOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 8));
+    const uint64_t upperOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 16));
+    if ((info.leaf_count && leafOff + uint64_t(info.leaf_count) * 2144ull > grid->bytes) || (info.lower_count && lowerOff + uint64_t(info.lower_count) * 33856ull > grid->bytes) ||
+        (info.upper_count && upperOff + uint64_t(info.upper_count) * 270400ull > grid->bytes) || ((leafOff | lowerOff | upperOff | rootOff) & 31))
+        return setError(VDBRT_ERR_BAD_GRID, "node arrays outside the buffer or misaligned");
+    int init[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
     CUDA_TRY(cudaMemcpyAsync(ctx->scratch, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     if (info.root_tiles) {
+        const NodeAreas ar = {upperOff, info.upper_count, lowerOff, info.lower_count, leafOff, info.leaf_count};
         const unsigned long long threads = (unsigned long long)info.root_tiles << 15;
-        k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch));
+        k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch), ar);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(init, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (init[6] != 0) return setError(VDBRT_ERR_BAD_GRID, "corrupt NanoVDB tree: " + std::to_string(init[6]) + " child offsets do not point at a node of their level inside the buffer");
     }
     // "leaf or active tile" masks of the lower nodes (DevGrid::lowmask), for the volume walk; VDBRT_LOWMASK=0 keeps them off
-    const uint64_t lowerOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 8));
     static const bool useLowmask = [] { const char* e = std::getenv("VDBRT_LOWMASK"); return !(e && *e == '0'); }();
     cudaFree(grid->lowmask); grid->lowmask = nullptr;
     if (useLowmask && info.lower_count && info.root_tiles && !(lowerOff & 31) && lowerOff + uint64_t(info.lower_count) * 33856ull <= grid->bytes) {
@@ -139,7 +149,6 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     }
     // halo blocks of the leaves (DevGrid::halo): an acceleration structure like the node bbox, built once here.
     // Needs 2944 B per leaf next to the grid; without the memory (or with VDBRT_HALO=0) the stencil walks the leaves instead.
-    const uint64_t leafOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 0));
     static const bool useHalo = [] { const char* e = std::getenv("VDBRT_HALO"); return !(e && *e == '0'); }();
     cudaFree(grid->halo); grid->halo = nullptr;
     if (useHalo && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
@@ -154,7 +163,6 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
             d.halo = grid->halo;
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(init, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 6; ++i) info.node_bbox[i] = init[i];
     for (int a = 0; a < 3; ++a) { d.bbox_min[a] = init[a]; d.bbox_max[a] = init[3 + a]; }
@@ -223,12 +231,27 @@ void ls_params(const vdbrt_grid* grid, const vdbrt_ls_opts* o, const vdbrt_film*
 // A pinned host film is written by the kernels directly (unified addressing: the stores travel over PCIe while the rest of
 // the frame is still being traced), so no device->host copy of the film follows the render.  Returns the device alias of
 // the host pointer, or null for pageable memory.
-float4* pinnedAlias(const void* host)
+// 0: pageable (stage it), 1: the whole range is one page-locked, mapped allocation / registration (*alias = its device address),
+// 2: only a part of it is page-locked -- CUDA can neither map nor copy such a range in one piece, the caller gets an error
+int classifyHostFilm(const void* host, size_t bytes, float4** alias)
 {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return a.type == cudaMemoryTypeHost ? static_cast<float4*>(a.devicePointer) : nullptr;
+    // the kernels read and write the WHOLE film in place: the first and the last byte must belong to the same registration
+    *alias = nullptr;
+    cudaPointerAttributes a, z;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool firstPinned = a.type == cudaMemoryTypeHost && a.devicePointer;
+    if (bytes > 1) {
+        const char* last = static_cast<const char*>(host) + (bytes - 1);
+        if (cudaPointerGetAttributes(&z, last) != cudaSuccess) { cudaGetLastError(); return firstPinned ? 2 : 0; }
+        const bool lastPinned = z.type == cudaMemoryTypeHost && z.devicePointer;
+        if (firstPinned != lastPinned) return 2;
+        if (firstPinned && static_cast<const char*>(z.devicePointer) - static_cast<const char*>(a.devicePointer) != ptrdiff_t(bytes - 1)) return 2;
+    }
+    if (!firstPinned) return 0;
+    *alias = static_cast<float4*>(a.devicePointer);
+    return 1;
 }
+const char* kPartlyPinned = "the host film is only partly page-locked: cudaHostRegister / vdbrt_host_register must cover the whole film";
 
 void vol_params(const vdbrt_vol_opts* o, VolParams& p)
 {
@@ -269,13 +292,16 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     if (prop.major < 10) return setError(VDBRT_ERR_CUDA, "kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
     auto* ctx = new vdbrt_ctx;
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    // a context that cannot be completed is taken apart again (vdbrt_destroy copes with the members that were never created)
+    auto fail = [&](cudaError_t e, const char* what) { const int rc = cudaFail(e, what); vdbrt_destroy(ctx); return rc; };
+    cudaError_t ce;
+    if ((ce = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreateWithFlags");
     ctx->stream = ctx->own_stream;
-    CUDA_TRY(cudaEventCreate(&ctx->ev0));
-    CUDA_TRY(cudaEventCreate(&ctx->ev1));
-    if (std::getenv("VDBRT_TIME_PROBE")) CUDA_TRY(cudaEventCreate(&ctx->evp));
-    CUDA_TRY(cudaMalloc(&ctx->scratch, 4096));
-    CUDA_TRY(cudaMemset(ctx->scratch, 0, 4096));
+    if ((ce = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail(ce, "cudaEventCreate");
+    if ((ce = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail(ce, "cudaEventCreate");
+    if (std::getenv("VDBRT_TIME_PROBE") && (ce = cudaEventCreate(&ctx->evp)) != cudaSuccess) return fail(ce, "cudaEventCreate");
+    if ((ce = cudaMalloc(&ctx->scratch, 4096)) != cudaSuccess) return fail(ce, "cudaMalloc(scratch)");
+    if ((ce = cudaMemset(ctx->scratch, 0, 4096)) != cudaSuccess) return fail(ce, "cudaMemset(scratch)");
     // tuning knobs of the long-ray rounds (see vdbrt_kernels.cuh); the defaults were measured on the B200
     const char* ev = std::getenv("VDBRT_LS_BUDGET");
     ctx->ls_budget = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : kDefaultBudget;
@@ -320,16 +346,19 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
 {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->film) cudaFree(ctx->film);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->lng) cudaFree(ctx->lng);
     if (ctx->ord) cudaFree(ctx->ord);
     if (ctx->fog) cudaFree(ctx->fog);
-    cudaFree(ctx->scratch);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->own_stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evp) cudaEventDestroy(ctx->evp);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    cudaGetLastError();
     delete ctx;
 }
 
@@ -417,6 +446,7 @@ int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32
 {
     if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (bytes < GRID_SIZE + TREE_SIZE) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const bool onDevice = memspace == VDBRT_MEM_DEVICE;
     uint8_t head[GRID_SIZE + TREE_SIZE];
@@ -459,6 +489,7 @@ int vdbrt_upload_color_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, 
 {
     if (!ctx || !buffer || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (bytes < GRID_SIZE + TREE_SIZE) return setError(VDBRT_ERR_BAD_GRID, "buffer smaller than GridData+TreeData");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     auto* g = new vdbrt_grid;
     g->bytes = bytes; g->device = ctx->device; g->is_color = true;
@@ -657,7 +688,9 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     ctx->last_launches = launches;
     if (rounds) {
         // K leaf visits per ray and round: small first (most suspended rays hit soon), then growing
-        const uint32_t* kLeaves = ctx->ls_leaves;
+        // K is clamped so that the 32-bit segment counter cannot wrap (every live ray adds K per round, at most capLong rays are live)
+        uint32_t kLeaves[kMaxRounds];
+        for (int r = 0; r < kMaxRounds; ++r) kLeaves[r] = std::max(1u, std::min(ctx->ls_leaves[r], uint32_t(0xffffffffu / std::max(1u, lb.capLong)) - 1u));
         const int wide = ctx->sm_count * 8;
         const int nr = int(ctx->ls_rounds);
         for (int r = 0; r < nr; ++r) {
@@ -696,7 +729,9 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
         return setError(VDBRT_ERR_INVALID_ARG, "color_grid is not a Vec3f grid uploaded to this device with vdbrt_upload_color_grid");
     if (grid->is_color) return setError(VDBRT_ERR_NOT_FLOAT, "a colour grid cannot be rendered itself");
     if (opts->spp == 0) return setError(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
+    if (opts->part.count && opts->part.rank >= opts->part.count) return setError(VDBRT_ERR_INVALID_ARG, "partition rank must be smaller than the partition count");
     if (int rc = checkLevelSet(grid, opts->iso)) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mx);         // one render at a time per context: the work queue, counters and staging buffers are the context's
     DeviceGuard guard(ctx->device);
     const size_t npx = size_t(film->width) * film->height;
     const bool host = film->memspace == VDBRT_MEM_HOST;
@@ -710,7 +745,10 @@ int vdbrt_render_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
         // still being traced, and the pixels of other ranks are never touched -- no film copy in either direction.  A pageable
         // film is staged on the device: one copy in (unless the old film is known to be uniform), one copy out.
         const bool uniform = (opts->flags & VDBRT_LS_UNIFORM_BG) != 0;
-        if (float4* alias = pinnedAlias(film->pixels)) { dFilm = alias; dBg = uniform ? nullptr : alias; }
+        float4* alias = nullptr;
+        const int kind = classifyHostFilm(film->pixels, npx * 16, &alias);
+        if (kind == 2) return setError(VDBRT_ERR_INVALID_ARG, kPartlyPinned);
+        if (kind == 1) { dFilm = alias; dBg = uniform ? nullptr : alias; }
         else {
             if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
             if (!uniform || opts->part.count > 1) CUDA_TRY(cudaMemcpyAsync(ctx->film, film->pixels, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
@@ -759,6 +797,7 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     if (!ctx || !grid || !cam || !opts || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (opts->spp == 0) return setError(VDBRT_ERR_SPP_ZERO, "pixelSamples must be larger than zero!");
     if (int rc = checkLevelSet(grid, opts->iso)) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const size_t npx = size_t(cam->width) * cam->height;
     if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;      // scratch film, discarded
@@ -866,7 +905,9 @@ int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     if (!ctx || !grid || !cam || !opts || !film || !film->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (film->width == 0 || film->height == 0) return setError(VDBRT_ERR_INVALID_ARG, "empty film");
     if (cam->width != film->width || cam->height != film->height) return setError(VDBRT_ERR_INVALID_ARG, "camera was built for a different film size");
+    if (opts->part.count && opts->part.rank >= opts->part.count) return setError(VDBRT_ERR_INVALID_ARG, "partition rank must be smaller than the partition count");
     if (int rc = checkVolume(grid)) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const size_t npx = size_t(film->width) * film->height;
     const bool host = film->memspace == VDBRT_MEM_HOST;
@@ -875,7 +916,10 @@ int vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     if (host) {
         // every owned pixel is overwritten (tools/RayTracer.h:1020) and nothing is read: a pinned film is written in place by
         // the kernel; a pageable one is staged (a partitioned render then needs the old film for the pixels of other ranks)
-        if (float4* alias = pinnedAlias(film->pixels)) dFilm = alias;
+        float4* alias = nullptr;
+        const int kind = classifyHostFilm(film->pixels, npx * 16, &alias);
+        if (kind == 2) return setError(VDBRT_ERR_INVALID_ARG, kPartlyPinned);
+        if (kind == 1) dFilm = alias;
         else {
             if (int rc = ensureBuffer(&ctx->film, &ctx->film_cap, npx * 16)) return rc;
             dFilm = static_cast<float4*>(ctx->film); copyBack = true;
@@ -893,6 +937,7 @@ int vdbrt_film_over(vdbrt_ctx* ctx, vdbrt_film* top, const vdbrt_film* bottom)
     if (!ctx || !top || !bottom || !top->pixels || !bottom->pixels) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (top->width != bottom->width || top->height != bottom->height || top->memspace != bottom->memspace)
         return setError(VDBRT_ERR_INVALID_ARG, "films differ in size or memory space");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const size_t npx = size_t(top->width) * top->height;
     float4* dTop = reinterpret_cast<float4*>(top->pixels);
@@ -921,6 +966,7 @@ int vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camer
 {
     if (!ctx || !grid || !cam || !opts || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (int rc = checkVolume(grid)) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const size_t npx = size_t(cam->width) * cam->height;
     if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;
@@ -945,6 +991,7 @@ int vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt
     if (int rc = checkLevelSet(grid, iso)) return rc;
     if (n == 0) return VDBRT_OK;
     static_assert(sizeof(vdbrt_ray) == sizeof(RayIn) && sizeof(vdbrt_hit) == sizeof(HitOut), "POD mismatch");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const RayIn* dR = reinterpret_cast<const RayIn*>(rays);
     HitOut* dH = reinterpret_cast<HitOut*>(hits);
@@ -974,6 +1021,7 @@ int vdbrt_volume_spans(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* 
     if (!ctx || !grid || (n && (!rays || !spans || !counts))) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (int rc = checkVolume(grid)) return rc;
     if (n == 0) return VDBRT_OK;
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const RayIn* dR = reinterpret_cast<const RayIn*>(rays);
     double* dS = spans; int32_t* dC = counts;

@@ -16,6 +16,7 @@
 // over blocks -> node indices, (4) fill kernels write upper / lower / leaf nodes in place.  No sort, no atomics on
 // voxel data; HBM traffic is essentially the bytes of the grid written once.
 #include "vdbrt_host.h"
+#include <mutex>
 
 #include <algorithm>
 #include <climits>
@@ -428,6 +429,7 @@ int vdbrt_build_levelset_sphere(vdbrt_ctx* ctx, double radius, const double cent
 {
     if (!ctx || !center || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (!(radius > 0) || !(voxelSize > 0) || !(halfWidth > 1)) return setError(VDBRT_ERR_INVALID_ARG, "radius and voxel size must be positive, half-width > 1");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     // float set-up exactly as LevelSetSphere::rasterSphere (tools/LevelSetSphere.h:133-145)
     const float dx = float(voxelSize), w = float(halfWidth);
@@ -445,6 +447,7 @@ int vdbrt_build_levelset_torus(vdbrt_ctx* ctx, double majorRadius, double minorR
 {
     if (!ctx || !center || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (!(minorRadius > 0) || !(majorRadius > minorRadius) || !(voxelSize > 0) || !(halfWidth > 0)) return setError(VDBRT_ERR_INVALID_ARG, "bad torus parameters");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     // nanovdb initTorus (nanovdb/tools/CreatePrimitives.h:689-705)
     PrimTorus p;
@@ -461,6 +464,7 @@ int vdbrt_build_levelset_spheres(vdbrt_ctx* ctx, const double* spheres, uint32_t
 {
     if (!ctx || !spheres || !out || n == 0) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (!(voxelSize > 0) || !(halfWidth > 1)) return setError(VDBRT_ERR_INVALID_ARG, "voxel size must be positive, half-width > 1");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     const float dx = float(voxelSize), w = float(halfWidth);
     std::vector<float4> s;
@@ -646,6 +650,7 @@ extern "C" int vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* l
 {
     if (!ctx || !ls || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (ls->info.grid_class != VDBRT_GRID_CLASS_LEVEL_SET) return setError(VDBRT_ERR_NOT_LEVELSET, "sdfToFogVolume needs a level set");
+    std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = ctx->stream;
     // source layout

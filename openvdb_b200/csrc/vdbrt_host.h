@@ -3,10 +3,12 @@
 #include "../../include/vdbrt.h"
 #include "vdbrt_device.cuh"
 #include <cuda_runtime.h>
+#include <mutex>
 #include <string>
 
 struct vdbrt_ctx {
     int device = 0, sm_count = 0;
+    std::mutex mx;                              // serialises the entry points that use the context's queue word, counters and staging buffers
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;   // bracket the kernel(s) of the last call on `stream`
     uint32_t last_launches = 0;

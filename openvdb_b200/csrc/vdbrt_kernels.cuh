@@ -1048,7 +1048,16 @@ __global__ void __launch_bounds__(256) k_build_halo(const __grid_constant__ DevG
     }
 }
 
-__global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long rootOff, uint32_t tableSize, int* out)
+// The same pass validates the tree's links: a child offset must land on a node of the right level inside the buffer
+// (nodes of one level are stored contiguously, NanoVDB.h:67-122) before anything is read through it; out[6] counts the bad ones.
+struct NodeAreas { unsigned long long upper0, upperN, lower0, lowerN, leaf0, leafN; };      // byte offset of node 0 and node count, per level
+__device__ __forceinline__ bool inArea(const uint8_t* base, const uint8_t* p, unsigned long long first, unsigned long long count, unsigned long long size)
+{
+    const unsigned long long off = (unsigned long long)(p - base);
+    return p >= base + first && off - first < count * size && (off - first) % size == 0ull;
+}
+
+__global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long rootOff, uint32_t tableSize, int* out, const __grid_constant__ NodeAreas ar)
 {
     const unsigned long long gid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const uint32_t tile = uint32_t(gid >> 15), n = uint32_t(gid & 32767u);
@@ -1059,10 +1068,13 @@ __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long
     const long long child = ldgs64(t + 8);
     if (child == 0) { if (n == 0 && ldg32(t + 16)) expandBox(out, ox, oy, oz, 4096); return; }
     const uint8_t* u = base + rootOff + child;
+    if (!inArea(base, u, ar.upper0, ar.upperN, 270400ull)) { if (n == 0) atomicAdd(out + 6, 1); return; }
     const int ux = ox + int((n >> 10) << 7), uy = oy + int(((n >> 5) & 31u) << 7), uz = oz + int((n & 31u) << 7);
     if (!maskBit(u + kUpperCMask, n)) { if (maskBit(u + kUpperVMask, n)) expandBox(out, ux, uy, uz, 128); return; }
     const uint8_t* l = u + ldgs64(u + kUpperTable + 8u * n);
+    if (!inArea(base, l, ar.lower0, ar.lowerN, 33856ull)) { atomicAdd(out + 6, 1); return; }
     int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {int(0x80000000), int(0x80000000), int(0x80000000)};
+    int bad = 0;
     for (uint32_t w = 0; w < 64; ++w) {
         const unsigned long long cm = ldg64(l + kLowerCMask + 8u * w), vm = ldg64(l + kLowerVMask + 8u * w);
         unsigned long long tiles = vm & ~cm, kids = cm;
@@ -1074,6 +1086,7 @@ __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long
         while (kids) {
             const uint32_t m = w * 64u + uint32_t(__ffsll((long long)kids) - 1); kids &= kids - 1;
             const uint8_t* lf = l + ldgs64(l + kLowerTable + 8u * m);
+            if (!inArea(base, lf, ar.leaf0, ar.leafN, 2144ull)) { ++bad; continue; }
             unsigned long long any = 0;
             for (int q = 0; q < 8; ++q) any |= ldg64(lf + kLeafVMask + 8 * q);
             if (!any) continue;
@@ -1081,6 +1094,7 @@ __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long
             mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z); mx[0] = max(mx[0], x + 7); mx[1] = max(mx[1], y + 7); mx[2] = max(mx[2], z + 7);
         }
     }
+    if (bad) atomicAdd(out + 6, bad);
     if (mn[0] <= mx[0]) {
         atomicMin(out + 0, mn[0]); atomicMin(out + 1, mn[1]); atomicMin(out + 2, mn[2]);
         atomicMax(out + 3, mx[0]); atomicMax(out + 4, mx[1]); atomicMax(out + 5, mx[2]);
