@@ -72,7 +72,10 @@ def config_for(name, gpus):
             "partition": "single GPU" if gpus <= 1 else "%d GPUs, grid replicated, %dx%d film tiles interleaved over the ranks" % (gpus, TILE_W, TILE_H),
             "l2": "grid larger than the 126 MB L2, no explicit flush" if not name.startswith("c3") and "small" not in name and "tiny" not in name
                   else "grid not larger than the L2 on this small / fog workload; no explicit flush (every frame re-reads it through the same caches)",
-            "warmup_floor": WARMUP_FLOOR}
+            "warmup_floor": WARMUP_FLOOR,
+            "tile_order": "GPU arm: level-set frames after the first of a sequence hand out the heaviest 8x4 tiles first, from the previous frame's measured "
+                          "tile costs (a hint for the ORDER of the work queue only: every ray of every frame is traced; `without_tile_cost_history` is the same "
+                          "frame in plain tile order)"}
 
 
 class ClockSampler:
@@ -371,6 +374,22 @@ def measure(rig, name, steps, warmup, sampler=None):
     total_ms, kernel_ms_max = float(tt[0]), float(tt[1])
     rays = W * H
     value = rays * steps / (total_ms * 1e-3) / 1e6
+    # the same frame without the tile-cost history of the previous frame (plain tile order), for the record
+    plain = None
+    if not fog:
+        ctx.set_tuning(ls_history=0)
+        pm = []
+        for _ in range(4):
+            render()
+            if world > 1:
+                dist.all_reduce(rig.token)
+            rig.barrier()
+            pm.append(ctx.last_kernel_ms()[0])
+        ctx.set_tuning(ls_history=1)
+        tp = torch.tensor([float(np.median(pm[1:]))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        plain = {"kernel_ms": float(tp[0]), "value": rays / (float(tp[0]) * 1e-3) / 1e6}
     if shared is not None and rank == 0:
         api.memcpy(ctx, film.data_ptr(), shared.ptr, H * W * 16, 2)
         ctx.synchronize()
@@ -449,7 +468,7 @@ def measure(rig, name, steps, warmup, sampler=None):
         out = {
             "workload": wl["text"], "metric": "primary Mrays/s", "value": value, "unit": "Mrays/s", "ms_per_step": total_ms / steps,
             "kernel_ms": kernel_ms_max, "sync_ms": total_ms / steps - kernel_ms_max, "gpu_launches_per_step": launches_per_frame,
-            ("alpha_pixels" if fog else "hit_pixels"): hits,
+            ("alpha_pixels" if fog else "hit_pixels"): hits, "without_tile_cost_history": plain,
             "grid": {"active_voxels": int(grid.info.active_voxels), "bytes": int(grid.info.bytes), "leaves": int(grid.info.leaf_count), "gpu_build_s": build_s},
             "e2e": {"value": e2e_value, "unit": "Mrays/s",
                     "h2d_bytes_per_step": (0 if fog else (W * H - hits) * 16) + C.sizeof(abi.Camera) + (C.sizeof(abi.VolOpts) if fog else C.sizeof(abi.LsOpts) + C.sizeof(abi.Shader)),
@@ -551,7 +570,7 @@ def main():
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_for(args.workload, world), "e2e": head["e2e"],
                 "gpu_launches": args.steps * head["gpu_launches_per_step"], "roofline": head["roofline"], "clocks": head.get("clocks"),
-                "kernel_ms": head["kernel_ms"], "sync_ms": head["sync_ms"], "grid": head["grid"], "hit_pixels": head.get("hit_pixels", head.get("alpha_pixels"))}
+                "kernel_ms": head["kernel_ms"], "sync_ms": head["sync_ms"], "grid": head["grid"], "without_tile_cost_history": head["without_tile_cost_history"], "hit_pixels": head.get("hit_pixels", head.get("alpha_pixels"))}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference(args.workload, 3, 1, gpu_frame=lambda w, h: gpu_sample_frame(rig, state, w, h))

@@ -327,6 +327,9 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ctx->ls_affine = envU("VDBRT_LS_AFFINE", 0);          // SM-affine queues: strips per chunk (0: one global queue)
     ctx->ls_eager = envU("VDBRT_LS_EAGER", 0);            // take the next strip while lanes of the old one are still running
     ctx->ls_order = envU("VDBRT_LS_ORDER", 0);            // heavy strips first: 0 off, 1 on, 2 when a warp gets >= 2 tiles
+    ctx->ls_history = envU("VDBRT_LS_HISTORY", 1);        // heavy tiles first from the previous frame's tile costs
+    ctx->ls_hist_a = envU("VDBRT_LS_HIST_A", 250);        // list A: tiles that took at least this many percent of the mean tile
+    ctx->ls_hist_b = envU("VDBRT_LS_HIST_B", 105);        // list B
     ctx->ls_probe_cap = envU("VDBRT_LS_PROBE_CAP", 128);  // steps a probe ray may take; unfinished = list A
     ctx->ls_probe_b = envU("VDBRT_LS_PROBE_B", 64);       // steps from which a strip goes to list B
     ctx->fog_wave = envU("VDBRT_FOG_WAVE", 1);            // VolumeRender as a wavefront of three kernels (vdbrt_fog.cuh); 0: the one-loop kernel
@@ -352,6 +355,7 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->lng) cudaFree(ctx->lng);
     if (ctx->ord) cudaFree(ctx->ord);
+    if (ctx->hist) cudaFree(ctx->hist);
     if (ctx->fog) cudaFree(ctx->fog);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -640,6 +644,36 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     }
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     uint32_t launches = 0;
+    // Heavy tiles first from the previous frame's measured tile costs (k_order_from_history): on by default (ctx->ls_history), for
+    // any sequence of frames with the same film / tiles / partition through one context.  The costs are hints for the ORDER in
+    // which the work queue hands out tiles -- every ray of every frame is traced; a stale history only means a worse order.
+    const bool history = ctx->ls_history && !dCounters && !order && sc.strip_tiles == 1u && tm.items > 1u && !(opts->flags & VDBRT_LS_ORDER_OFF);
+    if (history) {
+        auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+        const size_t n = tm.items, oCost = 256, total = oCost + up(4 * n);
+        const bool same = ctx->hist && ctx->hist_valid && std::memcmp(ctx->hist_tm, &tm, sizeof(tm)) == 0 && ctx->hist_grid == grid && ctx->hist_spp == opts->spp;
+        if (!same) {
+            if (int rc = ensureBuffer(&ctx->hist, &ctx->hist_cap, total)) return rc;
+            ctx->hist_valid = 0;
+        }
+        uint8_t* hb = static_cast<uint8_t*>(ctx->hist);
+        sc.cost_sum = reinterpret_cast<unsigned long long*>(hb); sc.cost_out = reinterpret_cast<uint32_t*>(hb + oCost);
+        if (same) {
+            const size_t oCls = 256, oA = oCls + up(n), oB = oA + up(4 * n), totalB = oB + up(4 * n);
+            if (int rc = ensureBuffer(&ctx->ord, &ctx->ord_cap, totalB)) return rc;
+            uint8_t* b = static_cast<uint8_t*>(ctx->ord);
+            OrderBufs ob = {};
+            ob.ctl = reinterpret_cast<uint32_t*>(b); ob.cls = b + oCls; ob.listA = reinterpret_cast<uint32_t*>(b + oA); ob.listB = reinterpret_cast<uint32_t*>(b + oB);
+            CUDA_TRY(cudaMemsetAsync(b, 0, oA, ctx->stream));
+            k_order_from_history<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(sc.cost_out, sc.cost_sum, tm.items, ob, 0.01f * float(ctx->ls_hist_a), 0.01f * float(ctx->ls_hist_b));
+            CUDA_TRY(cudaGetLastError());
+            sc.ctl = ob.ctl; sc.listA = ob.listA; sc.listB = ob.listB; sc.cls = ob.cls;
+            ++launches;
+        }
+        CUDA_TRY(cudaMemsetAsync(sc.cost_sum, 0, 8, ctx->stream));
+        static_assert(sizeof(TileMap) <= sizeof(ctx->hist_tm), "history key");
+        std::memcpy(ctx->hist_tm, &tm, sizeof(tm)); ctx->hist_grid = grid; ctx->hist_spp = opts->spp; ctx->hist_valid = 1;
+    }
     if (order) {
         auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
         const size_t n = nStrips, oCost = 256, oDone = oCost + up(4 * n), oCls = oDone + up(4 * n), oA = oCls + up(n), oB = oA + up(4 * n), totalB = oB + up(4 * n);
@@ -1052,7 +1086,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     if (!ctx || !key) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     const std::string k(key);
     struct { const char* name; uint32_t* field; } table[] = {
-        {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order},
+        {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order}, {"ls_history", &ctx->ls_history}, {"ls_hist_a", &ctx->ls_hist_a}, {"ls_hist_b", &ctx->ls_hist_b},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
         {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };

@@ -17,6 +17,8 @@ struct vdbrt_ctx {
     void* aux = nullptr;   size_t aux_cap = 0;  // device staging for per-pixel records
     void* io = nullptr;    size_t io_cap = 0;   // device staging for ray batches / scratch films
     void* lng = nullptr;   size_t lng_cap = 0;  // long-ray records, segment lists and their control block (vdbrt_kernels.cuh)
+    void* hist = nullptr;  size_t hist_cap = 0; // per-tile costs of the last level-set frame (Sched::cost_out) and what they belong to
+    uint32_t hist_tm[16] = {}; const void* hist_grid = nullptr; uint32_t hist_spp = 0, hist_valid = 0, ls_history = 1, ls_hist_a = 250, ls_hist_b = 105;
     void* ord = nullptr;   size_t ord_cap = 0;  // tile-ordering buffers of the level-set render (OrderBufs, vdbrt_kernels.cuh)
     uint32_t ls_strip = 1, ls_strip_ratio = 4, ls_refill = 32, ls_eager = 0, ls_affine = 0, ls_order = 0, ls_probe_cap = 128, ls_probe_b = 64;   // Sched (vdbrt_kernels.cuh)
     void* fog = nullptr;   size_t fog_cap = 0;  // records / ray table of the fog wavefront (vdbrt_fog.cuh)

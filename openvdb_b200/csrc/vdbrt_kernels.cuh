@@ -101,6 +101,8 @@ struct Sched {
     uint32_t affine;             // strips per chunk (0: one global queue)
     unsigned int* smq;           // affine: one counter per SM (zeroed before the launch), nq of them
     uint32_t nq;
+    uint32_t* cost_out;          // history: warp iterations each tile of THIS frame took (null: not recorded); cost_sum: their sum
+    unsigned long long* cost_sum;
     unsigned long long* warp_exit;   // diagnostics (VDBRT_DEBUG_EXIT): %globaltimer of every warp when it leaves the kernel, [0] = launch start
     const uint32_t* ctl;         // [0], [1]: strips in the two heavy lists (null: no ordering)
     const uint32_t* listA; const uint32_t* listB;
@@ -266,6 +268,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
     unsigned sNext = 0, sEnd = 0;                       // pixel slots of the warp's strip that are still to be handed out (warp-uniform)
+    unsigned curStrip = 0xffffffffu, tileIt = 0;        // history: the strip the warp is working on and the iterations it has spent on it
 
     long long tileStart = 0; unsigned long long tileIters = 0, tileActive = 0;
     // warp iterations spent on the current tile, and what a tile may spend: at least lb.budget, and lb.factor percent of
@@ -296,6 +299,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             const bool sus = rayOn && walk.pendInterp != 3 && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
             const unsigned m = __ballot_sync(0xffffffffu, sus);
             if (lb.tail) spent = 0;                                 // the lanes that stay are looked at again `tail` iterations later
+            if (m && sc.cost_out && lane == 0 && curStrip != 0xffffffffu) { sc.cost_out[curStrip] = 0x7fffffffu; curStrip = 0xffffffffu; }
             if (m) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&lb.ctl->nLong, (unsigned)__popc(m));
@@ -318,6 +322,10 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 if (now - tileStart > 1500000) { atomicAdd(counters + 14, 1ull); atomicAdd(counters + 15, tileActive * 100ull / (tileIters ? tileIters : 1)); }
             }
             tileStart = now; tileIters = 0; tileActive = 0;
+        }
+        if (sc.cost_out && idle == 0xffffffffu && sNext >= sEnd && curStrip != 0xffffffffu) {
+            if (lane == 0) { sc.cost_out[curStrip] = tileIt; atomicAdd(sc.cost_sum, (unsigned long long)tileIt); }
+            curStrip = 0xffffffffu;
         }
         if (idle == 0xffffffffu && drained && sNext >= sEnd) break;
         if (LONG && idle == 0xffffffffu && !lb.tail) {
@@ -362,7 +370,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             }
             s = __shfl_sync(0xffffffffu, s, 0);
             if (s == 0xffffffffu) { drained = true; tail = true; }
-            else { sNext = s * stripSlots; sEnd = sNext + stripSlots < total ? sNext + stripSlots : total; }
+            else { sNext = s * stripSlots; sEnd = sNext + stripSlots < total ? sNext + stripSlots : total; curStrip = s; tileIt = 0; }
         }
         if (sNext < sEnd && (idle == 0xffffffffu || nIdle >= thr)) {
             if (!hasPix) {
@@ -394,6 +402,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         for (;;) {
             __syncwarp();
             if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
+            ++tileIt;
             if (LONG) {
                 ++spent;
                 if (lb.tail && !tail && (spent & 15u) == 0u) {
@@ -444,6 +453,21 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         sc.warp_exit[1 + blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)] = now;
     }
+}
+
+// Heavy tiles first from HISTORY: the warp iterations every tile took in the previous frame this context rendered with the same
+// film, tiles and partition (Sched::cost_out).  Tiles that took at least fA / fB times the mean go to list A / B; the render
+// kernel hands those out first (Sched::ctl, listA, listB, cls) and everything else in tile order.  Costs nothing but this launch
+// (one thread per tile) and needs no probe rays; the first frame of a sequence is rendered in plain tile order.
+__global__ void k_order_from_history(const uint32_t* __restrict__ cost, const unsigned long long* __restrict__ sum, uint32_t items, const __grid_constant__ OrderBufs ob,
+                                     float fA, float fB)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= items) return;
+    const float mean = float(*sum) / float(items);
+    const float c = float(cost[i]);
+    if (c >= fA * mean && c > 8.f) { ob.cls[i] = 1; ob.listA[atomicAdd(ob.ctl + 0, 1u)] = i; }
+    else if (c >= fB * mean && c > 8.f) { ob.cls[i] = 2; ob.listB[atomicAdd(ob.ctl + 1, 1u)] = i; }
 }
 
 // One ray per 8x4 tile (the pixel in its middle), traced for at most `cap` steps: the number of steps is the tile's cost

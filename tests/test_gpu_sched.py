@@ -12,12 +12,12 @@ from tests.test_gpu_parity import assert_records_equal
 
 pytestmark = pytest.mark.gpu
 
-DEFAULTS = dict(ls_strip=1, ls_strip_ratio=4, ls_refill=32, ls_eager=0, ls_affine=0, ls_order=0, ls_probe_cap=128, ls_probe_b=64)
+DEFAULTS = dict(ls_strip=1, ls_strip_ratio=4, ls_refill=32, ls_eager=0, ls_affine=0, ls_order=0, ls_probe_cap=128, ls_probe_b=64, ls_history=1, ls_hist_a=250, ls_hist_b=105)
 
 
 @pytest.fixture()
 def tuned(ctx):
-    ctx.set_tuning(ls_strip_ratio=0)      # small test frames keep the strip length they ask for
+    ctx.set_tuning(ls_strip_ratio=0, ls_history=0)      # small test frames keep the strip length they ask for; history has its own test
     yield ctx
     ctx.set_tuning(**DEFAULTS)
 
@@ -81,3 +81,49 @@ def test_ordering_puts_unfinished_probes_first(tuned, oracle, torus_small):
         ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(order=True))
         assert np.array_equal(film, ofilm), (cap, b)
     g.free()
+
+
+def test_history_ordering_over_a_sequence_of_frames(tuned, oracle, torus_small, sphere100):
+    """heavy tiles first from the previous frame's tile costs (k_order_from_history): frame 1 is rendered in tile order and records the
+    costs, frames 2.. are ordered -- all are the oracle's frame, for any thresholds, with the long-ray rounds on and off, for several
+    samples per pixel; a different partition, film size or grid starts a new history"""
+    ctx = tuned
+    g = ctx.upload(torus_small.buf)
+    g2 = ctx.upload(sphere100.buf)
+    W, H = 403, 237
+    cam = api.vdb_render_camera(W, H, (0.0, 90.0, 255.0), (0, 0, 0))
+    cam2 = api.vdb_render_camera(W, H, (0.0, 0.0, 300.0), (0, 0, 0))
+    sh = api.make_shader(abi.SHADER_DIFFUSE)
+    want = refapi.new_film(W, H)
+    oracle.render_levelset(torus_small.oracle_handle, cam, sh, want, threads=4)
+    want2 = refapi.new_film(W, H)
+    oracle.render_levelset(sphere100.oracle_handle, cam2, sh, want2, threads=4)
+    for a, b in ((250, 105), (100, 50), (1, 1), (100000, 100000)):
+        ctx.set_tuning(ls_history=1, ls_hist_a=a, ls_hist_b=b)
+        for rounds in (False, True):
+            launches = []
+            for frame in range(4):
+                film = refapi.new_film(W, H)
+                ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(rounds=rounds))
+                launches.append(ctx.last_kernel_ms()[1])
+                assert np.array_equal(film, want), (a, b, rounds, frame)
+            assert launches[1] == launches[0] + 1 or launches[0] == launches[1]      # the ordering launch appears from frame 2 on
+            # another grid with the same film: new history, then back
+            film = refapi.new_film(W, H)
+            ctx.render_levelset(g2, cam2, sh, film, opts=ctx.ls_opts(rounds=rounds))
+            assert np.array_equal(film, want2)
+            # three ranks into one film, twice (each call changes the partition -> each starts a new history)
+            film = refapi.new_film(W, H)
+            for rep in range(2):
+                for r in range(3):
+                    ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(rounds=rounds, part=api.partition(r, 3, 32, 16)))
+            assert np.array_equal(film, want)
+    # several samples per pixel
+    want5 = refapi.new_film(W, H)
+    oracle.render_levelset(torus_small.oracle_handle, cam, sh, want5, spp=3, jitter=api.jitter_table(1), threads=4)
+    ctx.set_tuning(ls_history=1, ls_hist_a=250, ls_hist_b=105)
+    for frame in range(3):
+        film = refapi.new_film(W, H)
+        ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(spp=3, seed=1))
+        assert np.array_equal(film, want5)
+    g.free(); g2.free()
