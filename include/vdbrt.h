@@ -107,7 +107,9 @@ typedef struct vdbrt_ls_opts {
     double   jitter[16];      /* mRand[16] from math::Rand01<double>(seed); see vdbrt_jitter_table              */
     vdbrt_partition part;
     uint32_t flags;           /* VDBRT_LS_*                                                                     */
-    uint32_t reserved;
+    uint32_t iterations;      /* LinearSearchImpl<GridT, Iterations>: secant refinements of the hit time after the
+                               * zero crossing (tools/RayIntersector.h:630-636).  0 = what tools::rayTrace and
+                               * vdb_render use (LevelSetRayIntersector's default search)                         */
 } vdbrt_ls_opts;
 #define VDBRT_LS_UNIFORM_BG 1u /* every film pixel currently equals bg_rgba: skip the host->device film copy    */
 #define VDBRT_ASYNC         2u /* device-memory film only: enqueue on the context's stream and return at once   */
@@ -277,6 +279,10 @@ int  vdbrt_render_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
 /* LevelSetRayIntersector::intersectsWS / intersectsIS on a batch of arbitrary rays (RayIntersector.h:119-240).  */
 int  vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n,
                               uint32_t space, float iso, vdbrt_hit* hits, uint32_t memspace);
+/* the same with LinearSearchImpl<GridT, Iterations> as the search (LevelSetRayIntersector<GridT, LinearSearchImpl<GridT, N>>,
+ * tools/RayIntersector.h:79-82,630-636): `iterations` secant refinements of every hit time                        */
+int  vdbrt_intersect_levelset_ex(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n,
+                                 uint32_t space, float iso, uint32_t iterations, vdbrt_hit* hits, uint32_t memspace);
 /* VolumeRayIntersector::setIndexRay/setWorldRay + hits() (RayIntersector.h:368-432): spans[i*max_spans*2 ..],
  * counts[i] = number of spans (may exceed max_spans: only the first max_spans are stored); counts[i] = -1 when the
  * ray misses the bbox.                                                                                          */

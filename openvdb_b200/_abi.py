@@ -44,7 +44,7 @@ class Partition(C.Structure):
 
 class LsOpts(C.Structure):
     _fields_ = [("iso", C.c_float), ("spp", C.c_uint32), ("jitter", C.c_double * 16), ("part", Partition),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("iterations", C.c_uint32)]
 
 
 class VolOpts(C.Structure):

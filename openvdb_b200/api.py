@@ -24,7 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
-    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over", "vdbrt_set_tuning",
+    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over", "vdbrt_set_tuning", "vdbrt_intersect_levelset_ex",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
     L.vdbrt_render_levelset.argtypes = [vp, vp, P(abi.Camera), P(abi.Shader), P(abi.LsOpts), P(abi.Film), P(abi.Aux)]
     L.vdbrt_render_volume.argtypes = [vp, vp, P(abi.Camera), P(abi.VolOpts), P(abi.Film)]
     L.vdbrt_intersect_levelset.argtypes = [vp, vp, vp, u64, u32, C.c_float, vp, u32]
+    L.vdbrt_intersect_levelset_ex.argtypes = [vp, vp, vp, u64, u32, C.c_float, u32, vp, u32]
     L.vdbrt_volume_spans.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp, u32]
     L.vdbrt_count_levelset.argtypes = [vp, vp, P(abi.Camera), P(abi.LsOpts), P(abi.Counters)]
     L.vdbrt_count_volume.argtypes = [vp, vp, P(abi.Camera), P(abi.VolOpts), P(abi.Counters)]
@@ -284,9 +285,10 @@ class Context:
         f.bg_rgba = (C.c_float * 4)(*bg)
         return f
 
-    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None, rounds=None, order=None):
+    def ls_opts(self, iso=0.0, spp=1, seed=0, part=None, uniform_bg=False, jitter=None, rounds=None, order=None, iterations=0):
         o = abi.LsOpts()
         o.iso, o.spp = iso, spp
+        o.iterations = iterations       # LinearSearchImpl<GridT, Iterations>
         if spp > 1:
             j = jitter_table(seed) if jitter is None else jitter
             o.jitter = (C.c_double * 16)(*j)
@@ -316,10 +318,10 @@ class Context:
         f = self._film_pod(film, width, height, memspace)
         _check(self.L.vdbrt_render_volume(self.handle, grid.handle, C.byref(cam), C.byref(opts), C.byref(f)))
 
-    def intersect(self, grid, rays, space=abi.SPACE_WORLD, iso=0.0):
+    def intersect(self, grid, rays, space=abi.SPACE_WORLD, iso=0.0, iterations=0):
         n = len(rays)
         hits = (abi.Hit * n)()
-        _check(self.L.vdbrt_intersect_levelset(self.handle, grid.handle, rays, n, space, iso, hits, abi.MEM_HOST))
+        _check(self.L.vdbrt_intersect_levelset_ex(self.handle, grid.handle, rays, n, space, iso, iterations, hits, abi.MEM_HOST))
         return hits
 
     def volume_spans(self, grid, rays, space=abi.SPACE_WORLD, max_spans=16):

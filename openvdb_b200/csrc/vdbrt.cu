@@ -221,6 +221,7 @@ void ls_params(const vdbrt_grid* grid, const vdbrt_ls_opts* o, const vdbrt_film*
     p.vmin = o->iso - float(2 * grid->info.voxel_size[0]);      // LinearSearchImpl ctor (tools/RayIntersector.h:530-531)
     p.vmax = o->iso + float(2 * grid->info.voxel_size[0]);
     p.sub = o->spp - 1;
+    p.iters = o->iterations; p.pad = 0;
     p.frac = 1.0f / (1.0f + float(p.sub));                       // tools/RayTracer.h:905
     p.uniform_bg = (o->flags & VDBRT_LS_UNIFORM_BG) ? 1u : 0u;
     for (int i = 0; i < 4; ++i) p.bg[i] = film ? film->bg_rgba[i] : 0.f;
@@ -617,7 +618,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     // (ctx->ls_tail, vdbrt_kernels.cuh) unless VDBRT_LS_TAIL=0 selects round 1's per-tile budget.
     const double tilesPerWarp = double(tm.items) / (double(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32));
     const bool automatic = tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
-    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
+    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && opts->iterations == 0 && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
     LongBufs lb = {};
     lb.budget = 0xffffffffu;
     if (rounds) {
@@ -693,8 +694,11 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     }
     // LONG = true compiles the suspension of over-budget rays into the kernel; MULTI = more than one sample per pixel
     const bool multi = opts->spp > 1;
+    const bool refine = opts->iterations > 0;      // LinearSearchImpl<.., Iterations > 0>: its own instantiations (never with the rounds)
     void (*kern)(DevGrid, DevCamera, DevShader, LsParams, TileMap, float4*, AuxOut, unsigned int*, unsigned long long*, LongBufs, Sched) =
         dCounters ? k_render_levelset<false, true, false, true>
+        : refine ? (wantAux ? (multi ? k_render_levelset<true, false, false, true, true> : k_render_levelset<true, false, false, false, true>)
+                            : (multi ? k_render_levelset<false, false, false, true, true> : k_render_levelset<false, false, false, false, true>))
         : wantAux ? (rounds ? k_render_levelset<true, false, true, false> : multi ? k_render_levelset<true, false, false, true> : k_render_levelset<true, false, false, false>)
                   : (rounds ? k_render_levelset<false, false, true, false> : multi ? k_render_levelset<false, false, false, true> : k_render_levelset<false, false, false, false>);
     const int blocks = persistentGrid(ctx, (const void*)kern, nStrips);
@@ -1021,6 +1025,12 @@ int vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camer
 int vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso,
                              vdbrt_hit* hits, uint32_t memspace)
 {
+    return vdbrt_intersect_levelset_ex(ctx, grid, rays, n, space, iso, 0u, hits, memspace);
+}
+
+int vdbrt_intersect_levelset_ex(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso,
+                                uint32_t iterations, vdbrt_hit* hits, uint32_t memspace)
+{
     if (!ctx || !grid || (n && (!rays || !hits))) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (int rc = checkLevelSet(grid, iso)) return rc;
     if (n == 0) return VDBRT_OK;
@@ -1040,7 +1050,7 @@ int vdbrt_intersect_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt
     const float vmin = iso - float(2 * grid->info.voxel_size[0]), vmax = iso + float(2 * grid->info.voxel_size[0]);
     const unsigned blocks = unsigned(std::min<uint64_t>((n + kBlockThreads - 1) / kBlockThreads, uint64_t(ctx->sm_count) * 16));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    k_intersect_levelset<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH);
+    k_intersect_levelset<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH, int(iterations));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->last_launches = 1;

@@ -491,10 +491,13 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 // time range in w.c0/w.c1, the cursor pointing at it) and the DDA steps on as if the leaf had returned "no hit": the
 // leaf visits of one ray are independent of each other (the tester is re-initialised per leaf, DDA.h:172-173), so they
 // can be marched by other threads (vdbrt_kernels.cuh, long-ray rounds).
-template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false>
+// REFINE = true: LinearSearchImpl<GridT, Iterations> with Iterations = `iters` > 0 -- after the zero crossing the hit time is refined by
+// `iters` secant steps, each one stencil evaluation at the current estimate (tools/RayIntersector.h:630-636).  A separate instantiation:
+// the default kernels (Iterations = 0, what vdb_render and tools::rayTrace use) do not carry the loop.
+template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false, bool REFINE = false>
 __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
                                          TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
-                                         LsWalk& w, LsHit& out, Counters& c)
+                                         LsWalk& w, LsHit& out, Counters& c, int iters = 0)
 {
     Dda& cur = w.cur;
     int status = kWalkContinue;
@@ -546,22 +549,39 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
     if (active && w.pendInterp && runC) {
         const int purpose = w.pendInterp;
-        const double tq = w.tq;
+        double tq = w.tq;
         w.pendInterp = 0;
-        const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
-        st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
-        if (purpose == 3) {
-            // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
-            out.px = px; out.py = py; out.pz = pz;
-            st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
-            status = kWalkHit;
-        } else {
-            const float V1 = st.interpolation(px, py, pz) - iso;
-            if (purpose == 2 && w.V0 * V1 <= 0.0f) {                         // math::ZeroCrossing (math/Math.h:821)
-                out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
-                out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
-                w.pendInterp = 3; w.tq = out.time; w.pendStep = false;
-            } else { w.T0 = tq; w.V0 = V1; }                                  // init: mT[0],mV[0]; no crossing: slide
+        // refinement state (REFINE, purpose 3): mT[0..1], mV[0..1] of the crossing -- mT[1] is the voxel's exit time again (the DDA has
+        // not moved), mV[1] was left in out.gx by the iteration that found the crossing
+        double rT0 = w.T0, rT1 = REFINE ? cur.next() : 0.0;
+        float rV0 = w.V0, rV1 = REFINE ? out.gx : 0.f;
+#pragma unroll 1
+        for (int n = 0;; ++n) {
+            const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
+            st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
+            if (purpose == 3) {
+                if (REFINE && n < iters) {
+                    // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
+                    const float V = st.interpolation(px, py, pz) - iso;
+                    if (rV0 * V <= 0.0f) { rV1 = V; rT1 = tq; } else { rV0 = V; rT0 = tq; }
+                    tq = rT0 + (rT1 - rT0) * rV0 / (rV0 - rV1);
+                    continue;
+                }
+                // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
+                if (REFINE) out.time = tq;
+                out.px = px; out.py = py; out.pz = pz;
+                st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
+                status = kWalkHit;
+            } else {
+                const float V1 = st.interpolation(px, py, pz) - iso;
+                if (purpose == 2 && w.V0 * V1 <= 0.0f) {                         // math::ZeroCrossing (math/Math.h:821)
+                    out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
+                    out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
+                    if (REFINE) out.gx = V1;
+                    w.pendInterp = 3; w.tq = out.time; w.pendStep = false;
+                } else { w.T0 = tq; w.V0 = V1; }                                  // init: mT[0],mV[0]; no crossing: slide
+            }
+            break;
         }
     }
     if (SYNC) __syncwarp();
@@ -586,12 +606,12 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
 // plain per-thread form (arbitrary-ray batches)
 template<bool COUNT, int THREADS>
 __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm, TreeCursor& acc, Stencil& st, Ray& ray,
-                                                  float iso, float vmin, float vmax, LsHit& out, Counters& c)
+                                                  float iso, float vmin, float vmax, LsHit& out, Counters& c, int iters = 0)
 {
     LsWalk w; w.begin(ray);
 #pragma unroll 1
     for (;;) {
-        const int r = lsAdvance<COUNT, false, THREADS>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c);
+        const int r = lsAdvance<COUNT, false, THREADS, false, true>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
         if (r != kWalkContinue) return r == kWalkHit;
     }
 }

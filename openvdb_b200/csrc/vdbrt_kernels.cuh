@@ -55,7 +55,7 @@ __device__ __forceinline__ bool nextPixel(const TileMap& m, unsigned int* queue,
 }
 
 struct AuxOut { uint8_t* hit; int32_t* ijk; double* t_index; double* t_world; double* xyz; double* nml; };
-struct LsParams { float iso, vmin, vmax, frac; uint32_t sub; uint32_t uniform_bg; float bg[4]; double jitter[16];
+struct LsParams { float iso, vmin, vmax, frac; uint32_t sub; uint32_t uniform_bg; float bg[4]; uint32_t iters, pad; double jitter[16];
                   const float4* bg_film; };   // where a miss reads its old pixel from (the film itself, or the device copy of a host film)
 
 __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long long* out)
@@ -226,7 +226,8 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
 }
 
 // MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
-template<bool AUX, bool COUNT, bool LONG, bool MULTI>
+// REFINE = true: LinearSearchImpl's secant refinements (p.iters > 0), see lsAdvance.
+template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
@@ -413,7 +414,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
-                const int r = lsAdvance<COUNT, true, kBlockThreads>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c);
+                const int r = lsAdvance<COUNT, true, kBlockThreads, false, REFINE>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
                 if (rayOn) status = r;
             }
             __syncwarp();
@@ -728,7 +729,7 @@ struct RayIn { double eye[3], dir[3], t0, t1; };
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays, unsigned long long n, uint32_t space,
-                     float iso, float vmin, float vmax, HitOut* __restrict__ hits)
+                     float iso, float vmin, float vmax, HitOut* __restrict__ hits, int iters)
 {
     __shared__ RootSmem root;
     __shared__ WalkSmem<kBlockThreads> wsm;
@@ -745,7 +746,7 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
         if (space == 0) worldToIndex(g, ray);
         HitOut o = {};
         LsHit h;
-        if (clipRay(ray, g, 0) && intersectLevelSet<false, kBlockThreads>(g, root, wsm, acc, st, ray, iso, vmin, vmax, h, c)) {
+        if (clipRay(ray, g, 0) && intersectLevelSet<false, kBlockThreads>(g, root, wsm, acc, st, ray, iso, vmin, vmax, h, c, iters)) {
             double x = h.px, y = h.py, z = h.pz;
             double nx = h.gx, ny = h.gy, nz = h.gz;
             vnormalize(nx, ny, nz);

@@ -623,6 +623,86 @@ int vdbref_intersect_levelset(void* h, const vdbrt_ray* rays, uint64_t n, uint32
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// The stock intersector with LinearSearchImpl<FloatGrid, ITER, double> as its search (tools/RayIntersector.h:79-82,630-636): what the
+// reference's own accuracy sweep instantiates (unittest/TestLevelSetRayIntersector.cc:236-309 uses <FloatGrid, 2>).  No first-hit voxel
+// here (the stock search does not expose it): ijk stays zero.
+} // extern "C"
+template<int ITER>
+static void intersectIter(FloatGrid& grid, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso, vdbrt_hit* hits)
+{
+    using SearchT = tools::LinearSearchImpl<FloatGrid, ITER, double>;
+    tools::LevelSetRayIntersector<FloatGrid, SearchT> inter(grid, iso);
+    for (uint64_t k = 0; k < n; ++k) {
+        const vdbrt_ray& r = rays[k];
+        const math::Ray<double> ray(Vec3R(r.eye[0], r.eye[1], r.eye[2]), Vec3R(r.dir[0], r.dir[1], r.dir[2]), r.t0, r.t1);
+        vdbrt_hit& o = hits[k];
+        std::memset(&o, 0, sizeof(o));
+        Vec3R w(0.0), nm(0.0), xi(0.0);
+        double tw = 0.0, ti = 0.0;
+        bool hit;
+        if (space == VDBRT_SPACE_WORLD) {
+            hit = inter.intersectsWS(ray, w, nm, tw);                                   // world position, normal, world time
+            if (hit) inter.intersectsIS(ray.worldToIndex(grid), xi, ti);                // the same hit in index space (setWorldRay does this map)
+        } else {
+            hit = inter.intersectsIS(ray, xi, ti);                                      // index-space rays: index position and time only
+        }
+        o.hit = hit;
+        if (hit) {
+            o.t_index = ti; o.t_world = tw;
+            for (int a = 0; a < 3; ++a) { o.xyz_index[a] = xi[a]; o.xyz_world[a] = w[a]; o.nml[a] = nm[a]; }
+        }
+    }
+}
+
+extern "C" int vdbref_intersect_levelset_iter(void* h, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso, uint32_t iterations, vdbrt_hit* hits)
+{
+    try {
+        auto* g = static_cast<RefGrid*>(h);
+        switch (iterations) {
+        case 0: intersectIter<0>(*g->grid, rays, n, space, iso, hits); break;
+        case 1: intersectIter<1>(*g->grid, rays, n, space, iso, hits); break;
+        case 2: intersectIter<2>(*g->grid, rays, n, space, iso, hits); break;
+        case 3: intersectIter<3>(*g->grid, rays, n, space, iso, hits); break;
+        default: g_err = "iterations must be 0..3 in the reference driver"; return 1;
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// tools::rayTrace(grid, intersector, shader, camera, ...) with that intersector (tools/RayTracer.h:56-64)
+template<int ITER>
+static double renderIter(FloatGrid& grid, const vdbref_camera_desc* d, const vdbrt_shader* sh, float iso, uint32_t spp, unsigned seed, int threaded, float* filmRGBA)
+{
+    using SearchT = tools::LinearSearchImpl<FloatGrid, ITER, double>;
+    using InterT = tools::LevelSetRayIntersector<FloatGrid, SearchT>;
+    tools::Film film(d->width, d->height);
+    std::memcpy(reinterpret_cast<void*>(const_cast<tools::Film::RGBA*>(film.pixels())), filmRGBA, size_t(d->width) * d->height * 16);
+    auto cam = makeCamera(film, *d);
+    auto shader = makeShader(*sh);
+    const auto t0 = std::chrono::steady_clock::now();
+    InterT inter(grid, iso);
+    tools::rayTrace<FloatGrid, InterT>(grid, inter, *shader, *cam, spp, seed, threaded != 0);
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::memcpy(filmRGBA, film.pixels(), size_t(d->width) * d->height * 16);
+    return s;
+}
+
+extern "C" double vdbref_render_levelset_iter(void* h, const vdbref_camera_desc* d, const vdbrt_shader* sh, float iso, uint32_t spp, unsigned seed,
+                                   int threaded, uint32_t iterations, float* filmRGBA)
+{
+    try {
+        auto* g = static_cast<RefGrid*>(h);
+        switch (iterations) {
+        case 0: return renderIter<0>(*g->grid, d, sh, iso, spp, seed, threaded, filmRGBA);
+        case 1: return renderIter<1>(*g->grid, d, sh, iso, spp, seed, threaded, filmRGBA);
+        case 2: return renderIter<2>(*g->grid, d, sh, iso, spp, seed, threaded, filmRGBA);
+        case 3: return renderIter<3>(*g->grid, d, sh, iso, spp, seed, threaded, filmRGBA);
+        default: g_err = "iterations must be 0..3 in the reference driver"; return -1.0;
+        }
+    } catch (std::exception& e) { g_err = e.what(); return -1.0; }
+}
+
+extern "C" {
 // VolumeRayIntersector::setWorldRay/setIndexRay + hits()
 int vdbref_volume_spans(void* h, const vdbrt_ray* rays, uint64_t n, uint32_t space, uint32_t maxSpans, double* spans, int32_t* counts)
 {

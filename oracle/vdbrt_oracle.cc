@@ -344,6 +344,7 @@ struct Counters { uint64_t probes[3] = {0, 0, 0}, voxel = 0, refills = 0, pSampl
 struct Tester {
     const oracle_grid& g; Access acc; BoxStencil st; Ray ray;
     double time = 0; float V[2]; double T[2]; float iso, vmin, vmax; Coord hitIjk{0, 0, 0};
+    int iterations = 0;                                         // LinearSearchImpl<GridT, Iterations, RealT>
     Counters* ctr;
     Tester(const oracle_grid& grid, float isoValue, Counters* c) : g(grid), acc(grid), iso(isoValue), ctr(c) {
         vmin = isoValue - float(2 * grid.voxelSize[0]);         // RayIntersector.h:530-531 (as float)
@@ -367,6 +368,12 @@ struct Tester {
             T[1] = t; V[1] = float(interpValue(t));
             if (V[0] * V[1] <= 0.0f) {                                                                  // math::ZeroCrossing (Math.h:821)
                 time = T[0] + (T[1] - T[0]) * V[0] / (V[0] - V[1]);                                    // interpTime :646-650
+                for (int n = 0; n < iterations; ++n) {                                                  // secant refinements :630-636
+                    const float W = float(interpValue(time));
+                    const int m = (V[0] * W <= 0.0f) ? 1 : 0;
+                    V[m] = W; T[m] = time;
+                    time = T[0] + (T[1] - T[0]) * V[0] / (V[0] - V[1]);
+                }
                 hitIjk = ijk;
                 return true;
             }
@@ -751,6 +758,7 @@ int oracle_render_levelset_color(const oracle_grid* g, const oracle_color* color
     parallelRows(H, threads, [&](uint32_t j0, uint32_t j1, int tid) {
         Counters& c = counters[tid];
         Tester tester(*g, opts->iso, ctr ? &c : nullptr);
+        tester.iterations = int(opts->iterations);
         for (uint32_t j = j0; j < j1; ++j) for (uint32_t i = 0; i < W; ++i) {
             if (!ownsPixel(opts->part, i, j, W)) continue;
             const size_t p = size_t(j) * W + i;
@@ -790,8 +798,14 @@ int oracle_render_levelset_color(const oracle_grid* g, const oracle_color* color
 
 int oracle_intersect_levelset(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso, vdbrt_hit* hits)
 {
+    return oracle_intersect_levelset_iter(g, rays, n, space, iso, 0u, hits);
+}
+
+int oracle_intersect_levelset_iter(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso, uint32_t iterations, vdbrt_hit* hits)
+{
     if (int e = checkLevelSet(g, iso)) return e;
     Tester tester(*g, iso, nullptr);
+    tester.iterations = int(iterations);
     for (uint64_t k = 0; k < n; ++k) {
         const Ray ray = makeRay(rays[k]);
         vdbrt_hit& o = hits[k];

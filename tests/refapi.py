@@ -87,11 +87,11 @@ def make_rays(eyes, dirs, t0=1e-9, t1=np.finfo(np.float64).max):
     eyes = np.atleast_2d(np.asarray(eyes, np.float64))
     dirs = np.atleast_2d(np.asarray(dirs, np.float64))
     n = len(eyes)
+    flat = np.empty((n, 8), np.float64)                      # vdbrt_ray: eye[3], dir[3], t0, t1
+    flat[:, 0:3] = eyes; flat[:, 3:6] = dirs
+    flat[:, 6] = np.broadcast_to(np.asarray(t0, np.float64), (n,)); flat[:, 7] = np.broadcast_to(np.asarray(t1, np.float64), (n,))
     r = rays_array(n)
-    t0 = np.broadcast_to(np.asarray(t0, np.float64), (n,))
-    t1 = np.broadcast_to(np.asarray(t1, np.float64), (n,))
-    for k in range(n):
-        r[k].eye = abi.vec3(eyes[k]); r[k].dir = abi.vec3(dirs[k]); r[k].t0 = t0[k]; r[k].t1 = t1[k]
+    C.memmove(r, flat.ctypes.data, flat.nbytes)
     return r
 
 
@@ -292,6 +292,24 @@ class Ref:
             raise RuntimeError(self.err())
         return hits_to_dict(h, n)
 
+    def intersect_iter(self, g, rays, iterations, space=abi.SPACE_WORLD, iso=0.0):
+        """the stock intersector with LinearSearchImpl<FloatGrid, iterations> (0..3); no first-hit voxel; index-space rays: index outputs only"""
+        n = len(rays)
+        h = (abi.Hit * n)()
+        self.L.vdbref_intersect_levelset_iter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p]
+        if self.L.vdbref_intersect_levelset_iter(g, rays, n, space, iso, iterations, h):
+            raise RuntimeError(self.err())
+        return hits_to_dict(h, n)
+
+    def render_levelset_iter(self, g, desc, sh, film, iterations, iso=0.0, spp=1, seed=0, threaded=False):
+        self.L.vdbref_render_levelset_iter.restype = C.c_double
+        self.L.vdbref_render_levelset_iter.argtypes = [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(abi.Shader), C.c_float, C.c_uint32, C.c_uint, C.c_int,
+                                                       C.c_uint32, C.c_void_p]
+        t = self.L.vdbref_render_levelset_iter(g, C.byref(desc), C.byref(sh), iso, spp, seed, int(threaded), iterations, film.ctypes.data)
+        if t < 0:
+            raise RuntimeError(self.err())
+        return t
+
     def volume_spans(self, g, rays, space=abi.SPACE_WORLD, max_spans=16):
         n = len(rays)
         spans = np.zeros((n, max_spans, 2), np.float64); counts = np.zeros(n, np.int32)
@@ -390,10 +408,11 @@ class Oracle:
         return h.value
 
     def render_levelset(self, g, cam, sh, film, iso=0.0, spp=1, jitter=None, part=None, aux=False, counters=False,
-                        threads=1, color=None):
+                        threads=1, color=None, iterations=0):
         H, W = film.shape[:2]
         o = abi.LsOpts()
         o.iso, o.spp = iso, spp
+        o.iterations = iterations
         if jitter is not None:
             o.jitter = (C.c_double * 16)(*jitter)
         if part is not None:
@@ -422,10 +441,11 @@ class Oracle:
         assert top.shape == bottom.shape and top.dtype == np.float32 and bottom.dtype == np.float32
         self.check(self.L.oracle_film_over(top.ctypes.data, np.ascontiguousarray(bottom).ctypes.data, top.shape[0] * top.shape[1]))
 
-    def intersect(self, g, rays, space=abi.SPACE_WORLD, iso=0.0):
+    def intersect(self, g, rays, space=abi.SPACE_WORLD, iso=0.0, iterations=0):
         n = len(rays)
         h = (abi.Hit * n)()
-        self.check(self.L.oracle_intersect_levelset(g, rays, n, space, iso, h))
+        self.L.oracle_intersect_levelset_iter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p]
+        self.check(self.L.oracle_intersect_levelset_iter(g, rays, n, space, iso, iterations, h))
         return hits_to_dict(h, n)
 
     def volume_spans(self, g, rays, space=abi.SPACE_WORLD, max_spans=16):

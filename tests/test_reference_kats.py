@@ -5,7 +5,7 @@ openvdb/openvdb/unittest/*.cc; grids are made with the reference's generators (o
 import numpy as np
 import pytest
 
-from openvdb_b200 import _abi as abi
+from openvdb_b200 import api, _abi as abi
 from tests import refapi
 
 DELTA = 1e-9          # math::Delta<double>::value()
@@ -158,3 +158,39 @@ def test_volume_bbox_hit_but_leaf_miss(ref, oracle):
     s1, c1 = ref.volume_spans(g, rays, space=abi.SPACE_INDEX)
     s2, c2 = oracle.volume_spans(og, rays, space=abi.SPACE_INDEX)
     assert c1[0] == 0 and c2[0] == 0
+
+
+@pytest.mark.parametrize("iterations", [0, 1, 2, 3])
+def test_levelset_search_iterations_match_the_reference(ref, oracle, iterations):
+    """LinearSearchImpl<FloatGrid, Iterations> (tools/RayIntersector.h:630-636): the port's secant refinements are bit-identical to the
+    stock LevelSetRayIntersector<FloatGrid, LinearSearchImpl<FloatGrid, N>> for world- and index-space rays, and so is a rendered frame"""
+    radius, dx = 2.0, 0.05
+    g, og, buf = sphere_case(ref, oracle, radius, (0.3, -0.2, 0.1), dx, 3.0)
+    rng = np.random.default_rng(iterations)
+    n = 4000
+    eyes = np.column_stack([rng.uniform(-2.5, 2.5, n), rng.uniform(-2.5, 2.5, n), np.full(n, 10.0)])
+    dirs = np.column_stack([rng.uniform(-0.05, 0.05, n), rng.uniform(-0.05, 0.05, n), np.full(n, -1.0)])
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    rays = refapi.make_rays(eyes, dirs)
+    a = ref.intersect_iter(g, rays, iterations)
+    b = oracle.intersect(og, rays, iterations=iterations)
+    assert a["hit"].sum() > 1000
+    for k in ("hit", "t_index", "t_world", "xyz_index", "xyz_world", "nml"):
+        assert np.array_equal(a[k], b[k]), k
+    if iterations:
+        assert not np.array_equal(b["t_index"], oracle.intersect(og, rays)["t_index"])       # the refinement does change hit times
+    # index-space rays (index outputs only on the reference side)
+    irays = refapi.make_rays(eyes / dx, dirs)
+    a = ref.intersect_iter(g, irays, iterations, space=abi.SPACE_INDEX)
+    b = oracle.intersect(og, irays, space=abi.SPACE_INDEX, iterations=iterations)
+    for k in ("hit", "t_index", "xyz_index"):
+        assert np.array_equal(a[k], b[k]), k
+    # a frame through tools::rayTrace(grid, intersector, ...)
+    W, H = 96, 64
+    d = refapi.camera_desc(W, H, translation=(1.0, 2.0, 9.0), lookat=(0, 0, 0))
+    cam = api.vdb_render_camera(W, H, (1.0, 2.0, 9.0), (0, 0, 0))
+    f_ref, f_port = refapi.new_film(W, H), refapi.new_film(W, H)
+    ref.render_levelset_iter(g, d, refapi.shader(abi.SHADER_NORMAL), f_ref, iterations, spp=2, seed=4)
+    oracle.render_levelset(og, cam, api.make_shader(abi.SHADER_NORMAL), f_port, spp=2, jitter=api.jitter_table(4), iterations=iterations)
+    assert (f_ref[..., :3].sum(axis=2) > 0).sum() > 500
+    assert np.array_equal(f_ref, f_port)
