@@ -288,6 +288,12 @@ int  vdbrt_intersect_levelset_ex(vdbrt_ctx* ctx, const vdbrt_grid* grid, const v
  * ray misses the bbox.                                                                                          */
 int  vdbrt_volume_spans(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* rays, uint64_t n, uint32_t space,
                         uint32_t max_spans, double* spans, int32_t* counts, uint32_t memspace);
+/* VolumeRayIntersector::setIndexRay / setWorldRay (tools/RayIntersector.h:368-390) on the host: the ray mapped to index space
+ * (space == VDBRT_SPACE_WORLD; math/Ray.h:150-159) and clipped against the node-granular bbox with its max padded by one
+ * (:318, math/Ray.h:233-267).  *hit = 0 when it misses; `scale` receives the grid's index->world scale.  The same arithmetic,
+ * in the same order, as the device kernels use: the clipped ray can be handed to vdbrt_volume_spans with VDBRT_SPACE_INDEX.  */
+int  vdbrt_volume_clip(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* ray, uint32_t space, vdbrt_ray* clipped,
+                       int* hit, double scale[3]);
 
 /* ---- measurement ------------------------------------------------------------------------------------------- */
 /* counters of the most recent render with counting enabled (a separate instrumented launch, never timed)       */

@@ -15,7 +15,9 @@
 
 #include <cmath>
 #include <cstring>
+#include <iostream>
 #include <limits>
+#include <sstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -302,47 +304,151 @@ template<> class DiffuseShader<Vec3SGrid> : public BaseShader { public:
     DiffuseShader(const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_DIFFUSE, Film::RGBA(1.0f)) { mPod.color_grid = grid.get(); }
     BaseShader* copy() const override { return new DiffuseShader(*this); } };
 
-/// tools::LevelSetRayIntersector (RayIntersector.h:79-246): validates at construction, batches of rays on the device
-template<typename GridT = FloatGrid>
+/// math::Ray<double> as the facade's callers hand it over: eye, direction, times (math/Ray.h:57-63: t0 = 1e-9, t1 = max by default)
+struct Ray : vdbrt_ray
+{
+    Ray(const Vec3R& e = Vec3R(0.0), const Vec3R& d = Vec3R(1.0, 0.0, 0.0), double t0_ = 1e-9, double t1_ = std::numeric_limits<double>::max())
+    { eye[0] = e.x; eye[1] = e.y; eye[2] = e.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; t0 = t0_; t1 = t1_; }
+    explicit Ray(const vdbrt_ray& r) : vdbrt_ray(r) {}
+    Vec3R operator()(double t) const { return Vec3R(eye[0] + dir[0] * t, eye[1] + dir[1] * t, eye[2] + dir[2] * t); }      // math/Ray.h:109
+};
+
+/// tools::LinearSearchImpl<GridT, Iterations> (RayIntersector.h:514-668) as a tag: the facade's intersector only needs the iteration count
+template<typename GridT, int Iterations = 0>
+struct LinearSearchImpl { static constexpr uint32_t iterations = Iterations; };
+
+/// tools::LevelSetRayIntersector (RayIntersector.h:79-246): validates at construction; the twelve intersectsIS / intersectsWS overloads
+/// of the reference for one ray (one device call each), and the same for batches of rays (the shape to use on a GPU)
+template<typename GridT = FloatGrid, typename SearchImplT = LinearSearchImpl<GridT, 0>>
 class LevelSetRayIntersector
 {
 public:
+    using RayType = Ray;
     LevelSetRayIntersector(const GridT& grid, float isoValue = 0.0f) : mGrid(&grid), mIso(isoValue)
     {
         // same construction-time checks as the reference, evaluated by the library (empty batch = validation only)
         check(vdbrt_intersect_levelset(grid.context().get(), grid.get(), nullptr, 0, VDBRT_SPACE_WORLD, isoValue, nullptr, VDBRT_MEM_HOST));
     }
     const float& getIsoValue() const { return mIso; }
+    static constexpr uint32_t iterations() { return SearchImplT::iterations; }
     /// intersectsWS / intersectsIS for n rays at once; hits[i].hit == 0 leaves the record zeroed (outputs untouched)
-    void intersectsWS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const
-    { check(vdbrt_intersect_levelset(mGrid->context().get(), mGrid->get(), rays, n, VDBRT_SPACE_WORLD, mIso, hits, VDBRT_MEM_HOST)); }
-    void intersectsIS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const
-    { check(vdbrt_intersect_levelset(mGrid->context().get(), mGrid->get(), rays, n, VDBRT_SPACE_INDEX, mIso, hits, VDBRT_MEM_HOST)); }
-    bool intersectsWS(const vdbrt_ray& ray, Vec3R& world, Vec3R& normal, double& wTime) const
+    void intersectsWS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const { batch(rays, n, VDBRT_SPACE_WORLD, hits); }
+    void intersectsIS(const vdbrt_ray* rays, size_t n, vdbrt_hit* hits) const { batch(rays, n, VDBRT_SPACE_INDEX, hits); }
+    // ---- index-space rays (RayIntersector.h:119-160); outputs are untouched on a miss, as in the reference
+    bool intersectsIS(const vdbrt_ray& iRay) const { vdbrt_hit h; batch(&iRay, 1, VDBRT_SPACE_INDEX, &h); return h.hit != 0; }
+    bool intersectsIS(const vdbrt_ray& iRay, double& iTime) const
+    { vdbrt_hit h; batch(&iRay, 1, VDBRT_SPACE_INDEX, &h); if (!h.hit) return false; iTime = h.t_index; return true; }
+    bool intersectsIS(const vdbrt_ray& iRay, Vec3R& xyz) const
+    { vdbrt_hit h; batch(&iRay, 1, VDBRT_SPACE_INDEX, &h); if (!h.hit) return false; xyz = vec(h.xyz_index); return true; }
+    bool intersectsIS(const vdbrt_ray& iRay, Vec3R& xyz, double& iTime) const
+    { vdbrt_hit h; batch(&iRay, 1, VDBRT_SPACE_INDEX, &h); if (!h.hit) return false; xyz = vec(h.xyz_index); iTime = h.t_index; return true; }
+    // ---- world-space rays (RayIntersector.h:162-240)
+    bool intersectsWS(const vdbrt_ray& wRay) const { vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h); return h.hit != 0; }
+    bool intersectsWS(const vdbrt_ray& wRay, double& wTime) const
+    { vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h); if (!h.hit) return false; wTime = h.t_world; return true; }
+    bool intersectsWS(const vdbrt_ray& wRay, Vec3R& world) const
+    { vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h); if (!h.hit) return false; world = vec(h.xyz_world); return true; }
+    bool intersectsWS(const vdbrt_ray& wRay, Vec3R& world, double& wTime) const
+    { vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h); if (!h.hit) return false; world = vec(h.xyz_world); wTime = h.t_world; return true; }
+    bool intersectsWS(const vdbrt_ray& wRay, Vec3R& world, Vec3R& normal) const
+    { vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h); if (!h.hit) return false; world = vec(h.xyz_world); normal = vec(h.nml); return true; }
+    bool intersectsWS(const vdbrt_ray& wRay, Vec3R& world, Vec3R& normal, double& wTime) const
     {
-        vdbrt_hit h; intersectsWS(&ray, 1, &h);
+        vdbrt_hit h; batch(&wRay, 1, VDBRT_SPACE_WORLD, &h);
         if (!h.hit) return false;
-        world = Vec3R(h.xyz_world[0], h.xyz_world[1], h.xyz_world[2]); normal = Vec3R(h.nml[0], h.nml[1], h.nml[2]); wTime = h.t_world;
+        world = vec(h.xyz_world); normal = vec(h.nml); wTime = h.t_world;
         return true;
     }
     const GridT& grid() const { return *mGrid; }
 private:
+    static Vec3R vec(const double* v) { return Vec3R(v[0], v[1], v[2]); }
+    void batch(const vdbrt_ray* rays, size_t n, uint32_t space, vdbrt_hit* hits) const
+    { check(vdbrt_intersect_levelset_ex(mGrid->context().get(), mGrid->get(), rays, n, space, mIso, SearchImplT::iterations, hits, VDBRT_MEM_HOST)); }
     const GridT* mGrid; float mIso;
 };
 
-/// tools::VolumeRayIntersector (RayIntersector.h:277-485): hits() for batches of rays
+/// tools::VolumeRayIntersector (RayIntersector.h:277-485): setIndexRay / setWorldRay + march() / hits() for one ray (each march is one
+/// device call), hits() for batches of rays.  The bbox is the node-granular one, max padded by one (RayIntersector.h:318).
 template<typename GridT = FloatGrid>
 class VolumeRayIntersector
 {
 public:
+    struct TimeSpan {                                                   // math::Ray::TimeSpan (math/Ray.h:38-55)
+        double t0, t1;
+        TimeSpan(double a = -1.0, double b = -1.0) : t0(a), t1(b) {}
+        bool valid(double eps = 1e-9) const { return (t1 - t0) > eps; }
+        void get(double& a, double& b) const { a = t0; b = t1; }
+    };
     explicit VolumeRayIntersector(const GridT& grid) : mGrid(&grid)
     { check(vdbrt_volume_spans(grid.context().get(), grid.get(), nullptr, 0, VDBRT_SPACE_WORLD, 0, nullptr, nullptr, VDBRT_MEM_HOST)); }
     /// spans[i*maxSpans + k] = {t0,t1}; counts[i] = -1 when the ray misses the bbox
     void hits(const vdbrt_ray* rays, size_t n, bool indexSpace, uint32_t maxSpans, double* spans, int32_t* counts) const
     { check(vdbrt_volume_spans(mGrid->context().get(), mGrid->get(), rays, n, indexSpace ? VDBRT_SPACE_INDEX : VDBRT_SPACE_WORLD, maxSpans, spans, counts, VDBRT_MEM_HOST)); }
+    /// setIndexRay (:368-374): false if the ray misses the bbox; the ray is clipped to it and mTmax = its exit time
+    bool setIndexRay(const vdbrt_ray& iRay) { return this->start(iRay, VDBRT_SPACE_INDEX); }
+    /// setWorldRay (:387-390) = setIndexRay(wRay.worldToIndex(grid))
+    bool setWorldRay(const vdbrt_ray& wRay) { return this->start(wRay, VDBRT_SPACE_WORLD); }
+    /// march (:392-397): the next span of active values along the current ray (index-space times); invalid when there is none.
+    /// Afterwards the ray starts Delta<double> behind the span, exactly as the reference re-arms mRay.
+    TimeSpan march()
+    {
+        TimeSpan t(-1.0, -1.0);
+        if (!mArmed || !((mRay.t1 - mRay.t0) > 1e-5f)) return t;       // VolumeHDDA::march: if (ray.valid()) (Ray::valid, eps = Delta<float>)
+        double span[2] = {-1.0, -1.0}; int32_t count = 0;
+        check(vdbrt_volume_spans(mGrid->context().get(), mGrid->get(), &mRay, 1, VDBRT_SPACE_INDEX, 1, span, &count, VDBRT_MEM_HOST));
+        if (count > 0) { t.t0 = span[0]; t.t1 = span[1]; }
+        if (t.t1 > 0) { mRay.t0 = t.t1 + 1e-9; mRay.t1 = mTmax; }      // mRay.setTimes(t.t1 + Delta<RealType>, mTmax)
+        else mArmed = false;
+        return t;
+    }
+    bool march(double& t0, double& t1) { const TimeSpan t = this->march(); t.get(t0, t1); return t.valid(); }
+    /// hits (:428-432): all spans of the current ray
+    template<typename ListType> void hits(ListType& list)
+    {
+        list.clear();
+        if (!mArmed) return;
+        uint32_t cap = 16;
+        for (;;) {
+            std::vector<double> spans(2 * size_t(cap)); int32_t count = 0;
+            check(vdbrt_volume_spans(mGrid->context().get(), mGrid->get(), &mRay, 1, VDBRT_SPACE_INDEX, cap, spans.data(), &count, VDBRT_MEM_HOST));
+            if (count > int32_t(cap)) { cap = uint32_t(count); continue; }
+            for (int32_t k = 0; k < count; ++k) list.push_back(TimeSpan(spans[2 * k], spans[2 * k + 1]));
+            return;
+        }
+    }
+    Vec3R getIndexPos(double time) const { return Vec3R(mRay.eye[0] + mRay.dir[0] * time, mRay.eye[1] + mRay.dir[1] * time, mRay.eye[2] + mRay.dir[2] * time); }
+    /// getWorldPos (:440) = grid.indexToWorld(ray(time)): ScaleMap / ScaleTranslateMap, one multiply (and one add) per component
+    Vec3R getWorldPos(double time) const
+    {
+        const Vec3R p = getIndexPos(time); const vdbrt_grid_info i = mGrid->info();
+        const bool tr = i.translation[0] != 0 || i.translation[1] != 0 || i.translation[2] != 0;
+        return tr ? Vec3R(p.x * mScale[0] + i.translation[0], p.y * mScale[1] + i.translation[1], p.z * mScale[2] + i.translation[2])
+                  : Vec3R(p.x * mScale[0], p.y * mScale[1], p.z * mScale[2]);
+    }
+    /// print (:459-469): "BBox: [min] -> [max]" (levels 2 and 3 of the reference add statistics of its bool tree, which does not exist here)
+    void print(std::ostream& os = std::cout, int verboseLevel = 1) const
+    {
+        if (verboseLevel > 0) {
+            const vdbrt_grid_info i = mGrid->info();
+            os << "BBox: [" << i.node_bbox[0] << ", " << i.node_bbox[1] << ", " << i.node_bbox[2] << "] -> [" << i.node_bbox[3] + 1 << ", "
+               << i.node_bbox[4] + 1 << ", " << i.node_bbox[5] + 1 << "]" << std::endl;
+        }
+    }
     const GridT& grid() const { return *mGrid; }
 private:
+    bool start(const vdbrt_ray& ray, uint32_t space)
+    {
+        // the library clips the ray and returns its clipped index-space form: one span query with room for none
+        mArmed = false;
+        vdbrt_ray clipped;
+        int hit = 0;
+        check(vdbrt_volume_clip(mGrid->context().get(), mGrid->get(), &ray, space, &clipped, &hit, mScale));
+        if (!hit) return false;
+        mRay = clipped; mTmax = clipped.t1; mArmed = true;
+        return true;
+    }
     const GridT* mGrid;
+    vdbrt_ray mRay{}; double mTmax = 0.0; bool mArmed = false; double mScale[3] = {1.0, 1.0, 1.0};
 };
 
 /// tools::LevelSetRayTracer (RayTracer.h:72-140,789-918)
@@ -421,6 +527,17 @@ public:
     void setAbsorption(double x, double y, double z) { mOpts.absorption[0] = x; mOpts.absorption[1] = y; mOpts.absorption[2] = z; }
     void setLightGain(double g) { mOpts.light_gain = g; }
     void setCutOff(double c) { mOpts.cutoff = c; }
+    /// print (RayTracer.h:958-973)
+    void print(std::ostream& os = std::cout, int verboseLevel = 1)
+    {
+        auto v3 = [](const double* v) { std::ostringstream b; b << "[" << v[0] << ", " << v[1] << ", " << v[2] << "]"; return b.str(); };
+        if (verboseLevel > 0) {
+            os << "\nPrimary step: " << mOpts.primary_step << "\nShadow step: " << mOpts.shadow_step << "\nCutoff: " << mOpts.cutoff
+               << "\nLightGain: " << mOpts.light_gain << "\nLightDir: " << v3(mOpts.light_dir) << "\nLightColor: " << v3(mOpts.light_color)
+               << "\nAbsorption: " << v3(mOpts.absorption) << "\nScattering: " << v3(mOpts.scattering) << std::endl;
+        }
+        mInter.print(os, verboseLevel);
+    }
     void render(bool /*threaded*/ = true) const
     {
         Film& film = mCamera->film();

@@ -24,7 +24,7 @@ SYMBOLS = [
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
     "vdbrt_build_levelset_spheres", "vdbrt_build_fog_from_levelset", "vdbrt_random_spheres",
     "vdbrt_device_alloc", "vdbrt_device_free", "vdbrt_ipc_export", "vdbrt_ipc_import", "vdbrt_ipc_close", "vdbrt_memcpy",
-    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over", "vdbrt_set_tuning", "vdbrt_intersect_levelset_ex",
+    "vdbrt_upload_color_grid", "vdbrt_nvdb_list", "vdbrt_nvdb_read", "vdbrt_nvdb_read_typed", "vdbrt_nvdb_write", "vdbrt_buffer_free", "vdbrt_film_save_ppm", "vdbrt_film_over", "vdbrt_set_tuning", "vdbrt_intersect_levelset_ex", "vdbrt_volume_clip",
 ]
 
 

@@ -1112,6 +1112,37 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     return setError(VDBRT_ERR_INVALID_ARG, "unknown tuning key: " + k);
 }
 
+int vdbrt_volume_clip(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* ray, uint32_t space, vdbrt_ray* clipped, int* hit, double scale[3])
+{
+    if (!ctx || !grid || !ray || !clipped || !hit) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (int rc = checkVolume(grid)) return rc;
+    const DevGrid& g = grid->dgrid;
+    // worldToIndex and clipRay of vdbrt_device.cuh restated for the host (this file is compiled without contraction; / and sqrt are IEEE)
+    double ex = ray->eye[0], ey = ray->eye[1], ez = ray->eye[2], dx = ray->dir[0], dy = ray->dir[1], dz = ray->dir[2], t0 = ray->t0, t1 = ray->t1;
+    if (space == VDBRT_SPACE_WORLD) {
+        if (g.has_translation) { ex = (ex - g.trans[0]) * g.inv[0]; ey = (ey - g.trans[1]) * g.inv[1]; ez = (ez - g.trans[2]) * g.inv[2]; }
+        else { ex = ex * g.inv[0]; ey = ey * g.inv[1]; ez = ez * g.inv[2]; }
+        const double jx = dx * g.inv[0], jy = dy * g.inv[1], jz = dz * g.inv[2];
+        const double len = std::sqrt(jx * jx + jy * jy + jz * jz);
+        dx = jx / len; dy = jy / len; dz = jz / len;
+        t0 = len * t0; t1 = len * t1;
+    }
+    const double e[3] = {ex, ey, ez}, inv[3] = {1 / dx, 1 / dy, 1 / dz};
+    double a0 = t0, a1 = t1;
+    *hit = 1;
+    for (int k = 0; k < 3 && *hit; ++k) {
+        double a = (g.bbox_min[k] - e[k]) * inv[k], b = ((g.bbox_max[k] + 1) - e[k]) * inv[k];
+        if (a > b) { const double t = a; a = b; b = t; }
+        if (a > a0) a0 = a;
+        if (b < a1) a1 = b;
+        if (a0 > a1) *hit = 0;
+    }
+    clipped->eye[0] = ex; clipped->eye[1] = ey; clipped->eye[2] = ez; clipped->dir[0] = dx; clipped->dir[1] = dy; clipped->dir[2] = dz;
+    clipped->t0 = *hit ? a0 : t0; clipped->t1 = *hit ? a1 : t1;
+    if (scale) for (int k = 0; k < 3; ++k) scale[k] = g.scale[k];
+    return VDBRT_OK;
+}
+
 int vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches)
 {
     if (!ctx) return setError(VDBRT_ERR_INVALID_ARG, "null context");

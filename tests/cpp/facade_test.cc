@@ -6,6 +6,8 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <sstream>
+#include <vector>
 
 using namespace vdbrt;
 
@@ -69,6 +71,53 @@ int main(int argc, char** argv)
     for (size_t j = 0; j < vfilm.height(); ++j) for (size_t i = 0; i < vfilm.width(); ++i) alpha += vfilm.pixel(i, j).a;
     std::printf("fog: sum(alpha) = %.3f\n", alpha);
     EXPECT(alpha > 100.0);
+    // ---- the twelve single-ray overloads of LevelSetRayIntersector (RayIntersector.h:119-240); a miss leaves the outputs alone
+    {
+        tools::Ray wr(Vec3R(0.0, 0.0, 300.0), Vec3R(0.0, 0.0, -1.0));
+        Vec3R w(7.0), n(7.0), w2(7.0); double tw = -1.0, tw2 = -1.0;
+        EXPECT(inter.intersectsWS(wr));
+        EXPECT(inter.intersectsWS(wr, tw) && std::fabs(tw - 200.0) < 1e-3);
+        EXPECT(inter.intersectsWS(wr, w) && std::fabs(w.z - 100.0) < 1e-3);
+        EXPECT(inter.intersectsWS(wr, w2, tw2) && w2.z == w.z && tw2 == tw);
+        EXPECT(inter.intersectsWS(wr, w2, n) && n.z > 0.999);
+        Vec3R xi(7.0); double ti = -1.0;
+        EXPECT(inter.intersectsIS(wr));                                    // voxel size 1: the same ray in index space
+        EXPECT(inter.intersectsIS(wr, ti) && ti == tw);
+        EXPECT(inter.intersectsIS(wr, xi) && xi.z == w.z);
+        EXPECT(inter.intersectsIS(wr, xi, ti));
+        tools::Ray miss(Vec3R(0.0, 500.0, 300.0), Vec3R(0.0, 0.0, -1.0));
+        Vec3R keep(1.0, 2.0, 3.0); double tkeep = 42.0;
+        EXPECT(!inter.intersectsWS(miss, keep, tkeep) && keep.x == 1.0 && keep.z == 3.0 && tkeep == 42.0);
+        EXPECT(!inter.intersectsIS(miss, keep, tkeep) && keep.y == 2.0 && tkeep == 42.0);
+        // LinearSearchImpl<GridT, 2>: two secant refinements move the hit closer to the analytic sphere
+        tools::LevelSetRayIntersector<FloatGrid, tools::LinearSearchImpl<FloatGrid, 2>> inter2(*grid);
+        tools::Ray slanted(Vec3R(30.0, 20.0, 300.0), Vec3R(0.0, 0.0, -1.0));
+        Vec3R p0, p2;
+        EXPECT(inter.intersectsWS(slanted, p0) && inter2.intersectsWS(slanted, p2));
+        const double e0 = std::fabs(std::sqrt(p0.x * p0.x + p0.y * p0.y + p0.z * p0.z) - 100.0), e2 = std::fabs(std::sqrt(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) - 100.0);
+        std::printf("|x| - r: %.3g with Iterations = 0, %.3g with Iterations = 2\n", e0, e2);
+        EXPECT(e2 <= e0 && e2 < 1e-2);
+    }
+    // ---- VolumeRayIntersector: setWorldRay + march() until the spans are used up == hits() (RayIntersector.h:368-432)
+    {
+        tools::Ray wr(Vec3R(0.0, 0.0, 300.0), Vec3R(0.0, 0.0, -1.0));
+        EXPECT(vinter.setWorldRay(wr));
+        std::vector<tools::VolumeRayIntersector<FloatGrid>::TimeSpan> list;
+        vinter.hits(list);
+        EXPECT(list.size() == 1 && std::fabs(list[0].t0 - 196.0) < 8.5 && std::fabs(list[0].t1 - 404.0) < 8.5);
+        double t0 = 0.0, t1 = 0.0; size_t n = 0;
+        EXPECT(vinter.setWorldRay(wr));
+        while (vinter.march(t0, t1)) { EXPECT(n < list.size() && t0 == list[n].t0 && t1 == list[n].t1); ++n; }
+        EXPECT(n == list.size());
+        EXPECT(std::fabs(vinter.getWorldPos(list[0].t0).z - (300.0 - list[0].t0)) < 1e-9);
+        tools::Ray miss(Vec3R(0.0, 500.0, 300.0), Vec3R(0.0, 0.0, -1.0));
+        EXPECT(!vinter.setWorldRay(miss) && !vinter.march(t0, t1));
+        std::ostringstream os;
+        renderer.print(os, 1);
+        EXPECT(os.str().find("Primary step: 0.5") != std::string::npos && os.str().find("LightDir: [0.707107, 0.707107, 0]") != std::string::npos);
+        EXPECT(os.str().find("BBox: [-104, -104, -104] -> [104, 104, 104]") != std::string::npos);
+        std::printf("%s", os.str().c_str());
+    }
     if (argc > 2) film.savePPM(argv[2]);
     std::printf("facade ok\n");
     return 0;
