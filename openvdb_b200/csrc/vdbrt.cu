@@ -101,17 +101,20 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
 
     double m[9];
     for (int i = 0; i < 9; ++i) m[i] = rd<double>(head + OFF_MATD + 8 * i);
-    if (m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0)
-        return setError(VDBRT_ERR_UNSUPPORTED, "only scale(+translate) index->world maps are supported");
     DevGrid& d = grid->dgrid;
     std::memset(&d, 0, sizeof(d));
+    // off-diagonal terms: an AffineMap (rotation / shear).  The kernels then evaluate NanoVDB's stored matrix and inverse -- the tolerance
+    // path of SURVEY 0.7 (the reference multiplies through its own 4x4s); scale(+translate) maps keep the bit-exact single multiplies.
+    d.general = (m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0) ? 1u : 0u;
+    for (int i = 0; i < 9; ++i) { d.mat[i] = m[i]; d.imat[i] = rd<double>(head + OFF_MATD + 72 + 8 * i); }
     d.base = grid->dev; d.root_off = rootOff; d.tiles = grid->dev + rootOff + kRootTiles;
     d.table_size = info.root_tiles; d.background = info.background; d.grid_class = info.grid_class;
     for (int a = 0; a < 3; ++a) {
         d.scale[a] = m[4 * a];
         d.inv[a] = 1.0 / d.scale[a];                    // ScaleMap: mScaleValuesInverse = 1.0 / mScaleValues (math/Maps.h:674)
         d.trans[a] = rd<double>(head + OFF_VECD + 8 * a);
-        info.voxel_size[a] = std::fabs(d.scale[a]);     // mVoxelSize = |scale| (math/Maps.h:667)
+        // mVoxelSize = |scale| (math/Maps.h:667); AffineMap: length of the image of the unit vector (:630-633)
+        info.voxel_size[a] = d.general ? std::sqrt(m[a] * m[a] + m[3 + a] * m[3 + a] + m[6 + a] * m[6 + a]) : std::fabs(d.scale[a]);
         info.translation[a] = d.trans[a];
     }
     d.has_translation = (d.trans[0] != 0 || d.trans[1] != 0 || d.trans[2] != 0) ? 1u : 0u;
@@ -866,7 +869,11 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     VolParams p; vol_params(opts, p);
     {
         const DevGrid& g = grid->dgrid;
-        const double jx = p.light[0] * g.inv[0], jy = p.light[1] * g.inv[1], jz = p.light[2] * g.inv[2];
+        double jx = p.light[0], jy = p.light[1], jz = p.light[2];
+        if (g.general) {
+            const double a = jx * g.imat[0] + jy * g.imat[1] + jz * g.imat[2], b = jx * g.imat[3] + jy * g.imat[4] + jz * g.imat[5], c = jx * g.imat[6] + jy * g.imat[7] + jz * g.imat[8];
+            jx = a; jy = b; jz = c;
+        } else { jx *= g.inv[0]; jy *= g.inv[1]; jz *= g.inv[2]; }
         const double len = std::sqrt(jx * jx + jy * jy + jz * jz);
         const double dx = jx / len, dy = jy / len, dz = jz / len;
         p.sb[0] = dx; p.sb[1] = dy; p.sb[2] = dz; p.sb[3] = 1 / dx; p.sb[4] = 1 / dy; p.sb[5] = 1 / dz; p.sb[6] = len * 1e-9; p.sb[7] = len * DBL_MAX;
@@ -1120,9 +1127,16 @@ int vdbrt_volume_clip(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ray* r
     // worldToIndex and clipRay of vdbrt_device.cuh restated for the host (this file is compiled without contraction; / and sqrt are IEEE)
     double ex = ray->eye[0], ey = ray->eye[1], ez = ray->eye[2], dx = ray->dir[0], dy = ray->dir[1], dz = ray->dir[2], t0 = ray->t0, t1 = ray->t1;
     if (space == VDBRT_SPACE_WORLD) {
-        if (g.has_translation) { ex = (ex - g.trans[0]) * g.inv[0]; ey = (ey - g.trans[1]) * g.inv[1]; ez = (ez - g.trans[2]) * g.inv[2]; }
-        else { ex = ex * g.inv[0]; ey = ey * g.inv[1]; ez = ez * g.inv[2]; }
-        const double jx = dx * g.inv[0], jy = dy * g.inv[1], jz = dz * g.inv[2];
+        double jx, jy, jz;
+        if (g.general) {
+            const double qx = ex - g.trans[0], qy = ey - g.trans[1], qz = ez - g.trans[2];
+            ex = qx * g.imat[0] + qy * g.imat[1] + qz * g.imat[2]; ey = qx * g.imat[3] + qy * g.imat[4] + qz * g.imat[5]; ez = qx * g.imat[6] + qy * g.imat[7] + qz * g.imat[8];
+            jx = dx * g.imat[0] + dy * g.imat[1] + dz * g.imat[2]; jy = dx * g.imat[3] + dy * g.imat[4] + dz * g.imat[5]; jz = dx * g.imat[6] + dy * g.imat[7] + dz * g.imat[8];
+        } else {
+            if (g.has_translation) { ex = (ex - g.trans[0]) * g.inv[0]; ey = (ey - g.trans[1]) * g.inv[1]; ez = (ez - g.trans[2]) * g.inv[2]; }
+            else { ex = ex * g.inv[0]; ey = ey * g.inv[1]; ez = ez * g.inv[2]; }
+            jx = dx * g.inv[0]; jy = dy * g.inv[1]; jz = dz * g.inv[2];
+        }
         const double len = std::sqrt(jx * jx + jy * jy + jz * jz);
         dx = jx / len; dy = jy / len; dz = jz / len;
         t0 = len * t0; t1 = len * t1;

@@ -42,6 +42,10 @@ struct DevGrid {
     uint32_t has_translation;
     uint32_t grid_class;
     double   voxel_size0;
+    // a map with off-diagonal terms (rotation / shear: OpenVDB's AffineMap, math/Maps.h:411-445): nanovdb::Map::mMatD / mInvMatD as
+    // stored (NanoVDB.h:1418-1554).  TOLERANCE path: bit-exactness is only claimed for scale(+translate) maps.
+    uint32_t general, pad0;
+    double   mat[9], imat[9];
     // Halo blocks (null = none): for leaf i, the 9x9x9 values getValue() returns at origin + (0..8)^3 -- the
     // leaf's own 512 values plus the +x/+y/+z faces, edges and corner taken from whatever lies there (neighbour leaf, tile,
     // background) -- at halo + 736 * i floats, index 81 x + 9 y + z.  Built once when the grid is registered (k_build_halo).
@@ -301,27 +305,54 @@ __device__ __forceinline__ bool clipRay(Ray& r, const DevGrid& g, int pad)
     return true;
 }
 
+// nanovdb::Map::applyMap / applyInverseMap / applyJacobian / applyInverseJacobian / applyIJT (NanoVDB.h:1473-1548) for general maps
+__device__ __forceinline__ void mul3(const double* m, double& x, double& y, double& z)
+{
+    const double a = x * m[0] + y * m[1] + z * m[2], b = x * m[3] + y * m[4] + z * m[5], c = x * m[6] + y * m[7] + z * m[8];
+    x = a; y = b; z = c;
+}
+__device__ __forceinline__ void mul3T(const double* m, double& x, double& y, double& z)
+{
+    const double a = x * m[0] + y * m[3] + z * m[6], b = x * m[1] + y * m[4] + z * m[7], c = x * m[2] + y * m[5] + z * m[8];
+    x = a; y = b; z = c;
+}
+
 // Ray::worldToIndex == applyInverseMap (math/Ray.h:150-159)
 __device__ __forceinline__ void worldToIndex(const DevGrid& g, Ray& r)
 {
-    double x, y, z;
-    if (g.has_translation) { x = (r.ex - g.trans[0]) * g.inv[0]; y = (r.ey - g.trans[1]) * g.inv[1]; z = (r.ez - g.trans[2]) * g.inv[2]; }
-    else { x = r.ex * g.inv[0]; y = r.ey * g.inv[1]; z = r.ez * g.inv[2]; }
+    double x, y, z, jx, jy, jz;
+    if (g.general) {
+        x = r.ex - g.trans[0]; y = r.ey - g.trans[1]; z = r.ez - g.trans[2];
+        mul3(g.imat, x, y, z);
+        jx = r.dx; jy = r.dy; jz = r.dz;
+        mul3(g.imat, jx, jy, jz);
+    } else {
+        if (g.has_translation) { x = (r.ex - g.trans[0]) * g.inv[0]; y = (r.ey - g.trans[1]) * g.inv[1]; z = (r.ez - g.trans[2]) * g.inv[2]; }
+        else { x = r.ex * g.inv[0]; y = r.ey * g.inv[1]; z = r.ez * g.inv[2]; }
+        jx = r.dx * g.inv[0]; jy = r.dy * g.inv[1]; jz = r.dz * g.inv[2];
+    }
     r.ex = x; r.ey = y; r.ez = z;
-    const double jx = r.dx * g.inv[0], jy = r.dy * g.inv[1], jz = r.dz * g.inv[2];
     const double len = vlength(jx, jy, jz);
     r.setDir(jx / len, jy / len, jz / len);
     r.t0 = len * r.t0; r.t1 = len * r.t1;
 }
 __device__ __forceinline__ void indexToWorldPos(const DevGrid& g, double& x, double& y, double& z)
 {
+    if (g.general) { mul3(g.mat, x, y, z); x += g.trans[0]; y += g.trans[1]; z += g.trans[2]; return; }
     if (g.has_translation) { x = x * g.scale[0] + g.trans[0]; y = y * g.scale[1] + g.trans[1]; z = z * g.scale[2] + g.trans[2]; }
     else { x = x * g.scale[0]; y = y * g.scale[1]; z = z * g.scale[2]; }
 }
 __device__ __forceinline__ void worldToIndexPos(const DevGrid& g, double& x, double& y, double& z)
 {
+    if (g.general) { x -= g.trans[0]; y -= g.trans[1]; z -= g.trans[2]; mul3(g.imat, x, y, z); return; }
     if (g.has_translation) { x = (x - g.trans[0]) * g.inv[0]; y = (y - g.trans[1]) * g.inv[1]; z = (z - g.trans[2]) * g.inv[2]; }
     else { x = x * g.inv[0]; y = y * g.inv[1]; z = z * g.inv[2]; }
+}
+// |J dir|: the factor between index-space and world-space times (getWorldTime, tools/RayIntersector.h:588-591)
+__device__ __forceinline__ double jacobianLength(const DevGrid& g, double dx, double dy, double dz)
+{
+    if (g.general) { mul3(g.mat, dx, dy, dz); return vlength(dx, dy, dz); }
+    return vlength(dx * g.scale[0], dy * g.scale[1], dz * g.scale[2]);
 }
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // std::min
@@ -424,6 +455,7 @@ struct Stencil {
         A = D1 - D0;
         B = D3 - D2;
         const float y_ = A + (B - A) * u;
+        if (g.general) { double a = x_, b = y_, c = z_; mul3T(g.imat, a, b, c); gx = float(a); gy = float(b); gz = float(c); return; }   // applyIJT
         gx = float(double(x_) * g.inv[0]); gy = float(double(y_) * g.inv[1]); gz = float(double(z_) * g.inv[2]);
     }
 };

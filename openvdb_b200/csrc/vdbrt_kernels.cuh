@@ -135,7 +135,7 @@ __device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh
         if (aux.ijk) { aux.ijk[3 * pix] = h.ix; aux.ijk[3 * pix + 1] = h.iy; aux.ijk[3 * pix + 2] = h.iz; }
         if (aux.t_index) aux.t_index[pix] = h.time;
         // getWorldTime (:588-591): mTime * |J dir|
-        if (aux.t_world) aux.t_world[pix] = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
+        if (aux.t_world) aux.t_world[pix] = h.time * jacobianLength(g, ray.dx, ray.dy, ray.dz);
         if (aux.xyz) { aux.xyz[3 * pix] = x; aux.xyz[3 * pix + 1] = y; aux.xyz[3 * pix + 2] = z; }
         if (aux.nml) { aux.nml[3 * pix] = nx; aux.nml[3 * pix + 1] = ny; aux.nml[3 * pix + 2] = nz; }
     }
@@ -752,7 +752,7 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
             vnormalize(nx, ny, nz);
             o.hit = 1; o.ijk[0] = h.ix; o.ijk[1] = h.iy; o.ijk[2] = h.iz;
             o.t_index = h.time;
-            o.t_world = h.time * vlength(ray.dx * g.scale[0], ray.dy * g.scale[1], ray.dz * g.scale[2]);
+            o.t_world = h.time * jacobianLength(g, ray.dx, ray.dy, ray.dz);
             o.xyz_index[0] = x; o.xyz_index[1] = y; o.xyz_index[2] = z;
             indexToWorldPos(g, x, y, z);
             o.xyz_world[0] = x; o.xyz_world[1] = y; o.xyz_world[2] = z;
@@ -837,7 +837,8 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
     if (threadIdx.x == 0) {
         // the shadow ray's direction is the same for every sample: sRay(Vec3R(0), mLightDir) through worldToIndex
         // (tools/RayTracer.h:1017,1039-1040; Ray ctor defaults t0 = 1e-9, t1 = max, math/Ray.h:57-63)
-        const double jx = p.light[0] * g.inv[0], jy = p.light[1] * g.inv[1], jz = p.light[2] * g.inv[2];
+        double jx = p.light[0], jy = p.light[1], jz = p.light[2];
+        if (g.general) mul3(g.imat, jx, jy, jz); else { jx *= g.inv[0]; jy *= g.inv[1]; jz *= g.inv[2]; }
         const double len = vlength(jx, jy, jz);
         const double dx = jx / len, dy = jy / len, dz = jz / len;
         sm.sbase[0] = dx; sm.sbase[1] = dy; sm.sbase[2] = dz;

@@ -94,6 +94,10 @@ struct oracle_grid {
     float background = 0.f;
     double scale[3], inv[3], trans[3], voxelSize[3];
     bool hasTranslation = false;
+    // a map with off-diagonal terms (rotation / shear: OpenVDB's AffineMap, math/Maps.h:411-445): NanoVDB's Map::mMatD / mInvMatD as
+    // stored (NanoVDB.h:1418-1554).  TOLERANCE path: the reference multiplies through 4x4 matrices in another order of operations.
+    bool general = false;
+    double mat[9], imat[9];
     CoordBBox nodeBBox;   // RootNode::evalActiveBoundingBox(bbox, /*visitVoxels=*/false)  (tree/RootNode.h:1532-1541)
     int32_t indexBBox[6];
 };
@@ -220,17 +224,22 @@ struct Ray {
 };
 Ray makeRay(const vdbrt_ray& r) { Ray o; o.eye = Vec3{r.eye[0], r.eye[1], r.eye[2]}; o.setDir(Vec3{r.dir[0], r.dir[1], r.dir[2]}); o.t0 = r.t0; o.t1 = r.t1; return o; }
 
-// ScaleMap / ScaleTranslateMap (math/Maps.h:726-771,1255-1290): one multiply per component with the stored inverse
+// ScaleMap / ScaleTranslateMap (math/Maps.h:726-771,1255-1290): one multiply per component with the stored inverse.
+// General maps: nanovdb::Map::applyMap / applyInverseMap / applyJacobian / applyInverseJacobian / applyIJT (NanoVDB.h:1473-1548) without fma.
+inline Vec3 mul3(const double* m, const Vec3& p) { return Vec3{p.x * m[0] + p.y * m[1] + p.z * m[2], p.x * m[3] + p.y * m[4] + p.z * m[5], p.x * m[6] + p.y * m[7] + p.z * m[8]}; }
+inline Vec3 mul3T(const double* m, const Vec3& p) { return Vec3{p.x * m[0] + p.y * m[3] + p.z * m[6], p.x * m[1] + p.y * m[4] + p.z * m[7], p.x * m[2] + p.y * m[5] + p.z * m[8]}; }
 inline Vec3 applyMap(const oracle_grid& g, const Vec3& p) {
+    if (g.general) { const Vec3 q = mul3(g.mat, p); return Vec3{q.x + g.trans[0], q.y + g.trans[1], q.z + g.trans[2]}; }
     if (g.hasTranslation) return Vec3{p.x * g.scale[0] + g.trans[0], p.y * g.scale[1] + g.trans[1], p.z * g.scale[2] + g.trans[2]};
     return Vec3{p.x * g.scale[0], p.y * g.scale[1], p.z * g.scale[2]};
 }
 inline Vec3 applyInverseMap(const oracle_grid& g, const Vec3& p) {
+    if (g.general) return mul3(g.imat, Vec3{p.x - g.trans[0], p.y - g.trans[1], p.z - g.trans[2]});
     if (g.hasTranslation) return Vec3{(p.x - g.trans[0]) * g.inv[0], (p.y - g.trans[1]) * g.inv[1], (p.z - g.trans[2]) * g.inv[2]};
     return Vec3{p.x * g.inv[0], p.y * g.inv[1], p.z * g.inv[2]};
 }
-inline Vec3 applyJacobian(const oracle_grid& g, const Vec3& d) { return Vec3{d.x * g.scale[0], d.y * g.scale[1], d.z * g.scale[2]}; }
-inline Vec3 applyInverseJacobian(const oracle_grid& g, const Vec3& d) { return Vec3{d.x * g.inv[0], d.y * g.inv[1], d.z * g.inv[2]}; }
+inline Vec3 applyJacobian(const oracle_grid& g, const Vec3& d) { return g.general ? mul3(g.mat, d) : Vec3{d.x * g.scale[0], d.y * g.scale[1], d.z * g.scale[2]}; }
+inline Vec3 applyInverseJacobian(const oracle_grid& g, const Vec3& d) { return g.general ? mul3(g.imat, d) : Vec3{d.x * g.inv[0], d.y * g.inv[1], d.z * g.inv[2]}; }
 
 // Ray::worldToIndex == applyInverseMap (Ray.h:150-159): new eye, renormalised direction, times scaled by |J^-1 dir|
 Ray worldToIndex(const oracle_grid& g, const Ray& w) {
@@ -332,6 +341,7 @@ struct BoxStencil {
         A = D[1] - D[0];
         B = D[3] - D[2];
         const float gy = A + (B - A) * u;
+        if (g.general) { const Vec3 t = mul3T(g.imat, Vec3{double(gx), double(gy), double(gz)}); out[0] = float(t.x); out[1] = float(t.y); out[2] = float(t.z); return; }   // applyIJT
         out[0] = float(double(gx) * g.inv[0]); out[1] = float(double(gy) * g.inv[1]); out[2] = float(double(gz) * g.inv[2]);
     }
 };
@@ -661,11 +671,13 @@ int oracle_grid_open(const void* buf, uint64_t bytes, oracle_grid** out)
     g->gridClass = rd<uint32_t>(b + OFF_CLASS);
     for (int i = 0; i < 6; ++i) g->indexBBox[i] = rd<int32_t>(g->root + 4 * i);
     double m[9]; for (int i = 0; i < 9; ++i) m[i] = rd<double>(b + OFF_MATD + 8 * i);
-    if (m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0) { delete g; return fail(VDBRT_ERR_UNSUPPORTED, "only scale(+translate) maps are supported"); }
+    g->general = m[1] != 0 || m[2] != 0 || m[3] != 0 || m[5] != 0 || m[6] != 0 || m[7] != 0;
+    for (int i = 0; i < 9; ++i) { g->mat[i] = m[i]; g->imat[i] = rd<double>(b + OFF_MATD + 72 + 8 * i); }
     for (int a = 0; a < 3; ++a) {
         g->scale[a] = m[4 * a]; g->inv[a] = 1.0 / g->scale[a];                  // ScaleMap ctor: mScaleValuesInverse = 1.0/scale (Maps.h:674)
         g->trans[a] = rd<double>(b + OFF_VECD + 8 * a);
-        g->voxelSize[a] = std::fabs(g->scale[a]);
+        // mVoxelSize: |scale|, or for an affine map the length of the image of the unit vector (Maps.h:630-633,667)
+        g->voxelSize[a] = g->general ? std::sqrt(m[a] * m[a] + m[3 + a] * m[3 + a] + m[6 + a] * m[6 + a]) : std::fabs(g->scale[a]);
     }
     g->hasTranslation = g->trans[0] != 0 || g->trans[1] != 0 || g->trans[2] != 0;
     g->nodeBBox = evalNodeBBox(*g);
@@ -700,16 +712,16 @@ static int checkLevelSet(const oracle_grid* g, float iso)
     // member mTester (LinearSearchImpl) is constructed first: empty / iso checks precede the intersector's own checks
     if (g->tableSize == 0) return fail(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids");
     if (iso <= -g->background || iso >= g->background) return fail(VDBRT_ERR_ISO_RANGE, "The iso-value must be inside the narrow-band!");
-    const double s0 = std::fabs(g->scale[0]);
-    if (std::fabs(s0 - std::fabs(g->scale[1])) > 5e-7 || std::fabs(s0 - std::fabs(g->scale[2])) > 5e-7)
+    const double s0 = g->voxelSize[0];
+    if (std::fabs(s0 - g->voxelSize[1]) > 5e-7 || std::fabs(s0 - g->voxelSize[2]) > 5e-7)
         return fail(VDBRT_ERR_NONUNIFORM, "LevelSetRayIntersector only supports uniform voxels!");
     if (g->gridClass != VDBRT_GRID_CLASS_LEVEL_SET) return fail(VDBRT_ERR_NOT_LEVELSET, "LevelSetRayIntersector only supports level sets!");
     return VDBRT_OK;
 }
 static int checkVolume(const oracle_grid* g)
 {
-    const double s0 = std::fabs(g->scale[0]);
-    if (std::fabs(s0 - std::fabs(g->scale[1])) > 5e-7 || std::fabs(s0 - std::fabs(g->scale[2])) > 5e-7)
+    const double s0 = g->voxelSize[0];
+    if (std::fabs(s0 - g->voxelSize[1]) > 5e-7 || std::fabs(s0 - g->voxelSize[2]) > 5e-7)
         return fail(VDBRT_ERR_NONUNIFORM, "VolumeRayIntersector only supports uniform voxels!");
     if (g->tableSize == 0) return fail(VDBRT_ERR_EMPTY_GRID, "LinearSearchImpl does not supports empty grids");
     return VDBRT_OK;

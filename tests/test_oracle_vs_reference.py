@@ -168,3 +168,72 @@ def test_error_conditions_match_reference(ref, oracle, sphere100, fog100):
     with pytest.raises(refapi.OracleError) as e:
         oracle.render_levelset(sphere100.oracle_handle, cam, refapi.shader(), film, spp=0)
     assert e.value.code == 8
+
+
+def rotated_copy(buf, angle_deg=(20.0, -35.0, 50.0), scale=0.75, translation=(3.0, -2.0, 1.5)):
+    """the same tree under a rotated, uniformly scaled, translated index->world map: nanovdb::Map (GridData + 296) holds float and double
+    copies of the matrix, its inverse and the translation (NanoVDB.h:1418-1428); GridData::mVoxelSize is at +608"""
+    ax, ay, az = np.radians(angle_deg)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    A = scale * (Rz @ Ry @ Rx)                                   # world = A index + t
+    Ai = np.linalg.inv(A)
+    t = np.asarray(translation, np.float64)
+    out = buf.copy()
+    m = 296
+    out[m:m + 36] = np.frombuffer(A.astype("<f4").tobytes(), np.uint8)
+    out[m + 36:m + 72] = np.frombuffer(Ai.astype("<f4").tobytes(), np.uint8)
+    out[m + 72:m + 84] = np.frombuffer(t.astype("<f4").tobytes(), np.uint8)
+    out[m + 88:m + 160] = np.frombuffer(A.astype("<f8").tobytes(), np.uint8)
+    out[m + 160:m + 232] = np.frombuffer(Ai.astype("<f8").tobytes(), np.uint8)
+    out[m + 232:m + 256] = np.frombuffer(t.astype("<f8").tobytes(), np.uint8)
+    out[608:632] = np.frombuffer(np.full(3, scale, "<f8").tobytes(), np.uint8)
+    return refapi.aligned_copy(out), A, t
+
+
+def test_rotated_affine_map_within_tolerance(ref, oracle, sphere100, fog100):
+    """a grid whose index->world map has off-diagonal terms (OpenVDB AffineMap, math/Maps.h:411-445) is the TOLERANCE path:
+    the port evaluates NanoVDB's stored matrices, the reference multiplies through its own 4x4s -- same frame within 1e-4 rel / 1e-3 abs,
+    hit mask equal except for a handful of silhouette pixels"""
+    buf, A, t = rotated_copy(sphere100.buf)
+    rg = ref.from_nanovdb(buf)
+    og = oracle.open(buf)
+    assert abs(oracle.info(og).voxel_size[0] - 0.75) < 1e-12
+    W, H = 240, 160
+    centre = t
+    eye = tuple(centre + np.array([30.0, 40.0, 250.0]))
+    d = refapi.camera_desc(W, H, translation=eye, lookat=tuple(centre))
+    cam = api.vdb_render_camera(W, H, eye, tuple(centre))
+    for kind in (abi.SHADER_DIFFUSE, abi.SHADER_NORMAL):
+        f_ref, f_port = refapi.new_film(W, H), refapi.new_film(W, H)
+        ref.render_levelset(rg, d, refapi.shader(kind), f_ref)
+        oracle.render_levelset(og, cam, api.make_shader(kind), f_port)
+        hit_ref, hit_port = f_ref[..., :3].sum(axis=2) > 0, f_port[..., :3].sum(axis=2) > 0
+        assert hit_ref.sum() > 5000
+        assert (hit_ref != hit_port).sum() <= 4
+        both = hit_ref & hit_port
+        assert np.allclose(f_ref[both], f_port[both], rtol=1e-4, atol=1e-3)
+    # arbitrary rays: times, positions and normals
+    rng = np.random.default_rng(3)
+    n = 3000
+    eyes = centre + np.column_stack([rng.uniform(-60, 60, n), rng.uniform(-60, 60, n), np.full(n, 200.0)])
+    dirs = np.column_stack([rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), np.full(n, -1.0)])
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    rays = refapi.make_rays(eyes, dirs)
+    a, b = ref.intersect(rg, rays), oracle.intersect(og, rays)
+    assert a["hit"].sum() > 1000 and (a["hit"] != b["hit"]).sum() <= 2
+    both = (a["hit"] == 1) & (b["hit"] == 1)
+    for k in ("t_world", "xyz_world", "nml"):
+        assert np.allclose(a[k][both], b[k][both], rtol=1e-4, atol=1e-3), k
+    # fog through the same map
+    fbuf, _, _ = rotated_copy(fog100.buf)
+    rf, of = ref.from_nanovdb(fbuf), oracle.open(fbuf)
+    vo = api.vol_opts_default()
+    vo.primary_step = 0.5
+    v_ref, v_port = refapi.new_film(W, H), refapi.new_film(W, H)
+    ref.render_volume(rf, d, vo, v_ref)
+    oracle.render_volume(of, cam, vo, v_port)
+    assert (v_ref[..., 3] > 0).sum() > 5000
+    assert ((v_ref[..., 3] > 0) != (v_port[..., 3] > 0)).sum() <= 4
+    assert np.mean(np.abs(v_ref - v_port) > 1e-3 + 1e-4 * np.abs(v_ref)) < 2e-3
