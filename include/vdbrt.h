@@ -198,8 +198,10 @@ typedef struct vdbrt_grid_info {
     float    background;
     uint32_t grid_class;      /* VDBRT_GRID_CLASS_*                                                             */
     uint32_t source_type;     /* nanovdb::GridType of the buffer that was uploaded: 1 Float, 13 Fp4, 14 Fp8, 15 Fp16,
-                               * 16 FpN (quantised leaves are expanded to floats at upload), 6 Vec3f (colour grids)    */
-    uint32_t pad;
+                               * 16 FpN, 6 Vec3f (colour grids)                                                  */
+    uint32_t leaf_kind;       /* how the kernels read the leaves: 0 float (Float sources, and Fp4 / FpN -- or Fp8 / Fp16
+                               * with the quant_native knob off -- expanded at upload), 1 Fp8 codes, 2 Fp16 codes     */
+    uint64_t resident_bytes;  /* device memory the grid occupies: the buffer, its halo blocks, its lower-node masks  */
 } vdbrt_grid_info;
 
 /* ---- context / memory ------------------------------------------------------------------------------------ */

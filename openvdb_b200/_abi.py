@@ -83,7 +83,7 @@ class GridInfo(C.Structure):
                 ("lower_count", C.c_uint32), ("upper_count", C.c_uint32), ("root_tiles", C.c_uint32),
                 ("index_bbox", C.c_int32 * 6), ("node_bbox", C.c_int32 * 6), ("voxel_size", C.c_double * 3),
                 ("translation", C.c_double * 3), ("background", C.c_float), ("grid_class", C.c_uint32),
-                ("source_type", C.c_uint32), ("pad", C.c_uint32)]
+                ("source_type", C.c_uint32), ("leaf_kind", C.c_uint32), ("resident_bytes", C.c_uint64)]
 
 
 class NvdbMeta(C.Structure):

@@ -79,7 +79,10 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     if (magic != MAGIC_NUMB && magic != MAGIC_GRID) return setError(VDBRT_ERR_BAD_GRID, "not a NanoVDB grid (bad magic number)");
     if ((rd<uint32_t>(head + OFF_VERSION) >> 21) != 32) return setError(VDBRT_ERR_BAD_GRID, "incompatible NanoVDB major version (need 32)");
     if (rd<uint64_t>(head + OFF_GRIDSIZE) > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "grid size exceeds the buffer");
-    if (rd<uint32_t>(head + OFF_TYPE) != 1) return setError(VDBRT_ERR_NOT_FLOAT, "grid value type is not float");
+    const uint32_t gridType = rd<uint32_t>(head + OFF_TYPE);
+    const uint32_t wantType = grid->leaf_kind == kLeafFp8 ? 14u : (grid->leaf_kind == kLeafFp16 ? 15u : 1u);      // nanovdb::GridType Float / Fp8 / Fp16
+    if (gridType != wantType) return setError(VDBRT_ERR_NOT_FLOAT, "grid value type is not float");
+    const uint64_t leafBytes = grid->leaf_kind == kLeafFp8 ? LeafKind<kLeafFp8>::bytes : (grid->leaf_kind == kLeafFp16 ? LeafKind<kLeafFp16>::bytes : LeafKind<kLeafFloat>::bytes);
     const uint8_t* tree = head + GRID_SIZE;
     const uint64_t rootOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 24));
     if (rootOff + 64 > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "root offset outside the buffer");
@@ -96,7 +99,8 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     info.background = rd<float>(rootHead + kRootBackground);
     for (int i = 0; i < 6; ++i) info.index_bbox[i] = rd<int32_t>(rootHead + 4 * i);
     info.grid_class = rd<uint32_t>(head + OFF_CLASS);
-    info.source_type = 1;                                   // GridType::Float (vdbrt_upload_grid overrides it for quantised sources)
+    info.source_type = gridType;                            // (vdbrt_upload_grid overrides it for sources it expanded)
+    info.leaf_kind = uint32_t(grid->leaf_kind);
     if (rootOff + 64 + uint64_t(info.root_tiles) * kTileSize > grid->bytes) return setError(VDBRT_ERR_BAD_GRID, "root table outside the buffer");
 
     double m[9];
@@ -124,13 +128,13 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     // buffer (counted in init[6]) -- the derived structures below and the render kernels follow those links without looking again
     const uint64_t leafOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 0)), lowerOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 8));
     const uint64_t upperOff = GRID_SIZE + uint64_t(rd<int64_t>(tree + 16));
-    if ((info.leaf_count && leafOff + uint64_t(info.leaf_count) * 2144ull > grid->bytes) || (info.lower_count && lowerOff + uint64_t(info.lower_count) * 33856ull > grid->bytes) ||
+    if ((info.leaf_count && leafOff + uint64_t(info.leaf_count) * leafBytes > grid->bytes) || (info.lower_count && lowerOff + uint64_t(info.lower_count) * 33856ull > grid->bytes) ||
         (info.upper_count && upperOff + uint64_t(info.upper_count) * 270400ull > grid->bytes) || ((leafOff | lowerOff | upperOff | rootOff) & 31))
         return setError(VDBRT_ERR_BAD_GRID, "node arrays outside the buffer or misaligned");
     int init[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
     CUDA_TRY(cudaMemcpyAsync(ctx->scratch, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     if (info.root_tiles) {
-        const NodeAreas ar = {upperOff, info.upper_count, lowerOff, info.lower_count, leafOff, info.leaf_count};
+        const NodeAreas ar = {upperOff, info.upper_count, lowerOff, info.lower_count, leafOff, info.leaf_count, leafBytes};
         const unsigned long long threads = (unsigned long long)info.root_tiles << 15;
         k_node_bbox<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(grid->dev, rootOff, info.root_tiles, reinterpret_cast<int*>(ctx->scratch), ar);
         CUDA_TRY(cudaGetLastError());
@@ -154,18 +158,22 @@ int vdbrt::finishGrid(vdbrt_ctx* ctx, vdbrt_grid* grid)
     // Needs 2944 B per leaf next to the grid; without the memory (or with VDBRT_HALO=0) the stencil walks the leaves instead.
     static const bool useHalo = [] { const char* e = std::getenv("VDBRT_HALO"); return !(e && *e == '0'); }();
     cudaFree(grid->halo); grid->halo = nullptr;
-    if (useHalo && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
-        leafOff + uint64_t(info.leaf_count) * 2144ull <= grid->bytes) {
-        if (cudaMalloc(&grid->halo, sizeof(float) * size_t(kHaloStride) * size_t(info.leaf_count)) != cudaSuccess) { cudaGetLastError(); grid->halo = nullptr; }
+    const size_t blockBytes = grid->leaf_kind == kLeafFp8 ? LeafKind<kLeafFp8>::block : (grid->leaf_kind == kLeafFp16 ? LeafKind<kLeafFp16>::block : LeafKind<kLeafFloat>::block);
+    if ((useHalo || grid->leaf_kind != kLeafFloat) && info.leaf_count && info.root_tiles && !(leafOff & 31) &&
+        leafOff + uint64_t(info.leaf_count) * leafBytes <= grid->bytes) {
+        if (cudaMalloc(&grid->halo, blockBytes * size_t(info.leaf_count)) != cudaSuccess) { cudaGetLastError(); grid->halo = nullptr; }
         else {
             d.leaf0 = uint32_t(leafOff >> 5); d.leaf_count = info.leaf_count;
             const unsigned cap = unsigned(ctx->sm_count > 0 ? ctx->sm_count : 148) * 32u;          // a multiple of the SM count, grid-stride loop
             const unsigned blocks = info.leaf_count < cap ? info.leaf_count : cap;
-            k_build_halo<<<blocks, 256, 0, ctx->stream>>>(d, leafOff, grid->halo);
+            if (grid->leaf_kind == kLeafFp8) k_build_halo_q<kLeafFp8><<<blocks, 256, 0, ctx->stream>>>(d, leafOff, reinterpret_cast<uint8_t*>(grid->halo));
+            else if (grid->leaf_kind == kLeafFp16) k_build_halo_q<kLeafFp16><<<blocks, 256, 0, ctx->stream>>>(d, leafOff, reinterpret_cast<uint8_t*>(grid->halo));
+            else k_build_halo<<<blocks, 256, 0, ctx->stream>>>(d, leafOff, grid->halo);
             CUDA_TRY(cudaGetLastError());
             d.halo = grid->halo;
         }
     }
+    info.resident_bytes = grid->bytes + (grid->halo ? blockBytes * uint64_t(info.leaf_count) : 0) + (grid->lowmask ? 512ull * info.lower_count : 0);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 6; ++i) info.node_bbox[i] = init[i];
     for (int a = 0; a < 3; ++a) { d.bbox_min[a] = init[a]; d.bbox_max[a] = init[3 + a]; }
@@ -336,6 +344,7 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ctx->ls_hist_b = envU("VDBRT_LS_HIST_B", 105);        // list B
     ctx->ls_probe_cap = envU("VDBRT_LS_PROBE_CAP", 128);  // steps a probe ray may take; unfinished = list A
     ctx->ls_probe_b = envU("VDBRT_LS_PROBE_B", 64);       // steps from which a strip goes to list B
+    ctx->quant_native = envU("VDBRT_QUANT_NATIVE", 1);     // NanoGrid<Fp8|Fp16> rendered as they are; 0: expanded to float leaves at upload
     ctx->fog_wave = envU("VDBRT_FOG_WAVE", 1);            // VolumeRender as a wavefront of three kernels (vdbrt_fog.cuh); 0: the one-loop kernel
     ctx->fog_refill = envU("VDBRT_FOG_REFILL", 8);        // shadow kernel: idle lanes that trigger a refill from the record queue
     ctx->fog_rec_per_ray = envU("VDBRT_FOG_REC_PER_RAY", 12);   // record budget per primary ray (average over a batch of tiles)
@@ -467,8 +476,11 @@ int vdbrt_upload_grid(vdbrt_ctx* ctx, const void* buffer, uint64_t bytes, uint32
                            isQuantisedType(rd<uint32_t>(head + OFF_TYPE));
     auto* g = new vdbrt_grid;
     g->device = ctx->device;
-    if (quantised) {
-        // NanoGrid<Fp4|Fp8|Fp16|FpN>: the leaves are expanded to floats once, on the device (vdbrt_quant.cu)
+    const uint32_t srcType = rd<uint32_t>(head + OFF_TYPE);
+    const bool native = quantised && ctx->quant_native && (srcType == 14u || srcType == 15u);
+    if (native) g->leaf_kind = srcType == 14u ? kLeafFp8 : kLeafFp16;        // rendered as it is: the Fp8 / Fp16 instantiations of the kernels
+    if (quantised && !native) {
+        // NanoGrid<Fp4|FpN> (and Fp8 / Fp16 with quant_native = 0): the leaves are expanded to floats once, on the device (vdbrt_quant.cu)
         uint8_t* staged = nullptr;
         if (!onDevice) {
             cudaError_t e = cudaMalloc(&staged, bytes);
@@ -597,10 +609,13 @@ static int longBuffers(vdbrt_ctx* ctx, size_t slots, LongBufs& lb)
     return VDBRT_OK;
 }
 
+static const char* kQuantNativeOnly = "not available on a grid that is rendered from its Fp8 / Fp16 leaves: upload it with quant_native = 0 (VDBRT_QUANT_NATIVE=0) to have the leaves expanded";
+
 static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_camera* cam, const vdbrt_shader* shader,
                           const vdbrt_ls_opts* opts, const vdbrt_film* film, float4* dFilm, const float4* dBg, const AuxOut& aux, bool wantAux,
                           unsigned long long* dCounters)
 {
+    if (grid->leaf_kind != kLeafFloat && (dCounters || opts->iterations > 0)) return setError(VDBRT_ERR_UNSUPPORTED, std::string("work counters / search iterations are ") + kQuantNativeOnly);
     LsParams p; ls_params(grid, opts, film, p);
     p.bg_film = dBg;
     const TileMap tm = makeTileMap(film->width, film->height, opts->part.tile_w, opts->part.tile_h, opts->part.rank, opts->part.count);
@@ -621,7 +636,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     // (ctx->ls_tail, vdbrt_kernels.cuh) unless VDBRT_LS_TAIL=0 selects round 1's per-tile budget.
     const double tilesPerWarp = double(tm.items) / (double(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32));
     const bool automatic = tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
-    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && opts->iterations == 0 && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
+    const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && opts->iterations == 0 && grid->leaf_kind == kLeafFloat && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
     LongBufs lb = {};
     lb.budget = 0xffffffffu;
     if (rounds) {
@@ -639,7 +654,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     const uint32_t nStrips = (tm.items + sc.strip_tiles - 1u) / sc.strip_tiles;
     // heavy strips first: worth a probe launch when a warp gets more than a couple of tiles (otherwise everything starts at once anyway)
     const bool orderAuto = ctx->ls_order == 1u || (ctx->ls_order == 2u && tilesPerWarp >= 2.0);
-    const bool order = !dCounters && nStrips > 1u && !(opts->flags & VDBRT_LS_ORDER_OFF) && ((opts->flags & VDBRT_LS_ORDER_ON) || orderAuto);
+    const bool order = !dCounters && nStrips > 1u && grid->leaf_kind == kLeafFloat && !(opts->flags & VDBRT_LS_ORDER_OFF) && ((opts->flags & VDBRT_LS_ORDER_ON) || orderAuto);
     CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
     if (ctx->ls_affine && !order) {
         sc.affine = ctx->ls_affine; sc.nq = uint32_t(ctx->sm_count > 0 ? std::min(ctx->sm_count, 256) : 1);
@@ -698,7 +713,17 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     // LONG = true compiles the suspension of over-budget rays into the kernel; MULTI = more than one sample per pixel
     const bool multi = opts->spp > 1;
     const bool refine = opts->iterations > 0;      // LinearSearchImpl<.., Iterations > 0>: its own instantiations (never with the rounds)
-    void (*kern)(DevGrid, DevCamera, DevShader, LsParams, TileMap, float4*, AuxOut, unsigned int*, unsigned long long*, LongBufs, Sched) =
+    using KernT = void (*)(DevGrid, DevCamera, DevShader, LsParams, TileMap, float4*, AuxOut, unsigned int*, unsigned long long*, LongBufs, Sched);
+    KernT kern;
+    if (grid->leaf_kind != kLeafFloat) {
+        // NanoGrid<Fp8|Fp16> as they are: the quantised instantiations (frames with or without records, one or several samples)
+        const bool q8 = grid->leaf_kind == kLeafFp8;
+        kern = wantAux ? (multi ? (q8 ? (KernT)k_render_levelset<true, false, false, true, false, kLeafFp8> : (KernT)k_render_levelset<true, false, false, true, false, kLeafFp16>)
+                                : (q8 ? (KernT)k_render_levelset<true, false, false, false, false, kLeafFp8> : (KernT)k_render_levelset<true, false, false, false, false, kLeafFp16>))
+                       : (multi ? (q8 ? (KernT)k_render_levelset<false, false, false, true, false, kLeafFp8> : (KernT)k_render_levelset<false, false, false, true, false, kLeafFp16>)
+                                : (q8 ? (KernT)k_render_levelset<false, false, false, false, false, kLeafFp8> : (KernT)k_render_levelset<false, false, false, false, false, kLeafFp16>));
+    } else
+    kern =
         dCounters ? k_render_levelset<false, true, false, true>
         : refine ? (wantAux ? (multi ? k_render_levelset<true, false, false, true, true> : k_render_levelset<true, false, false, false, true>)
                             : (multi ? k_render_levelset<false, false, false, true, true> : k_render_levelset<false, false, false, false, true>))
@@ -884,13 +909,17 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
     CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     const VolTiles all = {0u, tm.items, nullptr, nullptr};
+    const int kind = grid->leaf_kind;
+    using OneLoopT = void (*)(DevGrid, DevCamera, VolParams, TileMap, float4*, unsigned int*, unsigned long long*, VolTiles);
+    const OneLoopT oneLoop = kind == kLeafFp8 ? (OneLoopT)k_render_volume<false, kLeafFp8> : kind == kLeafFp16 ? (OneLoopT)k_render_volume<false, kLeafFp16> : (OneLoopT)k_render_volume<false>;
     if (dCounters) {
+        if (kind != kLeafFloat) return setError(VDBRT_ERR_UNSUPPORTED, std::string("work counters are ") + kQuantNativeOnly);
         const int blocks = persistentGrid(ctx, (const void*)k_render_volume<true>, tm.items);
         k_render_volume<true><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, dCounters, all);
         ctx->last_launches = 1;
     } else if (!ctx->fog_wave || tm.items == 0) {
-        const int blocks = persistentGrid(ctx, (const void*)k_render_volume<false>, tm.items);
-        k_render_volume<false><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr, all);
+        const int blocks = persistentGrid(ctx, (const void*)oneLoop, tm.items);
+        oneLoop<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr, all);
         ctx->last_launches = 1;
     } else {
         // Wavefront (vdbrt_fog.cuh): primary rays -> records of the dense samples -> shadow rays -> pixels, in batches of tiles whose
@@ -912,23 +941,26 @@ static int launchVolume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
         fw.ctl = reinterpret_cast<unsigned int*>(b + oCtl); fw.tileFlag = b + oFlag; fw.rays = reinterpret_cast<FogRayRec*>(b + oRays);
         fw.recs = reinterpret_cast<FogRec*>(b + oRecs); fw.cap = uint32_t(cap);
         fw.refill = ctx->fog_refill >= 1u && ctx->fog_refill <= 32u ? ctx->fog_refill : 32u;
+        using PrimT = void (*)(DevGrid, DevCamera, VolParams, TileMap, FogWave);
+        using ShadT = void (*)(DevGrid, VolParams, FogWave);
+        const PrimT primary = kind == kLeafFp8 ? (PrimT)k_fog_primary<kLeafFp8> : kind == kLeafFp16 ? (PrimT)k_fog_primary<kLeafFp16> : (PrimT)k_fog_primary<kLeafFloat>;
+        const ShadT shadow = kind == kLeafFp8 ? (ShadT)k_fog_shadow<kLeafFp8> : kind == kLeafFp16 ? (ShadT)k_fog_shadow<kLeafFp16> : (ShadT)k_fog_shadow<kLeafFloat>;
         int perSm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fog_shadow, kBlockThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)shadow, kBlockThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
         const int shadowBlocks = ctx->sm_count * perSm;
         uint32_t launches = 0;
         for (uint32_t t0 = 0; t0 < tm.items; t0 += batchTiles) {
             fw.tile0 = t0; fw.tile1 = std::min(tm.items, t0 + batchTiles);
             CUDA_TRY(cudaMemsetAsync(b, 0, oRays, ctx->stream));                       // queue words, counters, tile flags
-            const int blocks = persistentGrid(ctx, (const void*)k_fog_primary, fw.tile1 - fw.tile0);
-            k_fog_primary<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, fw);
-            k_fog_shadow<<<shadowBlocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, p, fw);
+            const int blocks = persistentGrid(ctx, (const void*)primary, fw.tile1 - fw.tile0);
+            primary<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, fw);
+            shadow<<<shadowBlocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, p, fw);
             const unsigned long long slots = (unsigned long long)(fw.tile1 - fw.tile0) * 32ull;
             k_fog_resolve<<<unsigned(std::min<unsigned long long>((slots + 255) / 256, (unsigned long long)ctx->sm_count * 32ull)), 256, 0, ctx->stream>>>(p, tm, fw, dFilm);
             // tiles that ran out of record space: the one-loop kernel (returns at once when there is none)
             CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
             const VolTiles flagged = {fw.tile0, fw.tile1, fw.tileFlag, fw.ctl + 2};
-            k_render_volume<false><<<persistentGrid(ctx, (const void*)k_render_volume<false>, fw.tile1 - fw.tile0), kBlockThreads, 0, ctx->stream>>>(
-                grid->dgrid, dc, p, tm, dFilm, queue, nullptr, flagged);
+            oneLoop<<<persistentGrid(ctx, (const void*)oneLoop, fw.tile1 - fw.tile0), kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, p, tm, dFilm, queue, nullptr, flagged);
             launches += 4;
         }
         ctx->last_launches = launches;
@@ -1057,7 +1089,9 @@ int vdbrt_intersect_levelset_ex(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vd
     const float vmin = iso - float(2 * grid->info.voxel_size[0]), vmax = iso + float(2 * grid->info.voxel_size[0]);
     const unsigned blocks = unsigned(std::min<uint64_t>((n + kBlockThreads - 1) / kBlockThreads, uint64_t(ctx->sm_count) * 16));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    k_intersect_levelset<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH, int(iterations));
+    if (grid->leaf_kind == kLeafFp8) k_intersect_levelset<kLeafFp8><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH, int(iterations));
+    else if (grid->leaf_kind == kLeafFp16) k_intersect_levelset<kLeafFp16><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH, int(iterations));
+    else k_intersect_levelset<kLeafFloat><<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dR, n, space, iso, vmin, vmax, dH, int(iterations));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->last_launches = 1;
@@ -1105,7 +1139,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     struct { const char* name; uint32_t* field; } table[] = {
         {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order}, {"ls_history", &ctx->ls_history}, {"ls_hist_a", &ctx->ls_hist_a}, {"ls_hist_b", &ctx->ls_hist_b},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
-        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
+        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"quant_native", &ctx->quant_native}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };
     for (auto& t : table) if (k == t.name) {
         if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;

@@ -650,6 +650,7 @@ extern "C" int vdbrt_build_fog_from_levelset(vdbrt_ctx* ctx, const vdbrt_grid* l
 {
     if (!ctx || !ls || !out) return setError(VDBRT_ERR_INVALID_ARG, "null argument");
     if (ls->info.grid_class != VDBRT_GRID_CLASS_LEVEL_SET) return setError(VDBRT_ERR_NOT_LEVELSET, "sdfToFogVolume needs a level set");
+    if (ls->leaf_kind != 0) return setError(VDBRT_ERR_UNSUPPORTED, "sdfToFogVolume needs float leaves: upload the quantised grid with quant_native = 0");
     std::lock_guard<std::mutex> lock(ctx->mx);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = ctx->stream;

@@ -51,8 +51,8 @@ struct DevGrid {
     // background) -- at halo + 736 * i floats, index 81 x + 9 y + z.  Built once when the grid is registered (k_build_halo).
     // A BoxStencil cell (tools: math/Stencils.h:414-423) whose base voxel lies in a leaf reads its 8 corners from that
     // leaf's block with 8 loads off one pointer: no walk over the up to 8 leaves the cell touches.
-    const float* halo;
-    uint32_t leaf0;           // handle (byte offset >> 5) of leaf 0; leaves are 2144 B = 67 handles apart
+    const float* halo;        // float leaves: 736 floats per block; quantised leaves: the same pointer holds the code blocks (LeafKind::block bytes each)
+    uint32_t leaf0;           // handle (byte offset >> 5) of leaf 0; leaves are LeafKind::handles apart (2144 B = 67 handles for float leaves)
     uint32_t leaf_count;
     // "leaf or active tile" masks of the lower nodes (null = none): lowmask[64 i + w] = child-mask word w | value-mask word w of
     // lower node i (512 B per node, built by k_build_lowmask).  The volume walk only needs this one bit per 8^3 cell: at the
@@ -62,6 +62,21 @@ struct DevGrid {
     uint32_t lower_count;
 };
 constexpr uint32_t kHaloStride = 736;   // floats per halo block (729 used; 2944 B keeps blocks 32-byte aligned)
+
+// ---- leaf kinds.  NanoGrid<Fp8> / NanoGrid<Fp16> (nanovdb/NanoVDB.h:3752-3930) can be rendered AS THEY ARE (vdbrt_upload_grid with
+// the context's quant_native knob): the tree above the leaves is the float build's, a leaf is LeafFnBase (96 B: origin, flags, value
+// mask, float mMinimum @80, float mQuantum @84, statistics) + 512 codes of 1 or 2 bytes, and
+//     LeafData<FpX>::getValue(i) = float(code_i) * mQuantum + mMinimum        (:3876, :3906; product and sum rounded separately)
+// is evaluated where the value is fetched.  The halo block of such a leaf keeps CODES too: 8 {minimum, quantum} pairs -- own leaf,
+// +z, +y, +yz, +x, +xz, +xy, +xyz neighbour block; a block without a leaf is {its tile / background value, 0} with code 0 -- then
+// 729 codes at 81 x + 9 y + z: 800 B (Fp8) or 1 536 B (Fp16) per leaf instead of 2 944.  Every kind is its own instantiation of
+// the kernels (LEAF template parameter): the float kernels carry none of this (the branch inside one kernel cost them 32 %, round 1).
+enum { kLeafFloat = 0, kLeafFp8 = 1, kLeafFp16 = 2 };
+template<int LEAF> struct LeafKind;
+template<> struct LeafKind<kLeafFloat> { static constexpr uint32_t handles = 67u, bytes = 2144u, block = 2944u; };
+template<> struct LeafKind<kLeafFp8> { static constexpr uint32_t handles = 19u, bytes = 608u, block = 800u; };
+template<> struct LeafKind<kLeafFp16> { static constexpr uint32_t handles = 35u, bytes = 1120u, block = 1536u; };
+constexpr uint32_t kLeafMinimum = 80, kLeafQuantum = 84, kQHaloCodes = 64;
 
 struct RootSmem {
     unsigned long long key[kMaxSmemTiles];
@@ -77,6 +92,26 @@ __device__ __forceinline__ long long ldgs64(const uint8_t* p) { return __ldg(rei
 __device__ __forceinline__ uint32_t ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ float ldgf(const uint8_t* p) { return __ldg(reinterpret_cast<const float*>(p)); }
 __device__ __forceinline__ bool maskBit(const uint8_t* mask, uint32_t n) { return (ldg64(mask + 8u * (n >> 6)) >> (n & 63u)) & 1ull; }
+
+// value n of a leaf (LeafData<float>::getValue / LeafData<FpX>::getValue)
+template<int LEAF>
+__device__ __forceinline__ float leafValue(const uint8_t* leaf, uint32_t n)
+{
+    if (LEAF == kLeafFloat) return ldgf(leaf + kLeafValues + 4u * n);
+    const float code = LEAF == kLeafFp8 ? float(__ldg(leaf + kLeafValues + n)) : float(__ldg(reinterpret_cast<const unsigned short*>(leaf + kLeafValues) + n));
+    return __fadd_rn(__fmul_rn(code, ldgf(leaf + kLeafQuantum)), ldgf(leaf + kLeafMinimum));
+}
+// value (x,y,z) in 0..8 of halo block `block`
+template<int LEAF>
+__device__ __forceinline__ float haloValue(const float* halo, uint32_t block, uint32_t x, uint32_t y, uint32_t z)
+{
+    const uint32_t i = x * 81u + y * 9u + z;
+    if (LEAF == kLeafFloat) return __ldg(halo + size_t(block) * kHaloStride + i);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(halo) + size_t(block) * LeafKind<LEAF>::block;
+    const float2 mq = __ldg(reinterpret_cast<const float2*>(b) + (((x >> 3) << 2) | ((y >> 3) << 1) | (z >> 3)));      // {minimum, quantum} of the block the value came from
+    const float code = LEAF == kLeafFp8 ? float(__ldg(b + kQHaloCodes + i)) : float(__ldg(reinterpret_cast<const unsigned short*>(b + kQHaloCodes) + i));
+    return __fadd_rn(__fmul_rn(code, mq.y), mq.x);
+}
 
 // RootData::CoordToKey with NANOVDB_USE_SINGLE_ROOT_KEY (NanoVDB.h:2630-2640)
 __device__ __forceinline__ unsigned long long rootKey(int x, int y, int z) {
@@ -169,9 +204,10 @@ struct TreeCursor {
     }
 
     // value and active state at the deepest node containing the coordinate (after descend())
+    template<int LEAF = kLeafFloat>
     __device__ __forceinline__ bool valueAt(const DevGrid& g, const RootSmem& s, int depth, int x, int y, int z, float& v) const
     {
-        if (depth == 0) { const uint8_t* p = node(g, n0); const uint32_t n = leafOffset(x, y, z); v = ldgf(p + kLeafValues + 4u * n); return maskBit(p + kLeafVMask, n); }
+        if (depth == 0) { const uint8_t* p = node(g, n0); const uint32_t n = leafOffset(x, y, z); v = leafValue<LEAF>(p, n); return maskBit(p + kLeafVMask, n); }
         if (depth == 1) { const uint8_t* p = node(g, n1); const uint32_t n = lowerOffset(x, y, z); v = ldgf(p + kLowerTable + 8u * n); return maskBit(p + kLowerVMask, n); }
         if (depth == 2) { const uint8_t* p = node(g, n2); const uint32_t n = upperOffset(x, y, z); v = ldgf(p + kUpperTable + 8u * n); return maskBit(p + kUpperVMask, n); }
         const int t = findTile(g, s, x, y, z);
@@ -188,14 +224,16 @@ struct TreeCursor {
         if (t < 0) return false;
         return (s.staged ? s.state[t] : ldg32(g.tiles + kTileSize * t + 16)) != 0u;
     }
+    template<int LEAF = kLeafFloat>
     __device__ __forceinline__ bool probeValue(const DevGrid& g, const RootSmem& s, int x, int y, int z, float& v)
     {
         const int depth = descend(g, s, x, y, z);
-        return valueAt(g, s, depth, x, y, z, v);
+        return valueAt<LEAF>(g, s, depth, x, y, z, v);
     }
+    template<int LEAF = kLeafFloat>
     __device__ __forceinline__ float getValue(const DevGrid& g, const RootSmem& s, int x, int y, int z)
     {
-        float v; probeValue(g, s, x, y, z, v); return v;
+        float v; probeValue<LEAF>(g, s, x, y, z, v); return v;
     }
 
     // the 8 corners of the cell (x..x+1, y..y+1, z..z+1) in BoxStencil slot order 000,001,011,010,100,101,111,110
@@ -206,7 +244,7 @@ struct TreeCursor {
     // visited leaf with predicated loads off one base pointer.  KEEP = false: the fetch works on a COPY of the cursor, so
     // the caller's path cache keeps pointing at the node its DDA is walking (no re-descent after a stencil that straddled
     // a face); KEEP = true: the cursor follows the fetch (the fog sampler's own cursor, tools/Interpolation.h:420-425).
-    template<bool KEEP>
+    template<bool KEEP, int LEAF = kLeafFloat>
     __device__ __forceinline__ void fetchCell(const DevGrid& g, const RootSmem& s, int x, int y, int z, float v[8])
     {
         if (g.halo) {
@@ -215,18 +253,26 @@ struct TreeCursor {
             TreeCursor& probe = KEEP ? *this : copy;
             const int depth = probe.descend(g, s, x, y, z);
             if (depth == 0) {
-                const uint32_t i = (probe.n0 - g.leaf0) / 67u;
+                const uint32_t i = (probe.n0 - g.leaf0) / LeafKind<LEAF>::handles;
                 if (i < g.leaf_count) {
-                    const float* b = g.halo + size_t(i) * kHaloStride + (uint32_t(x & 7) * 81u + uint32_t(y & 7) * 9u + uint32_t(z & 7));
-                    v[0] = __ldg(b); v[1] = __ldg(b + 1); v[2] = __ldg(b + 10); v[3] = __ldg(b + 9);
-                    v[4] = __ldg(b + 81); v[5] = __ldg(b + 82); v[6] = __ldg(b + 91); v[7] = __ldg(b + 90);
+                    if (LEAF == kLeafFloat) {
+                        const float* b = g.halo + size_t(i) * kHaloStride + (uint32_t(x & 7) * 81u + uint32_t(y & 7) * 9u + uint32_t(z & 7));
+                        v[0] = __ldg(b); v[1] = __ldg(b + 1); v[2] = __ldg(b + 10); v[3] = __ldg(b + 9);
+                        v[4] = __ldg(b + 81); v[5] = __ldg(b + 82); v[6] = __ldg(b + 91); v[7] = __ldg(b + 90);
+                    } else {
+                        const uint32_t bx = uint32_t(x & 7), by = uint32_t(y & 7), bz = uint32_t(z & 7);
+                        v[0] = haloValue<LEAF>(g.halo, i, bx, by, bz);         v[1] = haloValue<LEAF>(g.halo, i, bx, by, bz + 1);
+                        v[2] = haloValue<LEAF>(g.halo, i, bx, by + 1, bz + 1); v[3] = haloValue<LEAF>(g.halo, i, bx, by + 1, bz);
+                        v[4] = haloValue<LEAF>(g.halo, i, bx + 1, by, bz);     v[5] = haloValue<LEAF>(g.halo, i, bx + 1, by, bz + 1);
+                        v[6] = haloValue<LEAF>(g.halo, i, bx + 1, by + 1, bz + 1); v[7] = haloValue<LEAF>(g.halo, i, bx + 1, by + 1, bz);
+                    }
                     return;
                 }
             } else if (((x & 7) != 7) && ((y & 7) != 7) && ((z & 7) != 7)) {
                 // no leaf at the base voxel and the cell stays inside its 8^3 block (a ray entering the band through a high
                 // face: tester.init's position lies in the empty block it came from): one tile / the background covers all 8
                 float tile;
-                probe.valueAt(g, s, depth, x, y, z, tile);
+                probe.template valueAt<LEAF>(g, s, depth, x, y, z, tile);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = tile;
                 return;
@@ -243,14 +289,14 @@ struct TreeCursor {
             const int rx = x + (cmb >> 2), ry = y + ((cmb >> 1) & 1), rz = z + (cmb & 1);   // a corner inside that leaf
             const int depth = t.descend(g, s, rx, ry, rz);
             float tile = 0.f;
-            const float* lv = nullptr;
-            if (depth == 0) lv = reinterpret_cast<const float*>(node(g, t.n0) + kLeafValues);
-            else t.valueAt(g, s, depth, rx, ry, rz, tile);     // one tile (or the background) covers the whole 8^3 block
+            const uint8_t* lv = nullptr;
+            if (depth == 0) lv = node(g, t.n0);
+            else t.template valueAt<LEAF>(g, s, depth, rx, ry, rz, tile);     // one tile (or the background) covers the whole 8^3 block
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int dx = q >> 2, dy = (q >> 1) & 1, dz = (q ^ (q >> 1)) & 1;            // slot q -> corner offset
                 if ((((dx << 2) | (dy << 1) | dz) & fmask) == cmb)
-                    v[q] = lv ? __ldg(lv + ((dx ? ox1 : ox0) | (dy ? oy1 : oy0) | (dz ? oz1 : oz0))) : tile;
+                    v[q] = lv ? leafValue<LEAF>(lv, (dx ? ox1 : ox0) | (dy ? oy1 : oy0) | (dz ? oz1 : oz0)) : tile;
             }
             cmb = (cmb - fmask) & fmask;                        // next sub-mask of fmask; wraps to 0 after fmask itself
         } while (cmb != 0);
@@ -415,14 +461,14 @@ struct Stencil {
     float v[8];
     __device__ __forceinline__ void reset() { cx = cy = cz = 0x7fffffff; }    // BaseStencil: mCenter(Coord::max()) (:212)
 
-    template<bool COUNT>
+    template<bool COUNT, int LEAF = kLeafFloat>
     __device__ __forceinline__ void moveTo(const DevGrid& g, const RootSmem& s, TreeCursor& acc, double x, double y, double z, Counters& c)
     {
         const int i = int(floor(x)), j = int(floor(y)), k = int(floor(z));
         if (i == cx && j == cy && k == cz) return;
         cx = i; cy = j; cz = k;
         if (COUNT) ++c.refills;
-        acc.template fetchCell<false>(g, s, i, j, k, v);
+        acc.template fetchCell<false, LEAF>(g, s, i, j, k, v);
     }
     // interpolation(Vec3<float>) (:335-360): position converted to float first; every lerp in float
     __device__ __forceinline__ float interpolation(double x, double y, double z) const
@@ -526,7 +572,7 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 // REFINE = true: LinearSearchImpl<GridT, Iterations> with Iterations = `iters` > 0 -- after the zero crossing the hit time is refined by
 // `iters` secant steps, each one stencil evaluation at the current estimate (tools/RayIntersector.h:630-636).  A separate instantiation:
 // the default kernels (Iterations = 0, what vdb_render and tools::rayTrace use) do not carry the loop.
-template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false, bool REFINE = false>
+template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false, bool REFINE = false, int LEAF = kLeafFloat>
 __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
                                          TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
                                          LsWalk& w, LsHit& out, Counters& c, int iters = 0)
@@ -560,11 +606,11 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 // a voxel of a leaf: the value comes from the leaf's halo block when there is one (the same values; the stencil
                 // reads them from there too, so the leaf's own value array stays out of the caches), the active bit from the leaf
                 uint32_t hi = 0xffffffffu;
-                if (depth == 0 && g.halo) hi = (acc.n0 - g.leaf0) / 67u;
+                if (depth == 0 && g.halo) hi = (acc.n0 - g.leaf0) / LeafKind<LEAF>::handles;
                 if (hi < g.leaf_count) {
-                    V = __ldg(g.halo + size_t(hi) * kHaloStride + (uint32_t(cur.vx & 7) * 81u + uint32_t(cur.vy & 7) * 9u + uint32_t(cur.vz & 7)));
+                    V = haloValue<LEAF>(g.halo, hi, uint32_t(cur.vx & 7), uint32_t(cur.vy & 7), uint32_t(cur.vz & 7));
                     on = maskBit(TreeCursor::node(g, acc.n0) + kLeafVMask, leafOffset(cur.vx, cur.vy, cur.vz));
-                } else on = acc.valueAt(g, s, depth, cur.vx, cur.vy, cur.vz, V);
+                } else on = acc.template valueAt<LEAF>(g, s, depth, cur.vx, cur.vy, cur.vz, V);
                 if (on && V > vmin && V < vmax) { w.pendInterp = 2; w.tq = cur.next(); }
                 w.pendStep = true;
             }
@@ -590,7 +636,7 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
 #pragma unroll 1
         for (int n = 0;; ++n) {
             const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
-            st.template moveTo<COUNT>(g, s, acc, px, py, pz, c);
+            st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
             if (purpose == 3) {
                 if (REFINE && n < iters) {
                     // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
@@ -636,14 +682,14 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
 }
 
 // plain per-thread form (arbitrary-ray batches)
-template<bool COUNT, int THREADS>
+template<bool COUNT, int THREADS, int LEAF = kLeafFloat>
 __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm, TreeCursor& acc, Stencil& st, Ray& ray,
                                                   float iso, float vmin, float vmax, LsHit& out, Counters& c, int iters = 0)
 {
     LsWalk w; w.begin(ray);
 #pragma unroll 1
     for (;;) {
-        const int r = lsAdvance<COUNT, false, THREADS, false, true>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
+        const int r = lsAdvance<COUNT, false, THREADS, false, true, LEAF>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
         if (r != kWalkContinue) return r == kWalkHit;
     }
 }
@@ -749,13 +795,14 @@ struct SpanWalk {
 // tools::BoxSampler::sample through GridSampler::wsSample (tools/Interpolation.h:420-425,712-762): corner values are
 // float, each lerp is a + float((b-a) * w) with a DOUBLE weight.
 __device__ __forceinline__ float lerpBox(float a, float b, double w) { const double t = (b - a) * w; return a + float(t); }
+template<int LEAF = kLeafFloat>
 __device__ __forceinline__ float boxSampleWorld(const DevGrid& g, const RootSmem& s, TreeCursor& acc, double wx, double wy, double wz)
 {
     worldToIndexPos(g, wx, wy, wz);
     const int i = int(floor(wx)), j = int(floor(wy)), k = int(floor(wz));
     const double u = wx - i, v = wy - j, w = wz - k;
     float d[8];   // 000,001,011,010,100,101,111,110
-    acc.template fetchCell<true>(g, s, i, j, k, d);
+    acc.template fetchCell<true, LEAF>(g, s, i, j, k, d);
     return lerpBox(lerpBox(lerpBox(d[0], d[1], w), lerpBox(d[3], d[2], w), v),
                    lerpBox(lerpBox(d[4], d[5], w), lerpBox(d[7], d[6], w), v), u);
 }

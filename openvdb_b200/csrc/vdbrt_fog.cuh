@@ -100,6 +100,7 @@ constexpr int kFogWaveBatch = 8;       // a phase runs when this many lanes want
 // ---------------------------------------------------------------------------------------------------------------------------
 // 1. primary rays
 // ---------------------------------------------------------------------------------------------------------------------------
+template<int LEAF = kLeafFloat>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_FOG_PRIMARY_BLOCKS)
 k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
               const __grid_constant__ TileMap tm, const __grid_constant__ FogWave fw)
@@ -177,7 +178,7 @@ k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCame
                 // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035)
                 double wx = m.ray.ex + m.ray.dx * m.tcur, wy = m.ray.ey + m.ray.dy * m.tcur, wz = m.ray.ez + m.ray.dz * m.tcur;
                 indexToWorldPos(g, wx, wy, wz);
-                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
+                const double d = boxSampleWorld<LEAF>(g, root, accV, wx, wy, wz);
                 if (d < p.cutoff) m.tcur += p.pstep;                                      // continue (:1036)
                 else { dens = d; pendExp = true; }
             }
@@ -242,6 +243,7 @@ k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCame
 // ---------------------------------------------------------------------------------------------------------------------------
 // 2. shadow rays: one lane per record, 32 consecutive records per warp ticket
 // ---------------------------------------------------------------------------------------------------------------------------
+template<int LEAF = kLeafFloat>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_FOG_SHADOW_BLOCKS)
 k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParams p, const __grid_constant__ FogWave fw)
 {
@@ -304,7 +306,7 @@ k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParam
             if (marching && runM) {
                 double wx = m.ray.ex + m.ray.dx * m.tcur, wy = m.ray.ey + m.ray.dy * m.tcur, wz = m.ray.ez + m.ray.dz * m.tcur;
                 indexToWorldPos(g, wx, wy, wz);
-                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);               // (:1048)
+                const double d = boxSampleWorld<LEAF>(g, root, accV, wx, wy, wz);         // (:1048)
                 if (d < p.cutoff) m.tcur += p.sstep;                                      // continue (:1049)
                 else { dens = d; pendExp = true; }
             }

@@ -22,6 +22,7 @@ struct vdbrt_ctx {
     void* ord = nullptr;   size_t ord_cap = 0;  // tile-ordering buffers of the level-set render (OrderBufs, vdbrt_kernels.cuh)
     uint32_t ls_strip = 1, ls_strip_ratio = 4, ls_refill = 32, ls_eager = 0, ls_affine = 0, ls_order = 0, ls_probe_cap = 128, ls_probe_b = 64;   // Sched (vdbrt_kernels.cuh)
     void* fog = nullptr;   size_t fog_cap = 0;  // records / ray table of the fog wavefront (vdbrt_fog.cuh)
+    uint32_t quant_native = 1;                  // NanoGrid<Fp8|Fp16> rendered as they are (their own kernel instantiations) instead of expanded to float leaves
     uint32_t fog_wave = 1, fog_refill = 8, fog_rec_per_ray = 12, fog_cap_mb = 4096;
     uint32_t ls_voxel_only = 0;                 // tail rule: only rays that are marching voxels are suspended
     uint32_t ls_tail = 0;                       // tail rule: iterations a tile may still spend once the work queue has run dry (0: per-tile rule below)
@@ -39,6 +40,7 @@ struct vdbrt_grid {
     vdbrt::DevGrid dgrid;
     float* halo = nullptr;                      // DevGrid::halo (9^3 values per leaf)
     unsigned long long* lowmask = nullptr;      // DevGrid::lowmask (512 B per lower node)
+    int leaf_kind = 0;                          // vdbrt::kLeafFloat / kLeafFp8 / kLeafFp16: how the kernels read this grid's leaves
     bool is_color = false;                      // a NanoGrid<Vec3f> for the colour-grid shaders (dcolor instead of dgrid)
     vdbrt::DevColor dcolor;
 };

@@ -227,7 +227,7 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
 
 // MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
 // REFINE = true: LinearSearchImpl's secant refinements (p.iters > 0), see lsAdvance.
-template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false>
+template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false, int LEAF = kLeafFloat>
 __global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
@@ -414,7 +414,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
-                const int r = lsAdvance<COUNT, true, kBlockThreads, false, REFINE>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
+                const int r = lsAdvance<COUNT, true, kBlockThreads, false, REFINE, LEAF>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
                 if (rayOn) status = r;
             }
             __syncwarp();
@@ -727,6 +727,7 @@ k_long_finish(const __grid_constant__ DevGrid g, const __grid_constant__ DevShad
 struct HitOut { int32_t hit; int32_t ijk[3]; double t_index, t_world; double xyz_index[3], xyz_world[3], nml[3]; };
 struct RayIn { double eye[3], dir[3], t0, t1; };
 
+template<int LEAF = kLeafFloat>
 __global__ void __launch_bounds__(kBlockThreads)
 k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict__ rays, unsigned long long n, uint32_t space,
                      float iso, float vmin, float vmax, HitOut* __restrict__ hits, int iters)
@@ -746,7 +747,7 @@ k_intersect_levelset(const __grid_constant__ DevGrid g, const RayIn* __restrict_
         if (space == 0) worldToIndex(g, ray);
         HitOut o = {};
         LsHit h;
-        if (clipRay(ray, g, 0) && intersectLevelSet<false, kBlockThreads>(g, root, wsm, acc, st, ray, iso, vmin, vmax, h, c, iters)) {
+        if (clipRay(ray, g, 0) && intersectLevelSet<false, kBlockThreads, LEAF>(g, root, wsm, acc, st, ray, iso, vmin, vmax, h, c, iters)) {
             double x = h.px, y = h.py, z = h.pz;
             double nx = h.gx, ny = h.gy, nz = h.gz;
             vnormalize(nx, ny, nz);
@@ -823,7 +824,7 @@ enum { kFogIdle = 0, kFogPrimary = 1, kFogShadow = 2 };
 struct VolTiles { uint32_t tile0, tile1; const uint8_t* only; const unsigned int* gate; };   // work items [tile0, tile1); only[t - tile0] != 0 if given; *gate != 0 if given
 constexpr int kFogBatch = 8;             // a phase runs when this many lanes want it, or when the other phases are starved
 
-template<bool COUNT>
+template<bool COUNT, int LEAF = kLeafFloat>
 __global__ void __launch_bounds__(kBlockThreads, 3)
 k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ VolParams p,
                 const __grid_constant__ TileMap tm, float4* __restrict__ film, unsigned int* queue, unsigned long long* counters,
@@ -938,7 +939,7 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                 // getWorldPos(t) = indexToWorld(ray(t)); sampler.wsSample -> worldToIndex -> BoxSampler (:1034-1035,1048)
                 double wx = ray.ex + ray.dx * tcur, wy = ray.ey + ray.dy * tcur, wz = ray.ez + ray.dz * tcur;
                 indexToWorldPos(g, wx, wy, wz);
-                const double d = boxSampleWorld(g, root, accV, wx, wy, wz);
+                const double d = boxSampleWorld<LEAF>(g, root, accV, wx, wy, wz);
                 if (COUNT) { if (mode == kFogPrimary) ++c.psamples; else ++c.ssamples; }
                 if (d < p.cutoff) tcur += mode == kFogPrimary ? p.pstep : p.sstep;        // continue
                 else { dens = d; pendExp = mode; }
@@ -1076,11 +1077,47 @@ __global__ void __launch_bounds__(256) k_build_halo(const __grid_constant__ DevG
 
 // The same pass validates the tree's links: a child offset must land on a node of the right level inside the buffer
 // (nodes of one level are stored contiguously, NanoVDB.h:67-122) before anything is read through it; out[6] counts the bad ones.
-struct NodeAreas { unsigned long long upper0, upperN, lower0, lowerN, leaf0, leafN; };      // byte offset of node 0 and node count, per level
+struct NodeAreas { unsigned long long upper0, upperN, lower0, lowerN, leaf0, leafN, leafBytes; };      // byte offset of node 0 and node count, per level; size of a leaf
 __device__ __forceinline__ bool inArea(const uint8_t* base, const uint8_t* p, unsigned long long first, unsigned long long count, unsigned long long size)
 {
     const unsigned long long off = (unsigned long long)(p - base);
     return p >= base + first && off - first < count * size && (off - first) % size == 0ull;
+}
+
+// DevGrid::halo for quantised leaves (see the leaf kinds in vdbrt_device.cuh): per leaf 8 {minimum, quantum} pairs -- one per source
+// block (own leaf, then the blocks at +z, +y, +yz, +x, +xz, +xy, +xyz) -- and the 729 CODES.  A source block that is a leaf gives its
+// own pair and codes; one that is a tile or the background gives {value, 0} and code 0 (0 * 0 + value is the value, exactly).
+template<int LEAF>
+__global__ void __launch_bounds__(256) k_build_halo_q(const __grid_constant__ DevGrid g, unsigned long long leafOff, uint8_t* __restrict__ out)
+{
+    __shared__ RootSmem root;
+    __shared__ const uint8_t* src[8];      // the leaf of source block r, or null
+    stageRoot(g, root);
+    __syncthreads();
+    for (uint32_t leaf = blockIdx.x; leaf < g.leaf_count; leaf += gridDim.x) {
+        const uint8_t* lf = g.base + leafOff + (unsigned long long)leaf * LeafKind<LEAF>::bytes;
+        const int ox = int(ldg32(lf)) & ~7, oy = int(ldg32(lf + 4)) & ~7, oz = int(ldg32(lf + 8)) & ~7;
+        uint8_t* dst = out + size_t(leaf) * LeafKind<LEAF>::block;
+        if (threadIdx.x < 8) {
+            const uint32_t r = threadIdx.x;
+            TreeCursor c; c.reset();
+            const int x = ox + int((r >> 2) << 3), y = oy + int(((r >> 1) & 1u) << 3), z = oz + int((r & 1u) << 3);
+            const int depth = c.descend(g, root, x, y, z);
+            float mn, q = 0.f;
+            if (depth == 0) { const uint8_t* nl = TreeCursor::node(g, c.n0); src[r] = nl; mn = ldgf(nl + kLeafMinimum); q = ldgf(nl + kLeafQuantum); }
+            else { src[r] = nullptr; c.template valueAt<LEAF>(g, root, depth, x, y, z, mn); }
+            reinterpret_cast<float2*>(dst)[r] = make_float2(mn, q);
+        }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < 729u; t += 256u) {
+            const uint32_t lx = t / 81u, ly = (t / 9u) % 9u, lz = t % 9u;
+            const uint8_t* nl = src[((lx >> 3) << 2) | ((ly >> 3) << 1) | (lz >> 3)];
+            const uint32_t n = ((lx & 7u) << 6) | ((ly & 7u) << 3) | (lz & 7u);
+            if (LEAF == kLeafFp8) dst[kQHaloCodes + t] = nl ? __ldg(nl + kLeafValues + n) : uint8_t(0);
+            else reinterpret_cast<unsigned short*>(dst + kQHaloCodes)[t] = nl ? __ldg(reinterpret_cast<const unsigned short*>(nl + kLeafValues) + n) : (unsigned short)0;
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long rootOff, uint32_t tableSize, int* out, const __grid_constant__ NodeAreas ar)
@@ -1112,7 +1149,7 @@ __global__ void k_node_bbox(const uint8_t* __restrict__ base, unsigned long long
         while (kids) {
             const uint32_t m = w * 64u + uint32_t(__ffsll((long long)kids) - 1); kids &= kids - 1;
             const uint8_t* lf = l + ldgs64(l + kLowerTable + 8u * m);
-            if (!inArea(base, lf, ar.leaf0, ar.leafN, 2144ull)) { ++bad; continue; }
+            if (!inArea(base, lf, ar.leaf0, ar.leafN, ar.leafBytes)) { ++bad; continue; }
             unsigned long long any = 0;
             for (int q = 0; q < 8; ++q) any |= ldg64(lf + kLeafVMask + 8 * q);
             if (!any) continue;

@@ -1,5 +1,7 @@
-"""Quantised grids on the GPU: vdbrt_upload_grid expands NanoGrid<Fp4|Fp8|Fp16|FpN> leaves to floats on the
-device (openvdb_b200/csrc/vdbrt_quant.cu) and the grid then renders like any NanoGrid<float>.  Everything is bit-exact:
+"""Quantised grids on the GPU.  NanoGrid<Fp8|Fp16> are rendered AS THEY ARE by their own kernel instantiations
+(codes dequantised where a value is fetched, code halo blocks: csrc/vdbrt_device.cuh "leaf kinds"; knob quant_native, default on);
+NanoGrid<Fp4|FpN> -- and Fp8 / Fp16 with quant_native = 0 -- have their leaves expanded to floats on the device at upload
+(csrc/vdbrt_quant.cu) and then render like any NanoGrid<float>.  Both ways everything is bit-exact:
 against the oracle dequantising in place, against the frames the unmodified reference rendered from nanoToOpenVDB of the same
 buffers (tests/golden/quantized.npz) and -- when oracle/_ref travelled -- against the reference run here."""
 import ctypes as C
@@ -35,11 +37,24 @@ def gold():
     return np.load(GOLD)
 
 
+@pytest.fixture(params=[1, 0], ids=["native", "expanded"])
+def mode(ctx, request):
+    """quant_native = 1: Fp8 / Fp16 rendered from their codes; 0: every quantised grid expanded at upload"""
+    ctx.set_tuning(quant_native=request.param)
+    yield request.param
+    ctx.set_tuning(quant_native=1)
+
+
 @pytest.mark.parametrize("name,gtype", [(t[0], t[1]) for t in TYPES])
 def test_expanded_grid_is_the_dequantised_float_grid(ctx, oracle, gold, name, gtype):
     q = refapi.aligned_copy(gold["ls_" + name])
     og = oracle.open(q)
-    g = ctx.upload(q)
+    ctx.set_tuning(quant_native=0)
+    try:
+        g = ctx.upload(q)
+    finally:
+        ctx.set_tuning(quant_native=1)
+    assert g.info.leaf_kind == 0
     qi = oracle.info(og)
     assert g.info.source_type == gtype
     assert g.info.leaf_count == qi.leaf_count and g.info.active_voxels == qi.active_voxels
@@ -79,10 +94,11 @@ def test_expanded_grid_is_the_dequantised_float_grid(ctx, oracle, gold, name, gt
 
 
 @pytest.mark.parametrize("name,gtype", [(t[0], t[1]) for t in TYPES])
-def test_levelset_render_of_quantised_grid(ctx, oracle, gold, name, gtype):
+def test_levelset_render_of_quantised_grid(ctx, oracle, gold, mode, name, gtype):
     q = refapi.aligned_copy(gold["ls_" + name])
     og = oracle.open(q)
     g = ctx.upload(q)
+    assert g.info.leaf_kind == ({14: 1, 15: 2}.get(gtype, 0) if mode else 0)
     cam, _ = ls_camera()
     sh = api.make_shader(abi.SHADER_DIFFUSE)
     film, aux = gpu_levelset(ctx, g, cam, sh, W, H)
@@ -103,9 +119,19 @@ def test_levelset_render_of_quantised_grid(ctx, oracle, gold, name, gtype):
 
 
 @pytest.mark.parametrize("name", ["fp8", "fpn"])
-def test_fog_render_of_quantised_grid(ctx, oracle, gold, name):
+def test_fog_render_of_quantised_grid(ctx, oracle, gold, mode, name):
     q = refapi.aligned_copy(gold["fog_" + name])
     g = ctx.upload(q)
+    # both fog paths: the wavefront (default) and the one-loop kernel
+    cam0, _ = fog_camera()
+    opts0 = abi.VolOpts.from_buffer_copy(gold["fog_opts"].tobytes())
+    ctx.set_tuning(fog_wave=0)
+    one = refapi.new_film(FW, FH)
+    ctx.render_volume(g, cam0, opts0, one)
+    ctx.set_tuning(fog_wave=1)
+    two = refapi.new_film(FW, FH)
+    ctx.render_volume(g, cam0, opts0, two)
+    assert np.array_equal(one, two)
     assert g.info.grid_class == abi.GRID_CLASS_FOG_VOLUME and g.info.source_type in (14, 16)
     cam, _ = fog_camera()
     opts = abi.VolOpts.from_buffer_copy(gold["fog_opts"].tobytes())
@@ -131,7 +157,7 @@ def test_quantised_upload_from_device_memory(ctx, oracle, gold):
     g.free(); h.free()
 
 
-def test_corrupt_quantised_grids_are_rejected(ctx, gold):
+def test_corrupt_quantised_grids_are_rejected(ctx, gold, mode):
     q = refapi.aligned_copy(gold["ls_fp8"])
     tree = 672
     lower_off = tree + int(np.frombuffer(q[tree + 8:tree + 16].tobytes(), np.int64)[0])
@@ -163,7 +189,7 @@ def test_corrupt_quantised_grids_are_rejected(ctx, gold):
     ok.free()
 
 
-def test_quantised_grid_against_the_reference_directly(ctx, ref):
+def test_quantised_grid_against_the_reference_directly(ctx, ref, mode):
     """a larger sphere than the fixture, all four types, reference run here: createNanoGrid<.., FpX> -> upload / nanoToOpenVDB -> rayTrace"""
     ls = ref.sphere(60.0, (3.0, -1.0, 2.0))
     Wd, Hd = 200, 160
@@ -200,3 +226,42 @@ def test_command_line_takes_a_quantised_file(ctx, oracle, gold, tmp_path):
     assert r.returncode == 0, r.stderr
     from tests.test_gpu_cli import read_ppm, to_bits
     assert np.array_equal(read_ppm(str(out)), to_bits(gold["film_fp8"]))
+
+
+def test_native_quantised_grid_memory_and_limits(ctx, ref, oracle):
+    """what rendering from the codes buys: the resident grid (buffer + halo blocks + masks) of an Fp8 / Fp16 grid against the float
+    one; arbitrary rays, spans and the things a native grid does not do (work counters, search iterations, sdfToFogVolume)"""
+    ls = ref.sphere(60.0, (3.0, -1.0, 2.0))
+    fbuf = ref.nanovdb(ls)
+    gf = ctx.upload(fbuf)
+    sizes = {"float": gf.info.resident_bytes}
+    rng = np.random.default_rng(9)
+    n = 4000
+    eyes = np.column_stack([rng.uniform(-70, 70, n), rng.uniform(-70, 70, n), np.full(n, 200.0)])
+    dirs = np.column_stack([rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), np.full(n, -1.0)])
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    rays = refapi.make_rays(eyes, dirs)
+    for gtype, kind in ((14, 1), (15, 2)):
+        q = ref.nanovdb_quantized(ls, gtype)
+        g = ctx.upload(q)
+        assert g.info.leaf_kind == kind and g.info.source_type == gtype and g.info.bytes == q.size
+        assert np.array_equal(g.download(), q)                                   # the buffer is resident as it was uploaded
+        sizes[gtype] = g.info.resident_bytes
+        og = oracle.open(q)
+        got = refapi.hits_to_dict(ctx.intersect(g, rays), n)
+        want = oracle.intersect(og, rays)
+        assert want["hit"].sum() > 1000 and got.tobytes() == want.tobytes()
+        cam = api.vdb_render_camera(64, 48, (40.0, 50.0, 190.0), (3.0, -1.0, 2.0))
+        with pytest.raises(api.VdbrtError) as e:
+            ctx.count_levelset(g, cam)
+        assert e.value.code == abi.ERR_UNSUPPORTED
+        with pytest.raises(api.VdbrtError) as e:
+            ctx.render_levelset(g, cam, api.make_shader(), refapi.new_film(64, 48), opts=ctx.ls_opts(iterations=2))
+        assert e.value.code == abi.ERR_UNSUPPORTED
+        with pytest.raises(api.VdbrtError) as e:
+            ctx.build_fog(g)
+        assert e.value.code == abi.ERR_UNSUPPORTED
+        g.free(); oracle.close(og)
+    print("resident bytes: float %d, Fp8 %d (%.2fx), Fp16 %d (%.2fx)" % (sizes["float"], sizes[14], sizes["float"] / sizes[14], sizes[15], sizes["float"] / sizes[15]))
+    assert sizes[14] < 0.5 * sizes["float"] and sizes[15] < 0.7 * sizes["float"]      # (a small grid: its internal nodes weigh as much as its leaves)
+    gf.free(); ref.free(ls)
