@@ -95,7 +95,10 @@ struct FogMarch {
     }
 };
 
-constexpr int kFogWaveBatch = 8;       // a phase runs when this many lanes want it, or when the other phases are starved
+#ifndef VDBRT_FOG_BATCH
+#define VDBRT_FOG_BATCH 4
+#endif
+constexpr int kFogWaveBatch = VDBRT_FOG_BATCH;       // a phase runs when this many lanes want it, or when the other phases are starved
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // 1. primary rays
@@ -165,11 +168,14 @@ k_fog_primary(const __grid_constant__ DevGrid g, const __grid_constant__ DevCame
             const bool act = busy && !pendExp;
             const bool marching = act && m.marching();
             const bool walking = act && !marching;
-            const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
-            const int nE = __popc(__ballot_sync(0xffffffffu, pendExp));
-            const bool runW = nW >= kFogWaveBatch || (nM < kFogWaveBatch && nE < kFogWaveBatch);
-            const bool runM = nM >= kFogWaveBatch || (nW < kFogWaveBatch && nE < kFogWaveBatch);
-            const bool runE = nE >= kFogWaveBatch || (nW < kFogWaveBatch && nM < kFogWaveBatch);
+            bool runW = true, runM = true, runE = true;
+            if (kFogWaveBatch > 1) {
+                const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
+                const int nE = __popc(__ballot_sync(0xffffffffu, pendExp));
+                runW = nW >= kFogWaveBatch || (nM < kFogWaveBatch && nE < kFogWaveBatch);
+                runM = nM >= kFogWaveBatch || (nW < kFogWaveBatch && nE < kFogWaveBatch);
+                runE = nE >= kFogWaveBatch || (nW < kFogWaveBatch && nM < kFogWaveBatch);
+            }
             // (2) walk: one unit of VolumeHDDA::hits
             if (walking && runW) { if (m.walkUnit(g, root, sm, accW, p.pstep, c)) fin = true; }
             __syncwarp();
@@ -295,11 +301,14 @@ k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParam
             const bool act = busy && !pendExp;
             const bool marching = act && m.marching();
             const bool walking = act && !marching;
-            const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
-            const int nE = __popc(__ballot_sync(0xffffffffu, pendExp));
-            const bool runW = nW >= kFogWaveBatch || (nM < kFogWaveBatch && nE < kFogWaveBatch);
-            const bool runM = nM >= kFogWaveBatch || (nW < kFogWaveBatch && nE < kFogWaveBatch);
-            const bool runE = nE >= kFogWaveBatch || (nW < kFogWaveBatch && nM < kFogWaveBatch);
+            bool runW = true, runM = true, runE = true;
+            if (kFogWaveBatch > 1) {
+                const int nW = __popc(__ballot_sync(0xffffffffu, walking)), nM = __popc(__ballot_sync(0xffffffffu, marching));
+                const int nE = __popc(__ballot_sync(0xffffffffu, pendExp));
+                runW = nW >= kFogWaveBatch || (nM < kFogWaveBatch && nE < kFogWaveBatch);
+                runM = nM >= kFogWaveBatch || (nW < kFogWaveBatch && nE < kFogWaveBatch);
+                runE = nE >= kFogWaveBatch || (nW < kFogWaveBatch && nM < kFogWaveBatch);
+            }
             bool lum = false;
             if (walking && runW) { if (m.walkUnit(g, root, sm, accW, p.sstep, c)) lum = true; }     // shadow spans exhausted: Luminance
             __syncwarp();
