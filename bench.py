@@ -463,7 +463,7 @@ def measure(rig, name, steps, warmup, sampler=None):
         rays_per_launch = rays / world                  # this rank's share of the frame's rays
         achieved = bpr * rays_per_launch / (kernel_ms_max * 1e-3) / 1e9
         pc = profile_constants(name) if world == 1 else None
-        kernel = "k_render_volume" if fog else "k_render_levelset"
+        kernel = "k_fog_shadow" if fog else "k_render_levelset"
         film_bytes = H * W * 16
         out = {
             "workload": wl["text"], "metric": "primary Mrays/s", "value": value, "unit": "Mrays/s", "ms_per_step": total_ms / steps,
@@ -484,7 +484,7 @@ def measure(rig, name, steps, warmup, sampler=None):
                          "l2_frac": pc.get("l2_throughput_frac") if pc else None, "issue_slot_util": pc.get("issue_slot_util") if pc else None,
                          "active_lanes": pc.get("active_lanes") if pc else None,
                          "peak_source": peak_src,
-                         "kernel": kernel + (" (+ %d more launches per frame: probe / long-ray round kernels)" % (launches_per_frame - 1) if launches_per_frame > 1 else ""),
+                         "kernel": kernel + ((" (+ %d more launches per frame: k_fog_primary / k_fog_resolve of the wavefront)" if fog else " (+ %d more launches per frame: probe / long-ray round kernels)") % (launches_per_frame - 1) if launches_per_frame > 1 else ""),
                          "kernel_ms": kernel_ms_max, "algorithmic_bytes_per_ray": bpr, "rays_per_launch": rays_per_launch, "counters": counters},
         }
         if clocks is not None:
