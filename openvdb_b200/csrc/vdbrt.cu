@@ -632,10 +632,10 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
     // With many tiles per warp the tail is a small part of the launch and the rounds cost about what they save (C2 whole frame
     // 2.72 -> 2.63 ms), and where the long rays cross empty space rather than graze a surface they lose outright (C4: 34.4 -> 36.7 ms,
     // 1/8 share 5.2 -> 5.5 ms: the scout walks empty cells no faster than the render kernel): profiles/r02_summary.md.  Default: fewer
-    // than kRoundsMaxTilesPerWarp tiles per warp.  VDBRT_LS_ROUNDS_ON / _OFF override.  WHICH rays are suspended is the tail rule
+    // than kRoundsMaxTilesPerSm tiles per SM.  VDBRT_LS_ROUNDS_ON / _OFF override.  WHICH rays are suspended is the tail rule
     // (ctx->ls_tail, vdbrt_kernels.cuh) unless VDBRT_LS_TAIL=0 selects round 1's per-tile budget.
     const double tilesPerWarp = double(tm.items) / (double(ctx->sm_count) * VDBRT_MINBLOCKS * (kBlockThreads / 32));
-    const bool automatic = tilesPerWarp < kRoundsMaxTilesPerWarp && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
+    const bool automatic = double(tm.items) / double(ctx->sm_count) < kRoundsMaxTilesPerSm && !(opts->flags & VDBRT_LS_ROUNDS_OFF);
     const bool rounds = ((opts->flags & VDBRT_LS_ROUNDS_ON) || automatic) && !dCounters && opts->spp == 1 && opts->iterations == 0 && grid->leaf_kind == kLeafFloat && (ctx->ls_tail != 0 || ctx->ls_budget != 0) && ctx->ls_rounds != 0;
     LongBufs lb = {};
     lb.budget = 0xffffffffu;

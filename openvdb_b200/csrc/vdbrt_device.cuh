@@ -518,12 +518,13 @@ struct LsHit { double time; int ix, iy, iz; double px, py, pz; float gx, gy, gz;
 // is a handful of ST.S / LD.S indexed by the level, instead of a three-way branch over 33 registers.
 template<int THREADS>
 struct WalkSmem {
-    double t1[3][THREADS], nx[3][THREADS], ny[3][THREADS], nz[3][THREADS];
+    double t0[3][THREADS], t1[3][THREADS], nx[3][THREADS], ny[3][THREADS], nz[3][THREADS];
     int vx[3][THREADS], vy[3][THREADS], vz[3][THREADS];
+    // t0 (the time the parent entered the cell it descends into) is only read when a ray is suspended inside a leaf: step() rewrites it
     __device__ __forceinline__ void park(int lvl, const Dda& d)
     {
         const int t = threadIdx.x;
-        t1[lvl][t] = d.t1; nx[lvl][t] = d.nx; ny[lvl][t] = d.ny; nz[lvl][t] = d.nz; vx[lvl][t] = d.vx; vy[lvl][t] = d.vy; vz[lvl][t] = d.vz;
+        t0[lvl][t] = d.t0; t1[lvl][t] = d.t1; nx[lvl][t] = d.nx; ny[lvl][t] = d.ny; nz[lvl][t] = d.nz; vx[lvl][t] = d.vx; vy[lvl][t] = d.vy; vz[lvl][t] = d.vz;
     }
     __device__ __forceinline__ void unpark(int lvl, Dda& d) const
     {
@@ -532,32 +533,26 @@ struct WalkSmem {
     }
 };
 
-// Traversal state of one ray.  lsAdvance() performs at most ONE level set-up, ONE cell probe, ONE stencil evaluation and
-// ONE DDA step, each of which exists exactly once in the instruction stream: all lanes of a warp run the same short
-// loop body whatever level they are on (the warp-synchronous render loop reconverges after every phase), and the hot
-// loop stays inside the instruction cache.  The rare, expensive phases (level set-up, stencil evaluation) are
-// deferred: a lane that needs one parks itself until enough lanes of its warp need the same phase (runA / runC).
+// Traversal state of one ray.  lsAdvance() performs at most ONE cell probe, ONE level set-up, ONE stencil evaluation (two for the
+// first one of a leaf visit, see lazyInit) and ONE DDA step, each of which exists exactly once in the instruction stream: all lanes
+// of a warp run the same short loop body whatever level they are on (the warp-synchronous render loop reconverges after every
+// phase), and the hot loop stays inside the instruction cache.  What is carried from one call to the next is kept small -- the
+// child range of a descent and the time of a voxel's evaluation live inside one call only, the parents' DDAs in shared memory.
 struct LsWalk {
     Dda cur;
     double T0;            // LinearSearchImpl::mT[0]
-    double c0, c1;        // pending child range: tester.setRange(dda.time(), dda.next())
-    double tq;            // time of the pending stencil evaluation
     float V0;             // LinearSearchImpl::mV[0]
     int lvl;              // 0: root-level DDA (4096^3 cells) 1: inside an upper node (128^3) 2: inside a lower node (8^3) 3: voxels
-    int pendInterp;       // 0 none, 1: tester.init, 2: tester(ijk,t), 3: getWorldPosAndNml
+    int pendInterp;       // 0 none, 3: the crossing was found in the previous call, getWorldPosAndNml at out.time is due
     bool skip;            // the current cell was already handled (we just came back up): only step
-    bool pendLevel;       // a DDA must be initialised over [c0,c1] at `lvl`
     bool pendStep;        // the current cell is done: step
-    bool emit;            // scout mode only: a leaf was found, its range is [c0,c1] (see lsAdvance<.., SCOUT>)
+    bool lazyInit;        // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
 
     __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }   // 12, 7, 3, 0
-    // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562)
-    __device__ __forceinline__ void begin(const Ray& ray)
-    {
-        lvl = 0; skip = false; pendLevel = true; pendStep = false; pendInterp = 0; T0 = 0.0; V0 = 0.f; c0 = ray.t0; c1 = ray.t1; tq = 0.0;
-        emit = false;
-    }
-    __device__ __forceinline__ bool runnable() const { return !pendLevel && !pendInterp; }
+    __device__ __forceinline__ void reset() { lvl = 0; skip = false; pendStep = false; pendInterp = 0; T0 = 0.0; V0 = 0.f; lazyInit = false; }
+    // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562); sets up the root-level
+    // DDA over the whole ray: LevelSetHDDA<TreeT, RootLevel>::test's math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150)
+    __device__ __forceinline__ void begin(const Ray& ray) { reset(); cur.init(ray, ray.t0, ray.t1, shiftOf(0)); }
 };
 
 enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
@@ -565,23 +560,26 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 // SYNC = true: the caller runs a warp-synchronous loop in which ALL 32 lanes call lsAdvance every iteration (lanes
 // without a ray pass active = false).  __syncwarp() between the phases makes the warp reconverge after each phase and
 // stops the compiler from cloning the later phases per control-flow path.  SYNC = false: plain per-thread use.
-// SCOUT = true: the walk never enters a leaf.  A leaf found by the lower node's DDA is reported instead (w.emit with its
-// time range in w.c0/w.c1, the cursor pointing at it) and the DDA steps on as if the leaf had returned "no hit": the
-// leaf visits of one ray are independent of each other (the tester is re-initialised per leaf, DDA.h:172-173), so they
-// can be marched by other threads (vdbrt_kernels.cuh, long-ray rounds).
 // REFINE = true: LinearSearchImpl<GridT, Iterations> with Iterations = `iters` > 0 -- after the zero crossing the hit time is refined by
 // `iters` secant steps, each one stencil evaluation at the current estimate (tools/RayIntersector.h:630-636).  A separate instantiation:
 // the default kernels (Iterations = 0, what vdb_render and tools::rayTrace use) do not carry the loop.
-template<bool COUNT, bool SYNC, int THREADS, bool SCOUT = false, bool REFINE = false, int LEAF = kLeafFloat>
-__device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
+//
+// tester.init(dda.time()) (:597-601) evaluates the stencil at the leaf's entry time only to fill mT[0], mV[0], which nothing reads
+// before the first voxel of the visit that passes the value gate (:622-624).  That evaluation is therefore made together with the
+// first gated one (lazyInit) and never for the leaf visits in which no voxel passes: 1.4 of 8.6 evaluations per ray on C2.  Same
+// values in the same order -- the stencil's cache only makes moveTo cheaper, never changes what it returns.
+template<bool COUNT, bool SYNC, int THREADS, bool REFINE = false, int LEAF = kLeafFloat>
+__device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
                                          TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
                                          LsWalk& w, LsHit& out, Counters& c, int iters = 0)
 {
     Dda& cur = w.cur;
     int status = kWalkContinue;
-    // ---- phase B: probe the current cell.  (B comes before A: a lane that finds a leaf sets up the leaf's DDA and evaluates the
-    // tester's first value in the SAME call, one warp iteration per leaf visit less than with the set-up first.)
-    if (active && !w.pendLevel && !w.pendInterp && !w.pendStep) {
+    int purpose = w.pendInterp;          // 2: tester(ijk, t) of the voxel probed in this call
+    bool level = false;                  // a child was found: its DDA is set up over [c0,c1] in this call
+    double c0 = 0.0, c1 = 0.0, tq = out.time;
+    // ---- phase B: probe the current cell
+    if (active && !purpose && !w.pendStep) {
         if (w.skip) { w.skip = false; w.pendStep = true; }
         else {
             const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
@@ -590,13 +588,10 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 if (COUNT) { if (w.lvl == 0) ++c.root; else if (w.lvl == 1) ++c.upper; else ++c.lower; }
                 if (depth <= 2 - w.lvl) {
                     // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
-                    w.c0 = cur.t0; w.c1 = cur.next();
-                    if (SCOUT && w.lvl == 2) { w.emit = true; w.pendStep = true; }
-                    else {
-                        sm.park(w.lvl, cur);
-                        ++w.lvl;
-                        w.pendLevel = true;
-                    }
+                    c0 = cur.t0; c1 = cur.next();
+                    sm.park(w.lvl, cur);
+                    ++w.lvl;
+                    level = true;
                 } else w.pendStep = true;
             } else {
                 // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
@@ -611,23 +606,20 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                     V = haloValue<LEAF>(g.halo, hi, uint32_t(cur.vx & 7), uint32_t(cur.vy & 7), uint32_t(cur.vz & 7));
                     on = maskBit(TreeCursor::node(g, acc.n0) + kLeafVMask, leafOffset(cur.vx, cur.vy, cur.vz));
                 } else on = acc.template valueAt<LEAF>(g, s, depth, cur.vx, cur.vy, cur.vz, V);
-                if (on && V > vmin && V < vmax) { w.pendInterp = 2; w.tq = cur.next(); }
+                if (on && V > vmin && V < vmax) { purpose = 2; tq = cur.next(); }
                 w.pendStep = true;
             }
         }
     }
     if (SYNC) __syncwarp();
     // ---- phase A: level set-up: math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
-    if (active && w.pendLevel && runA) {
-        cur.init(ray, w.c0, w.c1, LsWalk::shiftOf(w.lvl));
-        w.pendLevel = false;
-        if (w.lvl == 3) { w.pendInterp = 1; w.tq = w.c0; }               // tester.init(dda.time()) (:597-601)
+    if (level) {
+        cur.init(ray, c0, c1, LsWalk::shiftOf(w.lvl));
+        if (w.lvl == 3) { w.lazyInit = true; w.T0 = c0; }               // tester.init(dda.time()) (:597-601), evaluated on demand
     }
     if (SYNC) __syncwarp();
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
-    if (active && w.pendInterp && runC) {
-        const int purpose = w.pendInterp;
-        double tq = w.tq;
+    if (active && purpose) {
         w.pendInterp = 0;
         // refinement state (REFINE, purpose 3): mT[0..1], mV[0..1] of the crossing -- mT[1] is the voxel's exit time again (the DDA has
         // not moved), mV[1] was left in out.gx by the iteration that found the crossing
@@ -635,8 +627,11 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
         float rV0 = w.V0, rV1 = REFINE ? out.gx : 0.f;
 #pragma unroll 1
         for (int n = 0;; ++n) {
-            const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
+            const bool initPass = purpose == 2 && w.lazyInit;
+            const double te = initPass ? w.T0 : tq;
+            const double px = ray.ex + ray.dx * te, py = ray.ey + ray.dy * te, pz = ray.ez + ray.dz * te;
             st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
+            if (initPass) { w.V0 = st.interpolation(px, py, pz) - iso; w.lazyInit = false; n = -1; continue; }   // mV[0] = interpValue(mT[0])
             if (purpose == 3) {
                 if (REFINE && n < iters) {
                     // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
@@ -652,12 +647,12 @@ __device__ __forceinline__ int lsAdvance(bool active, bool runA, bool runC, cons
                 status = kWalkHit;
             } else {
                 const float V1 = st.interpolation(px, py, pz) - iso;
-                if (purpose == 2 && w.V0 * V1 <= 0.0f) {                         // math::ZeroCrossing (math/Math.h:821)
+                if (w.V0 * V1 <= 0.0f) {                                          // math::ZeroCrossing (math/Math.h:821)
                     out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
                     out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
                     if (REFINE) out.gx = V1;
-                    w.pendInterp = 3; w.tq = out.time; w.pendStep = false;
-                } else { w.T0 = tq; w.V0 = V1; }                                  // init: mT[0],mV[0]; no crossing: slide
+                    w.pendInterp = 3; w.pendStep = false;
+                } else { w.T0 = tq; w.V0 = V1; }                                  // no crossing: slide
             }
             break;
         }
@@ -689,7 +684,7 @@ __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSm
     LsWalk w; w.begin(ray);
 #pragma unroll 1
     for (;;) {
-        const int r = lsAdvance<COUNT, false, THREADS, false, true, LEAF>(true, true, true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
+        const int r = lsAdvance<COUNT, false, THREADS, true, LEAF>(true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
         if (r != kWalkContinue) return r == kWalkHit;
     }
 }

@@ -79,8 +79,14 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
 // are re-fed from the atomic queue in batches (one atomicAdd per refill, tickets numbered in tile order so a warp's
 // lanes stay spatially coherent), instead of idling until the slowest ray of a fixed tile is done.
 // ------------------------------------------------------------------------------------------------------------
+// CTAs per SM.  5 (96 registers; what ptxas then spills is the pixel bookkeeping and the hit record, touched once per ray) against 4
+// (122 registers, no spills): C4 34.1 -> 32.0 ms, C2 2.68 -> 2.60 ms; 6 (80 registers) spills inside the traversal and loses (36.5 / 3.1 ms).
+// The LONG instantiations (small shares of a frame, bounded by their slowest tile rather than by throughput) keep 4: C2 1/8 0.60 against 0.76 ms.
 #ifndef VDBRT_MINBLOCKS
-#define VDBRT_MINBLOCKS 4
+#define VDBRT_MINBLOCKS 5
+#endif
+#ifndef VDBRT_MINBLOCKS_LONG
+#define VDBRT_MINBLOCKS_LONG 4
 #endif
 // How a warp is fed (all run-time, warp-uniform; launchLevelSet fills it in):
 //   * the queue hands out STRIPS of `strip_tiles` consecutive 8x4 tiles (consecutive tiles of a macro-tile row are neighbours in x);
@@ -161,16 +167,15 @@ constexpr uint32_t kDefaultTail = 48;     // tail rule: warp iterations a tile m
 constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
 constexpr int kDefaultRounds = 2;
-constexpr double kRoundsMaxTilesPerWarp = 12.0;   // rounds are on by default only below this (see launchLevelSet)
+constexpr double kRoundsMaxTilesPerSm = 192.0;   // rounds are on by default only below this (12 tiles per warp at 16 warps / SM; see launchLevelSet)
 
 struct LongRay {
     Ray ray;                          // index space, clipped
     double wdx, wdy, wdz;             // world direction (shader input)
     Dda cur; int lvl;                 // the DDA of the level the walk is on (<= 2 while suspended)
     DdaSave park[2];                  // suspended parents: root level, upper level
-    double c0, c1;
     int kx, ky, kz; uint32_t n2, n1, n0;
-    uint32_t pix, flags;              // flags: skip | pendLevel << 1 | pendStep << 2
+    uint32_t pix, flags;              // flags: skip | pendStep << 2
     uint32_t segBase, segCount, best, state;   // this round's segments; index of the first one that hit; 1 = walked out of the grid
 };
 struct SegIn { double t0, t1; int kx, ky, kz; uint32_t n2, n1, n0; };
@@ -187,22 +192,18 @@ __device__ __forceinline__ void suspendRay(LongRay& r, const Ray& ray, double wd
 {
     const int t = threadIdx.x;
     r.ray = ray; r.wdx = wdx; r.wdy = wdy; r.wdz = wdz;
-    uint32_t flags = (w.skip ? 1u : 0u) | (w.pendLevel ? 2u : 0u) | (w.pendStep ? 4u : 0u);
+    uint32_t flags = (w.skip ? 1u : 0u) | (w.pendStep ? 4u : 0u);
     if (w.lvl == 3) {
-        // rewind to the lower node's DDA standing on this leaf: the scout finds the leaf again and the march redoes the visit.
-        // (pendLevel: the leaf's own DDA was not set up yet, `cur` still is the lower node's)
+        // rewind to the lower node's DDA standing on this leaf: the scout finds the leaf again and the march redoes the visit
         r.lvl = 2; flags = 0u;
-        r.cur.t0 = w.pendLevel ? w.cur.t0 : w.c0;
-        r.cur.t1 = w.pendLevel ? w.cur.t1 : sm.t1[2][t]; r.cur.nx = w.pendLevel ? w.cur.nx : sm.nx[2][t];
-        r.cur.ny = w.pendLevel ? w.cur.ny : sm.ny[2][t]; r.cur.nz = w.pendLevel ? w.cur.nz : sm.nz[2][t];
-        r.cur.vx = w.pendLevel ? w.cur.vx : sm.vx[2][t]; r.cur.vy = w.pendLevel ? w.cur.vy : sm.vy[2][t]; r.cur.vz = w.pendLevel ? w.cur.vz : sm.vz[2][t];
+        r.cur.t0 = sm.t0[2][t]; r.cur.t1 = sm.t1[2][t]; r.cur.nx = sm.nx[2][t]; r.cur.ny = sm.ny[2][t]; r.cur.nz = sm.nz[2][t];
+        r.cur.vx = sm.vx[2][t]; r.cur.vy = sm.vy[2][t]; r.cur.vz = sm.vz[2][t];
     } else { r.cur = w.cur; r.lvl = w.lvl; }
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
         r.park[l].t1 = sm.t1[l][t]; r.park[l].nx = sm.nx[l][t]; r.park[l].ny = sm.ny[l][t]; r.park[l].nz = sm.nz[l][t];
         r.park[l].vx = sm.vx[l][t]; r.park[l].vy = sm.vy[l][t]; r.park[l].vz = sm.vz[l][t];
     }
-    r.c0 = w.c0; r.c1 = w.c1;
     r.kx = acc.kx; r.ky = acc.ky; r.kz = acc.kz; r.n2 = acc.n2; r.n1 = acc.n1; r.n0 = acc.n0;
     r.pix = uint32_t(pix); r.flags = flags;
     r.segBase = 0u; r.segCount = 0u; r.best = kNoHit; r.state = 0u;
@@ -212,7 +213,7 @@ template<int THREADS>
 __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w, WalkSmem<THREADS>& sm, TreeCursor& acc)
 {
     ray = r.ray;
-    w.begin(ray);
+    w.reset();
     w.cur = r.cur; w.lvl = r.lvl;
     const int t = threadIdx.x;
 #pragma unroll
@@ -220,15 +221,14 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
         sm.t1[l][t] = r.park[l].t1; sm.nx[l][t] = r.park[l].nx; sm.ny[l][t] = r.park[l].ny; sm.nz[l][t] = r.park[l].nz;
         sm.vx[l][t] = r.park[l].vx; sm.vy[l][t] = r.park[l].vy; sm.vz[l][t] = r.park[l].vz;
     }
-    w.c0 = r.c0; w.c1 = r.c1;
     acc.kx = r.kx; acc.ky = r.ky; acc.kz = r.kz; acc.n2 = r.n2; acc.n1 = r.n1; acc.n0 = r.n0;
-    w.skip = (r.flags & 1u) != 0u; w.pendLevel = (r.flags & 2u) != 0u; w.pendStep = (r.flags & 4u) != 0u;
+    w.skip = (r.flags & 1u) != 0u; w.pendStep = (r.flags & 4u) != 0u;
 }
 
 // MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
 // REFINE = true: LinearSearchImpl's secant refinements (p.iters > 0), see lsAdvance.
 template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false, int LEAF = kLeafFloat>
-__global__ void __launch_bounds__(kBlockThreads, VDBRT_MINBLOCKS)
+__global__ void __launch_bounds__(kBlockThreads, LONG ? VDBRT_MINBLOCKS_LONG : VDBRT_MINBLOCKS)
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
                   AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb,
@@ -263,7 +263,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     size_t pix = 0;
     unsigned long long n = 0;
     float4 col = make_float4(0.f, 0.f, 0.f, 1.f);       // the pixel's background is re-read when a ray misses (the film is written once, at the end)
-    Ray ray; double wdx = 0.0, wdy = 0.0, wdz = 0.0;
+    Ray ray;
     LsWalk walk; LsHit h;
     ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray);
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
@@ -308,7 +308,9 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
                 if (base + __popc(m) > lb.capLong) longFull = true;
                 if (sus && idx < lb.capLong) {
-                    suspendRay(lb.rays[idx], ray, wdx, wdy, wdz, walk, wsm, acc, pix);
+                    Ray wr;
+                    cameraRay(cam, px, py, 0.5, 0.5, wr);                 // LONG kernels are one sample per pixel
+                    suspendRay(lb.rays[idx], ray, wr.dx, wr.dy, wr.dz, walk, wsm, acc, pix);
                     rayOn = false; hasPix = false;
                 }
             }
@@ -391,7 +393,6 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             const bool first = !MULTI || k == 0;
             cameraRay(cam, px, py, first ? 0.5 : p.jitter[n & 15], first ? 0.5 : p.jitter[(n + 1) & 15], ray);
             if (MULTI && !first) n += 2;
-            wdx = ray.dx; wdy = ray.dy; wdz = ray.dz;               // world direction for the shader
             if (COUNT) ++c.rays;
             // intersectsWS: setWorldRay = worldToIndex + clip (tools/RayIntersector.h:558-562)
             worldToIndex(g, ray);
@@ -414,7 +415,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
-                const int r = lsAdvance<COUNT, true, kBlockThreads, false, REFINE, LEAF>(rayOn, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
+                const int r = lsAdvance<COUNT, true, kBlockThreads, REFINE, LEAF>(rayOn, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
                 if (rayOn) status = r;
             }
             __syncwarp();
@@ -424,7 +425,12 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 float4 s;
                 if (hit) {
                     if (COUNT) ++c.hits;
-                    s = shadeHit<AUX>(g, sh, h, ray, wdx, wdy, wdz, pix, aux, !MULTI || k == 0);
+                    // the shader wants the WORLD direction of the ray: rebuilt from the camera here (the same arithmetic on the same
+                    // inputs) rather than carried through the traversal in six registers
+                    Ray wr;
+                    const bool first = !MULTI || k == 0;
+                    cameraRay(cam, px, py, first ? 0.5 : p.jitter[(n - 2) & 15], first ? 0.5 : p.jitter[(n - 1) & 15], wr);
+                    s = shadeHit<AUX>(g, sh, h, ray, wr.dx, wr.dy, wr.dz, pix, aux, first);
                 } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
                 if (AUX && (!MULTI || k == 0) && aux.hit) aux.hit[pix] = hit ? 1 : 0;
                 rayOn = false;
@@ -496,7 +502,7 @@ k_probe_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevC
                 LsHit h = {};
 #pragma unroll 1
                 for (; it < cap; ++it)
-                    if (lsAdvance<false, false, kBlockThreads>(true, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, w, h, c) != kWalkContinue) break;
+                    if (lsAdvance<false, false, kBlockThreads>(true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, w, h, c) != kWalkContinue) break;
             }
         }
         const uint32_t strip = item / stripTiles;
@@ -587,7 +593,6 @@ k_long_scout(const __grid_constant__ DevGrid g, const __grid_constant__ DevShade
         uint32_t emitted = 0;
         bool exhausted = false;
         bool advance = walk.pendStep || walk.skip;
-        if (walk.pendLevel) cur.init(ray, walk.c0, walk.c1, LsWalk::shiftOf(walk.lvl));
 #pragma unroll 1
         for (;;) {
             if (advance) {
@@ -635,7 +640,7 @@ k_long_scout(const __grid_constant__ DevGrid g, const __grid_constant__ DevShade
                 }
             }
         }
-        walk.pendLevel = false; walk.pendStep = false; walk.skip = false;
+        walk.pendStep = false; walk.skip = false;
         suspendRay(*r, ray, r->wdx, r->wdy, r->wdz, walk, wsm, acc, size_t(r->pix));
         r->segBase = sb; r->segCount = emitted; r->state = exhausted ? 1u : 0u;
     }
@@ -662,17 +667,22 @@ k_long_march(const __grid_constant__ DevGrid g, const __grid_constant__ LongBufs
         TreeCursor acc; acc.kx = sg.kx; acc.ky = sg.ky; acc.kz = sg.kz; acc.n2 = sg.n2; acc.n1 = sg.n1; acc.n0 = sg.n0;
         Stencil st; st.reset();
         Dda dda; dda.init(ray, sg.t0, sg.t1, 0);
-        // tester.init(dda.time()) (:597-601)
-        double T0 = sg.t0, px = ray.ex + ray.dx * T0, py = ray.ey + ray.dy * T0, pz = ray.ez + ray.dz * T0;
-        st.template moveTo<false>(g, root, acc, px, py, pz, c);
-        float V0 = st.interpolation(px, py, pz) - iso;
-        bool hit = false;
+        // tester.init(dda.time()) (:597-601) is evaluated with the first voxel that passes the value gate (see lsAdvance)
+        double T0 = sg.t0, px, py, pz;
+        float V0 = 0.f;
+        bool lazyInit = true, hit = false;
         SegOut o;
         do {
             // tester(dda.voxel(), dda.next()) (:620-644)
             float V;
             const int depth = acc.descend(g, root, dda.vx, dda.vy, dda.vz);
             if (acc.valueAt(g, root, depth, dda.vx, dda.vy, dda.vz, V) && V > vmin && V < vmax) {
+                if (lazyInit) {
+                    px = ray.ex + ray.dx * T0; py = ray.ey + ray.dy * T0; pz = ray.ez + ray.dz * T0;
+                    st.template moveTo<false>(g, root, acc, px, py, pz, c);
+                    V0 = st.interpolation(px, py, pz) - iso;
+                    lazyInit = false;
+                }
                 const double tq = dda.next();
                 px = ray.ex + ray.dx * tq; py = ray.ey + ray.dy * tq; pz = ray.ez + ray.dz * tq;
                 st.template moveTo<false>(g, root, acc, px, py, pz, c);
@@ -718,7 +728,7 @@ k_long_finish(const __grid_constant__ DevGrid g, const __grid_constant__ DevShad
         resumeRay(*r, ray, walk, wsm, acc);
         int status;
 #pragma unroll 1
-        do { status = lsAdvance<false, false, kBlockThreads>(true, true, true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
+        do { status = lsAdvance<false, false, kBlockThreads>(true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
         writeLongPixel<AUX>(g, sh, p, film, aux, *r, status == kWalkHit, h);
     }
 }

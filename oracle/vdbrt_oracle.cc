@@ -351,10 +351,16 @@ struct BoxStencil {
 // ------------------------------------------------------------------------------------------------------------
 struct Counters { uint64_t probes[3] = {0, 0, 0}, voxel = 0, refills = 0, pSamples = 0, sSamples = 0, sRays = 0, hits = 0, rays = 0; };
 
+// oracle_set_lazy_init (test knob): evaluate tester.init's mV[0] only when the first voxel of the leaf visit passes the value gate --
+// the evaluation order of the CUDA kernels (lsAdvance, vdbrt_device.cuh).  mV[0] is read nowhere else (RayIntersector.h:620-644), so the
+// results must be identical and only the stencil refill count drops; tests/test_oracle_vs_reference.py checks exactly that.
+static int g_lazyInit = 0;
+
 struct Tester {
     const oracle_grid& g; Access acc; BoxStencil st; Ray ray;
     double time = 0; float V[2]; double T[2]; float iso, vmin, vmax; Coord hitIjk{0, 0, 0};
     int iterations = 0;                                         // LinearSearchImpl<GridT, Iterations, RealT>
+    bool lazy = g_lazyInit != 0, pendingInit = false;
     Counters* ctr;
     Tester(const oracle_grid& grid, float isoValue, Counters* c) : g(grid), acc(grid), iso(isoValue), ctr(c) {
         vmin = isoValue - float(2 * grid.voxelSize[0]);         // RayIntersector.h:530-531 (as float)
@@ -363,7 +369,7 @@ struct Tester {
     bool setIndexRay(const Ray& r) { ray = r; return ray.clip(g.nodeBBox.mn, g.nodeBBox.mx); }        // :548-552
     bool setWorldRay(const Ray& r) { ray = worldToIndex(g, r); return ray.clip(g.nodeBBox.mn, g.nodeBBox.mx); } // :558-562
     double interpValue(double t) { const Vec3 pos = ray(t); st.moveTo(acc, pos); return st.interpolation(pos) - iso; } // :652-657
-    void init(double t0) { T[0] = t0; V[0] = float(interpValue(t0)); }                                 // :597-601
+    void init(double t0) { T[0] = t0; if (lazy) pendingInit = true; else V[0] = float(interpValue(t0)); }   // :597-601
     void setRange(double a, double b) { ray.t0 = a; ray.t1 = b; }
     template<int LEVEL> bool hasNode(const Coord& c) {                                                  // :609-613
         if (ctr) ++ctr->probes[LEVEL];
@@ -375,6 +381,7 @@ struct Tester {
         if (ctr) ++ctr->voxel;
         float v;
         if (acc.probeValue(ijk, v) && v > vmin && v < vmax) {
+            if (pendingInit) { V[0] = float(interpValue(T[0])); pendingInit = false; }
             T[1] = t; V[1] = float(interpValue(t));
             if (V[0] * V[1] <= 0.0f) {                                                                  // math::ZeroCrossing (Math.h:821)
                 time = T[0] + (T[1] - T[0]) * V[0] / (V[0] - V[1]);                                    // interpTime :646-650
@@ -812,6 +819,8 @@ int oracle_intersect_levelset(const oracle_grid* g, const vdbrt_ray* rays, uint6
 {
     return oracle_intersect_levelset_iter(g, rays, n, space, iso, 0u, hits);
 }
+
+void oracle_set_lazy_init(int on) { g_lazyInit = on; }
 
 int oracle_intersect_levelset_iter(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso, uint32_t iterations, vdbrt_hit* hits)
 {

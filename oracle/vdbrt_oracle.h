@@ -31,6 +31,9 @@ int  oracle_render_volume(const oracle_grid* g, const vdbrt_camera* cam, const v
                           vdbrt_film* film, vdbrt_counters* ctr, int threads);
 int  oracle_intersect_levelset(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso,
                                vdbrt_hit* hits);
+/* test knob: testers created after this call evaluate tester.init's value on demand (the CUDA kernels' evaluation order; same results, fewer
+ * stencil refills) */
+void oracle_set_lazy_init(int on);
 /* LinearSearchImpl<GridT, Iterations>: `iterations` secant refinements of the hit time (tools/RayIntersector.h:630-636) */
 int  oracle_intersect_levelset_iter(const oracle_grid* g, const vdbrt_ray* rays, uint64_t n, uint32_t space, float iso,
                                     uint32_t iterations, vdbrt_hit* hits);

@@ -436,6 +436,10 @@ class Oracle:
                                                C.byref(ctr) if counters else None, threads))
         return ctr
 
+    def set_lazy_init(self, on):
+        """test knob: tester.init's value is evaluated on demand (the CUDA kernels' evaluation order); same results, fewer refills"""
+        self.L.oracle_set_lazy_init(1 if on else 0)
+
     def film_over(self, top, bottom):
         """top = top.over(bottom), Film::RGBA::over per pixel (tools/RayTracer.h:252-259)"""
         assert top.shape == bottom.shape and top.dtype == np.float32 and bottom.dtype == np.float32

@@ -298,12 +298,20 @@ def test_work_counters_match_oracle(ctx, oracle, dsphere, sphere100):
     cam = api.vdb_render_camera(W, H, (0, 0, 300), (0, 0, 0))
     c = ctx.count_levelset(dsphere, cam).as_dict()
     film = refapi.new_film(W, H)
-    _, oc = oracle.render_levelset(sphere100.oracle_handle, cam, api.make_shader(), film, counters=True)
+    _, eager = oracle.render_levelset(sphere100.oracle_handle, cam, api.make_shader(), film, counters=True)
+    # the kernels evaluate tester.init's value on demand (lsAdvance); the oracle counts that way with its lazy-init knob, which
+    # tests/test_oracle_vs_reference.py::test_lazy_tester_init_is_exact pins against the reference
+    try:
+        oracle.set_lazy_init(True)
+        _, oc = oracle.render_levelset(sphere100.oracle_handle, cam, api.make_shader(), film, counters=True)
+    finally:
+        oracle.set_lazy_init(False)
     o = oc.as_dict()
     for k in ("rays", "root_probes", "upper_probes", "lower_probes", "voxel_probes", "hits"):
-        assert c[k] == o[k], k
+        assert c[k] == o[k] == eager.as_dict()[k], k
     # the GPU starts every ray with a cold stencil, the CPU keeps it across pixels: refills differ by < 1 %
     assert abs(c["stencil_refills"] - o["stencil_refills"]) < 0.01 * o["stencil_refills"]
+    assert o["stencil_refills"] < eager.as_dict()["stencil_refills"]
 
 
 def test_config2_full_size_vs_oracle(ctx, oracle):

@@ -63,6 +63,33 @@ def test_levelset_records_bit_exact(ref, oracle, sphere100):
     assert octr.hits == int(raux.hit.sum())
 
 
+def test_lazy_tester_init_is_exact(ref, oracle, sphere100, torus_small):
+    """The CUDA kernels evaluate tester.init's mV[0] only when the first voxel of a leaf visit passes the value gate (lsAdvance).  The
+    same change made to the oracle must leave every record of every pixel as the REFERENCE has it, and only drop stencil refills."""
+    d = refapi.camera_desc(160, 120, translation=(0, 0, 300), lookat=(0, 0, 0))
+    raux, rctr, _ = ref.levelset_records(sphere100.ref_handle, d)
+    try:
+        oracle.set_lazy_init(True)
+        film = refapi.new_film(160, 120)
+        oaux, octr = oracle.render_levelset(sphere100.oracle_handle, ref.camera_pod(d), refapi.shader(), film, aux=True, counters=True)
+        for k in ("hit", "ijk", "t_index", "t_world", "xyz", "nml"):
+            assert np.array_equal(getattr(raux, k), getattr(oaux, k)), k
+        for k in ("root_probes", "upper_probes", "lower_probes", "voxel_probes"):
+            assert getattr(rctr, k) == getattr(octr, k), k
+        assert octr.stencil_refills < rctr.stencil_refills
+        # grazing rays (many leaf visits without a gated voxel), all shaders' inputs, two samples per pixel, refinements
+        d2 = refapi.camera_desc(128, 96, translation=(0.0, 60.0, 120.0), lookat=(0, 0, 0))
+        for iters in (0, 2):
+            f_ref = refapi.new_film(128, 96)
+            ref.render_levelset_iter(torus_small.ref_handle, d2, refapi.shader(abi.SHADER_NORMAL), f_ref, iters, spp=2, seed=3)
+            f_orc = refapi.new_film(128, 96)
+            oracle.render_levelset(torus_small.oracle_handle, ref.camera_pod(d2), refapi.shader(abi.SHADER_NORMAL), f_orc, spp=2,
+                                   jitter=ref.jitter_table(3), iterations=iters)
+            assert np.array_equal(f_ref, f_orc)
+    finally:
+        oracle.set_lazy_init(False)
+
+
 def test_levelset_jittered_supersampling(ref, oracle, sphere100):
     d = refapi.camera_desc(96, 64, translation=(0, 0, 300), lookat=(0, 0, 0))
     for spp, seed in ((2, 0), (5, 3), (16, 0)):
