@@ -91,7 +91,8 @@ __device__ __forceinline__ unsigned long long ldg64(const uint8_t* p) { return _
 __device__ __forceinline__ long long ldgs64(const uint8_t* p) { return __ldg(reinterpret_cast<const long long*>(p)); }
 __device__ __forceinline__ uint32_t ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ float ldgf(const uint8_t* p) { return __ldg(reinterpret_cast<const float*>(p)); }
-__device__ __forceinline__ bool maskBit(const uint8_t* mask, uint32_t n) { return (ldg64(mask + 8u * (n >> 6)) >> (n & 63u)) & 1ull; }
+// bit n of a nanovdb::Mask (little-endian 64-bit words): read through the 32-bit half that holds it, a 32-bit shift is one instruction
+__device__ __forceinline__ bool maskBit(const uint8_t* mask, uint32_t n) { return (ldg32(mask + 4u * (n >> 5)) >> (n & 31u)) & 1u; }
 
 // value n of a leaf (LeafData<float>::getValue / LeafData<FpX>::getValue)
 template<int LEAF>
@@ -186,18 +187,19 @@ struct TreeCursor {
                 // entry is only a child offset -- relative to this InternalData (:3190-3199) -- when the mask bit is set
                 const uint8_t* u = node(g, n2);
                 const uint32_t n = upperOffset(x, y, z);
-                const unsigned long long word = ldg64(u + kUpperCMask + 8u * (n >> 6));
+                const uint32_t word = ldg32(u + kUpperCMask + 4u * (n >> 5));
                 const long long ent = ldgs64(u + kUpperTable + 8u * n);
-                if ((word >> (n & 63u)) & 1ull) n1 = n2 + uint32_t(int(ent >> 5));      // offsets are multiples of 32
+                if ((word >> (n & 31u)) & 1u) n1 = n2 + uint32_t(int(ent >> 5));        // offsets are multiples of 32
             }
         }
         n0 = 0u;
         if (n1) {
             const uint8_t* l = node(g, n1);
             const uint32_t n = lowerOffset(x, y, z);
-            const unsigned long long word = ldg64(l + kLowerCMask + 8u * (n >> 6));
+            const uint32_t word = ldg32(l + kLowerCMask + 4u * (n >> 5));
+            // (loading the entry only when the bit is set -- most cells of a lower node are empty -- was measured: no gain, +1 % on C2)
             const long long ent = ldgs64(l + kLowerTable + 8u * n);
-            if ((word >> (n & 63u)) & 1ull) n0 = n1 + uint32_t(int(ent >> 5));
+            if ((word >> (n & 31u)) & 1u) n0 = n1 + uint32_t(int(ent >> 5));
         }
         kx = x; ky = y; kz = z;
         return n0 ? 0 : (n1 ? 1 : (n2 ? 2 : 3));
@@ -427,7 +429,10 @@ struct Dda {
         nz = r.dz == 0.0 ? DBL_MAX : t0 + az;
     }
     // DDA::step (DDA.h:83-90); MinIndex ties go to the largest index (math/Math.h:999-1007).
-    // step/delta are rebuilt from the ray: step = 0/+DIM/-DIM, delta = DBL_MAX or double(step)*inv (DDA.h:61-73).
+    // step/delta are rebuilt from the ray: step = +-DIM with the sign of 1/dir, delta = double(step) * (1/dir) = DIM * |1/dir| (DDA.h:61-73;
+    // the same product, IEEE multiplication is symmetric in the signs).  An axis with dir == 0 has next == DBL_MAX (init) and can only
+    // be the minimum when the other two are DBL_MAX as well, i.e. when this step fails (t0 = DBL_MAX > t1) and the DDA is dropped by
+    // the caller -- so the reference's special case for it (step 0, delta DBL_MAX) needs no code here.
     // Branch-free: the three axes are handled by selects so that the lanes of a warp do not split on the axis.
     __device__ __forceinline__ bool step(const Ray& r, int shift)
     {
@@ -437,10 +442,10 @@ struct Dda {
         m = a2 ? nz : m;
         const bool a1 = b1 && !a2, a0 = !b1 && !a2;
         t0 = m;
-        const double d = a2 ? r.dz : (a1 ? r.dy : r.dx), iv = a2 ? r.iz : (a1 ? r.iy : r.ix);
-        const bool zero = d == 0.0, pos = iv > 0;
-        const int st = zero ? 0 : (pos ? (1 << shift) : -(1 << shift));
-        const double nn = m + (zero ? DBL_MAX : signedDim(shift, pos) * iv);     // mNext[axis] += mDelta[axis]
+        const double iv = a2 ? r.iz : (a1 ? r.iy : r.ix);
+        const int dim = 1 << shift;
+        const int st = __double2hiint(iv) < 0 ? -dim : dim;
+        const double nn = m + __hiloint2double((1023 + shift) << 20, 0) * fabs(iv);     // mNext[axis] += mDelta[axis]
         nx = a0 ? nn : nx; ny = a1 ? nn : ny; nz = a2 ? nn : nz;
         vx += a0 ? st : 0; vy += a1 ? st : 0; vz += a2 ? st : 0;
         return t0 <= t1;
@@ -539,20 +544,25 @@ struct WalkSmem {
 // phase), and the hot loop stays inside the instruction cache.  What is carried from one call to the next is kept small -- the
 // child range of a descent and the time of a voxel's evaluation live inside one call only, the parents' DDAs in shared memory.
 struct LsWalk {
+    enum : uint32_t {
+        kSkip = 1u,       // the current cell was already handled (we just came back up): only step
+        kStep = 2u,       // the current cell is done: step
+        kLazy = 4u,       // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
+        kInterp = 8u      // the crossing was found in the previous call, getWorldPosAndNml at out.time is due
+    };
     Dda cur;
     double T0;            // LinearSearchImpl::mT[0]
     float V0;             // LinearSearchImpl::mV[0]
     int lvl;              // 0: root-level DDA (4096^3 cells) 1: inside an upper node (128^3) 2: inside a lower node (8^3) 3: voxels
-    int pendInterp;       // 0 none, 3: the crossing was found in the previous call, getWorldPosAndNml at out.time is due
-    bool skip;            // the current cell was already handled (we just came back up): only step
-    bool pendStep;        // the current cell is done: step
-    bool lazyInit;        // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
+    int shift;            // shiftOf(lvl): every DDA step wants it
+    uint32_t f;           // the flags above in ONE register (bools cost a register and a mask each in the hot loop)
 
     __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }   // 12, 7, 3, 0
-    __device__ __forceinline__ void reset() { lvl = 0; skip = false; pendStep = false; pendInterp = 0; T0 = 0.0; V0 = 0.f; lazyInit = false; }
+    __device__ __forceinline__ void setLevel(int l) { lvl = l; shift = shiftOf(l); }
+    __device__ __forceinline__ void reset() { lvl = 0; shift = 12; f = 0u; T0 = 0.0; V0 = 0.f; }
     // `ray` must be the index-space ray already clipped to the node bbox (setIndexRay/setWorldRay, :548-562); sets up the root-level
     // DDA over the whole ray: LevelSetHDDA<TreeT, RootLevel>::test's math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150)
-    __device__ __forceinline__ void begin(const Ray& ray) { reset(); cur.init(ray, ray.t0, ray.t1, shiftOf(0)); }
+    __device__ __forceinline__ void begin(const Ray& ray) { reset(); cur.init(ray, ray.t0, ray.t1, 12); }
 };
 
 enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
@@ -566,7 +576,7 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 //
 // tester.init(dda.time()) (:597-601) evaluates the stencil at the leaf's entry time only to fill mT[0], mV[0], which nothing reads
 // before the first voxel of the visit that passes the value gate (:622-624).  That evaluation is therefore made together with the
-// first gated one (lazyInit) and never for the leaf visits in which no voxel passes: 1.4 of 8.6 evaluations per ray on C2.  Same
+// first gated one (kLazy) and never for the leaf visits in which no voxel passes: 1.4 of 8.6 evaluations per ray on C2.  Same
 // values in the same order -- the stencil's cache only makes moveTo cheaper, never changes what it returns.
 template<bool COUNT, bool SYNC, int THREADS, bool REFINE = false, int LEAF = kLeafFloat>
 __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
@@ -575,12 +585,12 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
 {
     Dda& cur = w.cur;
     int status = kWalkContinue;
-    int purpose = w.pendInterp;          // 2: tester(ijk, t) of the voxel probed in this call
+    bool gate = false;                   // tester(ijk, t) of the voxel probed in this call is due, at time tq
     bool level = false;                  // a child was found: its DDA is set up over [c0,c1] in this call
-    double c0 = 0.0, c1 = 0.0, tq = out.time;
+    double c0, c1, tq;                   // only read under `level` / `gate`
     // ---- phase B: probe the current cell
-    if (active && !purpose && !w.pendStep) {
-        if (w.skip) { w.skip = false; w.pendStep = true; }
+    if (active && !(w.f & (LsWalk::kStep | LsWalk::kInterp))) {
+        if (w.f & LsWalk::kSkip) w.f ^= LsWalk::kSkip | LsWalk::kStep;
         else {
             const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
             if (w.lvl != 3) {
@@ -590,9 +600,9 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
                     // tester.setRange(dda.time(), dda.next()); recurse one level down (DDA.h:154-156)
                     c0 = cur.t0; c1 = cur.next();
                     sm.park(w.lvl, cur);
-                    ++w.lvl;
+                    w.setLevel(w.lvl + 1);
                     level = true;
-                } else w.pendStep = true;
+                } else w.f |= LsWalk::kStep;
             } else {
                 // LinearSearchImpl::operator()(ijk, time) with time = dda.next() (:620-644)
                 if (COUNT) ++c.voxel;
@@ -606,33 +616,34 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
                     V = haloValue<LEAF>(g.halo, hi, uint32_t(cur.vx & 7), uint32_t(cur.vy & 7), uint32_t(cur.vz & 7));
                     on = maskBit(TreeCursor::node(g, acc.n0) + kLeafVMask, leafOffset(cur.vx, cur.vy, cur.vz));
                 } else on = acc.template valueAt<LEAF>(g, s, depth, cur.vx, cur.vy, cur.vz, V);
-                if (on && V > vmin && V < vmax) { purpose = 2; tq = cur.next(); }
-                w.pendStep = true;
+                if (on && V > vmin && V < vmax) { gate = true; tq = cur.next(); }
+                w.f |= LsWalk::kStep;
             }
         }
     }
     if (SYNC) __syncwarp();
     // ---- phase A: level set-up: math::DDA<Ray,Log2Dim> dda(tester.ray()) (DDA.h:150,172)
     if (level) {
-        cur.init(ray, c0, c1, LsWalk::shiftOf(w.lvl));
-        if (w.lvl == 3) { w.lazyInit = true; w.T0 = c0; }               // tester.init(dda.time()) (:597-601), evaluated on demand
+        cur.init(ray, c0, c1, w.shift);
+        if (w.lvl == 3) { w.f |= LsWalk::kLazy; w.T0 = c0; }             // tester.init(dda.time()) (:597-601), evaluated on demand
     }
     if (SYNC) __syncwarp();
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
-    if (active && purpose) {
-        w.pendInterp = 0;
-        // refinement state (REFINE, purpose 3): mT[0..1], mV[0..1] of the crossing -- mT[1] is the voxel's exit time again (the DDA has
-        // not moved), mV[1] was left in out.gx by the iteration that found the crossing
+    if (active && (gate || (w.f & LsWalk::kInterp))) {
+        if (!gate) tq = out.time;                                         // kInterp
+        w.f &= ~LsWalk::kInterp;
+        // refinement state (REFINE, after the crossing): mT[0..1], mV[0..1] of the crossing -- mT[1] is the voxel's exit time again (the
+        // DDA has not moved), mV[1] was left in out.gx by the iteration that found the crossing
         double rT0 = w.T0, rT1 = REFINE ? cur.next() : 0.0;
         float rV0 = w.V0, rV1 = REFINE ? out.gx : 0.f;
 #pragma unroll 1
         for (int n = 0;; ++n) {
-            const bool initPass = purpose == 2 && w.lazyInit;
+            const bool initPass = gate && (w.f & LsWalk::kLazy);
             const double te = initPass ? w.T0 : tq;
             const double px = ray.ex + ray.dx * te, py = ray.ey + ray.dy * te, pz = ray.ez + ray.dz * te;
             st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
-            if (initPass) { w.V0 = st.interpolation(px, py, pz) - iso; w.lazyInit = false; n = -1; continue; }   // mV[0] = interpValue(mT[0])
-            if (purpose == 3) {
+            if (initPass) { w.V0 = st.interpolation(px, py, pz) - iso; w.f &= ~LsWalk::kLazy; continue; }   // mV[0] = interpValue(mT[0])
+            if (!gate) {
                 if (REFINE && n < iters) {
                     // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
                     const float V = st.interpolation(px, py, pz) - iso;
@@ -651,7 +662,7 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
                     out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
                     out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
                     if (REFINE) out.gx = V1;
-                    w.pendInterp = 3; w.pendStep = false;
+                    w.f = (w.f | LsWalk::kInterp) & ~LsWalk::kStep;
                 } else { w.T0 = tq; w.V0 = V1; }                                  // no crossing: slide
             }
             break;
@@ -659,16 +670,16 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     }
     if (SYNC) __syncwarp();
     // ---- phase D: while (dda.step()) ... ; an exhausted level returns false to its parent (DDA.h:158-159,174-175)
-    if (active && w.pendStep && !w.pendInterp) {
-        w.pendStep = false;
-        if (!cur.step(ray, LsWalk::shiftOf(w.lvl))) {
+    if (active && (w.f & LsWalk::kStep)) {
+        w.f &= ~LsWalk::kStep;
+        if (!cur.step(ray, w.shift)) {
             if (w.lvl == 0) status = kWalkMiss;
             else {
                 // the parent steps right away (one level per call; a second exhausted level waits for the next call)
-                --w.lvl; sm.unpark(w.lvl, cur);
-                if (!cur.step(ray, LsWalk::shiftOf(w.lvl))) {
+                w.setLevel(w.lvl - 1); sm.unpark(w.lvl, cur);
+                if (!cur.step(ray, w.shift)) {
                     if (w.lvl == 0) status = kWalkMiss;
-                    else { --w.lvl; sm.unpark(w.lvl, cur); w.skip = true; }
+                    else { w.setLevel(w.lvl - 1); sm.unpark(w.lvl, cur); w.f |= LsWalk::kSkip; }
                 }
             }
         }

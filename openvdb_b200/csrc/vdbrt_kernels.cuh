@@ -175,7 +175,7 @@ struct LongRay {
     Dda cur; int lvl;                 // the DDA of the level the walk is on (<= 2 while suspended)
     DdaSave park[2];                  // suspended parents: root level, upper level
     int kx, ky, kz; uint32_t n2, n1, n0;
-    uint32_t pix, flags;              // flags: skip | pendStep << 2
+    uint32_t pix, flags;              // LsWalk::kSkip | kStep
     uint32_t segBase, segCount, best, state;   // this round's segments; index of the first one that hit; 1 = walked out of the grid
 };
 struct SegIn { double t0, t1; int kx, ky, kz; uint32_t n2, n1, n0; };
@@ -192,7 +192,7 @@ __device__ __forceinline__ void suspendRay(LongRay& r, const Ray& ray, double wd
 {
     const int t = threadIdx.x;
     r.ray = ray; r.wdx = wdx; r.wdy = wdy; r.wdz = wdz;
-    uint32_t flags = (w.skip ? 1u : 0u) | (w.pendStep ? 4u : 0u);
+    uint32_t flags = w.f & (LsWalk::kSkip | LsWalk::kStep);
     if (w.lvl == 3) {
         // rewind to the lower node's DDA standing on this leaf: the scout finds the leaf again and the march redoes the visit
         r.lvl = 2; flags = 0u;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
 {
     ray = r.ray;
     w.reset();
-    w.cur = r.cur; w.lvl = r.lvl;
+    w.cur = r.cur; w.setLevel(r.lvl);
     const int t = threadIdx.x;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
@@ -222,7 +222,7 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
         sm.vx[l][t] = r.park[l].vx; sm.vy[l][t] = r.park[l].vy; sm.vz[l][t] = r.park[l].vz;
     }
     acc.kx = r.kx; acc.ky = r.ky; acc.kz = r.kz; acc.n2 = r.n2; acc.n1 = r.n1; acc.n0 = r.n0;
-    w.skip = (r.flags & 1u) != 0u; w.pendStep = (r.flags & 4u) != 0u;
+    w.f = r.flags;
 }
 
 // MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
@@ -297,7 +297,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         if (LONG && spent > limit && !longFull && (!lb.tail || tail)) {
             // a ray that already found its crossing just finishes; tail rule with lb.voxel_only: only rays that are marching voxels go
             // to the rounds (the rounds parallelise leaf marches; a ray that is crossing empty nodes is walked by the scout no faster)
-            const bool sus = rayOn && walk.pendInterp != 3 && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
+            const bool sus = rayOn && !(walk.f & LsWalk::kInterp) && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
             const unsigned m = __ballot_sync(0xffffffffu, sus);
             if (lb.tail) spent = 0;                                 // the lanes that stay are looked at again `tail` iterations later
             if (m && sc.cost_out && lane == 0 && curStrip != 0xffffffffu) { sc.cost_out[curStrip] = 0x7fffffffu; curStrip = 0xffffffffu; }
@@ -592,7 +592,7 @@ k_long_scout(const __grid_constant__ DevGrid g, const __grid_constant__ DevShade
         Dda& cur = walk.cur;
         uint32_t emitted = 0;
         bool exhausted = false;
-        bool advance = walk.pendStep || walk.skip;
+        bool advance = (walk.f & (LsWalk::kStep | LsWalk::kSkip)) != 0u;
 #pragma unroll 1
         for (;;) {
             if (advance) {
@@ -640,7 +640,7 @@ k_long_scout(const __grid_constant__ DevGrid g, const __grid_constant__ DevShade
                 }
             }
         }
-        walk.pendStep = false; walk.skip = false;
+        walk.f = 0u;
         suspendRay(*r, ray, r->wdx, r->wdy, r->wdz, walk, wsm, acc, size_t(r->pix));
         r->segBase = sb; r->segCount = emitted; r->state = exhausted ? 1u : 0u;
     }
