@@ -869,12 +869,12 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     if (int rc = ensureBuffer(&ctx->io, &ctx->io_cap, npx * 16)) return rc;      // scratch film, discarded
     CUDA_TRY(cudaMemsetAsync(ctx->io, 0, npx * 16, ctx->stream));
     unsigned long long* dC = reinterpret_cast<unsigned long long*>(ctx->scratch + 128);
-    CUDA_TRY(cudaMemsetAsync(dC, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dC, 0, 40 * sizeof(unsigned long long), ctx->stream));
     vdbrt_film film = {}; film.width = cam->width; film.height = cam->height;
     vdbrt_shader sh = {}; sh.kind = VDBRT_SHADER_DIFFUSE; sh.rgba[0] = sh.rgba[1] = sh.rgba[2] = sh.rgba[3] = 1.f;
     AuxOut a = {};
     if (int rc = launchLevelSet(ctx, grid, cam, &sh, opts, &film, static_cast<float4*>(ctx->io), static_cast<const float4*>(ctx->io), a, false, dC)) return rc;
-    unsigned long long h[16];
+    unsigned long long h[40];
     CUDA_TRY(cudaMemcpyAsync(h, dC, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     out->rays = h[0]; out->root_probes = h[1]; out->upper_probes = h[2]; out->lower_probes = h[3]; out->voxel_probes = h[4];
@@ -882,6 +882,17 @@ int vdbrt_count_levelset(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_cam
     if (std::getenv("VDBRT_DEBUG_TILES"))
         std::fprintf(stderr, "[vdbrt] tiles %llu: max cycles %llu, max iterations %llu, mean cycles %.0f; %llu tiles > 1.5M cycles with mean active lanes %.2f\n", h[13], h[10], h[11],
                      h[13] ? double(h[12]) / double(h[13]) : 0.0, h[14], h[14] ? double(h[15]) / 100.0 / double(h[14]) : 0.0);
+    if (std::getenv("VDBRT_DEBUG_TILES")) {
+        unsigned long long its = 0;
+        for (int k = 0; k < 9; ++k) its += h[16 + k];
+        std::fprintf(stderr, "[vdbrt] warp iterations %llu; running lanes 0 / 1-4 / ... / 29-32:", its);
+        for (int k = 0; k < 9; ++k) std::fprintf(stderr, " %.1f%%", its ? 100.0 * double(h[16 + k]) / double(its) : 0.0);
+        static const char* names[4] = {"node probe", "voxel probe", "stencil", "step"};
+        std::fprintf(stderr, "\n[vdbrt] phase: share of the iterations that ran it, lanes in it when it ran:");
+        for (int k = 0; k < 4; ++k)
+            std::fprintf(stderr, " %s %.1f%% x %.1f;", names[k], its ? 100.0 * double(h[36 + k]) / double(its) : 0.0, h[36 + k] ? double(h[32 + k]) / double(h[36 + k]) : 0.0);
+        std::fprintf(stderr, "\n");
+    }
     return VDBRT_OK;
 }
 

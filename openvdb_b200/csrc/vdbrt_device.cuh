@@ -139,6 +139,9 @@ __device__ __forceinline__ void stageRoot(const DevGrid& g, RootSmem& s)
 
 struct Counters {   // per-thread work counters of the instrumented (never timed) launches
     uint32_t root, upper, lower, voxel, refills, psamples, ssamples, srays, hits, rays;
+    // diagnostics of the warp-synchronous level-set loop (VDBRT_DEBUG_TILES): lanes that ran the node probe / voxel probe / stencil
+    // evaluation / DDA step of an iteration [0..3], iterations in which the warp ran that phase at all [4..7] (counted by lane 0)
+    uint32_t diag[8];
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -586,6 +589,7 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     Dda& cur = w.cur;
     int status = kWalkContinue;
     bool gate = false;                   // tester(ijk, t) of the voxel probed in this call is due, at time tq
+    const uint32_t fIn = w.f; const int lvlIn = w.lvl;       // (diagnostics only)
     double tq;                           // only read under `gate`
     // ---- phase B: probe the current cell
     if (active && !(w.f & (LsWalk::kStep | LsWalk::kInterp))) {
@@ -623,8 +627,21 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
             }
         }
     }
+    if (COUNT && SYNC) {
+        const bool probed = active && (w.f & LsWalk::kStep || w.lvl != lvlIn) && !(fIn & (LsWalk::kStep | LsWalk::kInterp | LsWalk::kSkip));
+        const bool node = probed && lvlIn != 3, vox = probed && lvlIn == 3;
+        c.diag[0] += node; c.diag[1] += vox;
+        const unsigned bn = __ballot_sync(0xffffffffu, node), bv = __ballot_sync(0xffffffffu, vox);
+        if ((threadIdx.x & 31) == 0) { c.diag[4] += bn != 0u; c.diag[5] += bv != 0u; }
+    }
     if (SYNC) __syncwarp();
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
+    if (COUNT && SYNC) {
+        const bool ev = active && (gate || (w.f & LsWalk::kInterp));
+        c.diag[2] += ev;
+        const unsigned b = __ballot_sync(0xffffffffu, ev);
+        if ((threadIdx.x & 31) == 0) c.diag[6] += b != 0u;
+    }
     if (active && (gate || (w.f & LsWalk::kInterp))) {
         if (!gate) tq = out.time;                                         // kInterp
         w.f &= ~LsWalk::kInterp;
@@ -666,6 +683,12 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     }
     if (SYNC) __syncwarp();
     // ---- phase D: while (dda.step()) ... ; an exhausted level returns false to its parent (DDA.h:158-159,174-175)
+    if (COUNT && SYNC) {
+        const bool sp = active && (w.f & LsWalk::kStep);
+        c.diag[3] += sp;
+        const unsigned b = __ballot_sync(0xffffffffu, sp);
+        if ((threadIdx.x & 31) == 0) c.diag[7] += b != 0u;
+    }
     if (active && (w.f & LsWalk::kStep)) {
         w.f &= ~LsWalk::kStep;
         if (!cur.step(ray, w.shift)) {

@@ -70,6 +70,16 @@ __device__ __forceinline__ void flushCounters(const Counters& c, unsigned long l
     }
 }
 
+__device__ __forceinline__ void flushDiag(const Counters& c, unsigned long long* out)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t v = c.diag[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(out + k, (unsigned long long)v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // LevelSetRayTracer::operator() (tools/RayTracer.h:899-918): primary ray + (spp-1) jittered rays per pixel.
 // Jitter index n(i,j) = 2*(spp-1)*(j*W+i): the reference's counter for render(threaded=false).
@@ -107,7 +117,7 @@ struct Sched {
     uint32_t affine;             // strips per chunk (0: one global queue)
     unsigned int* smq;           // affine: one counter per SM (zeroed before the launch), nq of them
     uint32_t nq;
-    uint32_t* cost_out;          // history: warp iterations each tile of THIS frame took (null: not recorded); cost_sum: their sum
+    uint32_t* cost_out;          // history: SM clock cycles / 16 each tile of THIS frame took (null: not recorded); cost_sum: their sum
     unsigned long long* cost_sum;
     unsigned long long* warp_exit;   // diagnostics (VDBRT_DEBUG_EXIT): %globaltimer of every warp when it leaves the kernel, [0] = launch start
     const uint32_t* ctl;         // [0], [1]: strips in the two heavy lists (null: no ordering)
@@ -163,7 +173,7 @@ __device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kNoHit = 0xffffffffu;
 constexpr int kMaxRounds = 8;
-constexpr uint32_t kDefaultTail = 48;     // tail rule: warp iterations a tile may still spend once the queue has run dry
+constexpr uint32_t kDefaultTail = 24;     // tail rule: warp iterations a tile may still spend once the queue has run dry
 constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
 constexpr int kDefaultRounds = 2;
@@ -269,7 +279,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
     unsigned sNext = 0, sEnd = 0;                       // pixel slots of the warp's strip that are still to be handed out (warp-uniform)
-    unsigned curStrip = 0xffffffffu, tileIt = 0;        // history: the strip the warp is working on and the iterations it has spent on it
+    unsigned curStrip = 0xffffffffu, tileT0 = 0;        // history: the strip the warp is working on and the SM clock when it took it (nothing is counted per iteration)
 
     long long tileStart = 0; unsigned long long tileIters = 0, tileActive = 0;
     // warp iterations spent on the current tile, and what a tile may spend: at least lb.budget, and lb.factor percent of
@@ -327,7 +337,10 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             tileStart = now; tileIters = 0; tileActive = 0;
         }
         if (sc.cost_out && idle == 0xffffffffu && sNext >= sEnd && curStrip != 0xffffffffu) {
-            if (lane == 0) { sc.cost_out[curStrip] = tileIt; atomicAdd(sc.cost_sum, (unsigned long long)tileIt); }
+            if (lane == 0) {
+                const unsigned cost = (unsigned(clock()) - tileT0) >> 4;            // 16-cycle units: stays far below the 'suspended' mark
+                sc.cost_out[curStrip] = cost; atomicAdd(sc.cost_sum, (unsigned long long)cost);
+            }
             curStrip = 0xffffffffu;
         }
         if (idle == 0xffffffffu && drained && sNext >= sEnd) break;
@@ -373,7 +386,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             }
             s = __shfl_sync(0xffffffffu, s, 0);
             if (s == 0xffffffffu) { drained = true; tail = true; }
-            else { sNext = s * stripSlots; sEnd = sNext + stripSlots < total ? sNext + stripSlots : total; curStrip = s; tileIt = 0; }
+            else { sNext = s * stripSlots; sEnd = sNext + stripSlots < total ? sNext + stripSlots : total; curStrip = s; tileT0 = unsigned(clock()); }
         }
         if (sNext < sEnd && (idle == 0xffffffffu || nIdle >= thr)) {
             if (!hasPix) {
@@ -403,8 +416,11 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
 #pragma unroll 1
         for (;;) {
             __syncwarp();
-            if (COUNT) { ++tileIters; tileActive += __popc(__ballot_sync(0xffffffffu, rayOn)); }
-            ++tileIt;
+            if (COUNT) {
+                const unsigned live = __popc(__ballot_sync(0xffffffffu, rayOn));
+                ++tileIters; tileActive += live;
+                if (lane == 0) atomicAdd(counters + 16 + (live + 3u) / 4u, 1ull);      // histogram of running lanes per iteration: 0, 1-4, 5-8, ..., 29-32
+            }
             if (LONG) {
                 ++spent;
                 if (lb.tail && !tail && (spent & 15u) == 0u) {
@@ -454,7 +470,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (LONG && spent > limit && !longFull && (!lb.tail || tail)) break;
         }
     }
-    if (COUNT) flushCounters(c, counters);
+    if (COUNT) { flushCounters(c, counters); flushDiag(c, counters + 32); }
     if (sc.warp_exit && lane == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -462,7 +478,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     }
 }
 
-// Heavy tiles first from HISTORY: the warp iterations every tile took in the previous frame this context rendered with the same
+// Heavy tiles first from HISTORY: the time (SM clock) every tile took in the previous frame this context rendered with the same
 // film, tiles and partition (Sched::cost_out).  Tiles that took at least fA / fB times the mean go to list A / B; the render
 // kernel hands those out first (Sched::ctl, listA, listB, cls) and everything else in tile order.  Costs nothing but this launch
 // (one thread per tile) and needs no probe rays; the first frame of a sequence is rendered in plain tile order.

@@ -108,7 +108,7 @@ def test_tail_rule_any_budget(ctx, oracle, torus_small):
                 ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(part=api.partition(r, 3, 32, 32)))
             assert np.array_equal(film, ofilm), ("partitioned", tail)
     finally:
-        ctx.set_tuning(ls_tail=48)
+        ctx.set_tuning(ls_tail=24)
     g.free()
 
 
