@@ -27,6 +27,7 @@ namespace vdbrt {
 
 struct RuntimeError : std::runtime_error { using std::runtime_error::runtime_error; };   // openvdb::RuntimeError
 struct ValueError : std::runtime_error { using std::runtime_error::runtime_error; };     // openvdb::ValueError
+struct IoError : std::runtime_error { using std::runtime_error::runtime_error; };        // openvdb::IoError
 
 inline void check(int code)
 {

@@ -733,7 +733,7 @@ struct FogSmem {
     int vx[5][THREADS], vy[5][THREADS], vz[5][THREADS];
     double ray[6][THREADS];           // eye, dir of the primary index-space ray while a shadow ray is active (1/dir is recomputed)
     double dt0[THREADS];              // primary Dda::t0
-    double ts0[THREADS], topT1[THREADS], tcur[THREADS], tend[THREADS], bound[THREADS], c0[THREADS], c1[THREADS];
+    double ts0[THREADS], topT1[THREADS], tcur[THREADS], tend[THREADS], bound[THREADS];
     int misc[THREADS];                // primary walk: lvl | needStep << 8
     double sbase[8];                  // shadow ray constants shared by the CTA: dir xyz, inv xyz, t0, t1 (index space)
     __device__ __forceinline__ void park(int slot, const Dda& d)
@@ -754,15 +754,16 @@ enum { kSpanContinue = 0, kSpanEmit = 1, kSpanDone = 2 };
 struct SpanWalk {
     Dda cur;
     double ts0, topT1;     // open span start (<0: none), maxTime of the root-level DDA
-    double c0, c1;         // pending child range: ray.setTimes(time(), next()) (DDA.h:252,326)
     double bound;          // entry time of the last probed cell: while a span is open its end cannot be earlier than this
     int lvl;               // 0 root-level DDA (4096^3), 1 inside an upper node (128^3), 2 inside a lower node (8^3); -1 = finished
-    bool needStep, pendLevel;
+    bool needStep;
 
     __device__ __forceinline__ static int shiftOf(int lvl) { return (0x0003070C >> (8 * lvl)) & 0xff; }
+    // the root-level DDA is set up here, a child's DDA in the call that finds the child (math::DDA<RayT,Log2Dim> dda(ray), DDA.h:252,326)
     __device__ __forceinline__ void begin(const Ray& ray)
     {
-        lvl = 0; needStep = false; pendLevel = true; ts0 = -1.0; topT1 = ray.t1; c0 = ray.t0; c1 = ray.t1; bound = ray.t0;
+        lvl = 0; needStep = false; ts0 = -1.0; topT1 = ray.t1; bound = ray.t0;
+        cur.init(ray, ray.t0, ray.t1, 12);
     }
     // slotBase: first parking slot of this walk's parents (0 primary, 2 shadow)
     template<bool COUNT, class SM>
@@ -770,10 +771,7 @@ struct SpanWalk {
                                            double& a, double& b, Counters& c)
     {
         if (lvl < 0) return kSpanDone;
-        if (pendLevel) {
-            cur.init(ray, c0, c1, shiftOf(lvl));
-            pendLevel = false;
-        } else if (needStep) {
+        if (needStep) {
             if (!cur.step(ray, shiftOf(lvl))) {
                 // a level is exhausted: "if (t.t0>=0) t.t1 = mDDA.maxTime()" -- only the outermost assignment survives
                 // because any later close overwrites t1 (DDA.h:263,335)
@@ -799,9 +797,10 @@ struct SpanWalk {
             const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
             if (COUNT) { if (lvl == 0) ++c.root; else if (lvl == 1) ++c.upper; else ++c.lower; }
             if (lvl < 2 && depth <= 2 - lvl) {              // child node: walk it
-                c0 = cur.t0; c1 = cur.next();
+                const double c0 = cur.t0, c1 = cur.next();       // ray.setTimes(time(), next()) (DDA.h:252,326)
                 sm.park(slotBase + lvl, cur);
-                ++lvl; pendLevel = true; needStep = false;
+                ++lvl; needStep = false;
+                cur.init(ray, c0, c1, shiftOf(lvl));
                 return kSpanContinue;
             }
             // leaf level: any existing leaf counts as active (DDA.h:308-309,326-327); otherwise the tile's state

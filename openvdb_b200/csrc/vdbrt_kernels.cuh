@@ -998,8 +998,8 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                         // suspend the primary walk and ray, switch the lane to the shadow ray
                         sm.park(4, walk.cur);
                         sm.dt0[tid] = walk.cur.t0; sm.ts0[tid] = walk.ts0; sm.topT1[tid] = walk.topT1; sm.tcur[tid] = tcur; sm.tend[tid] = tend;
-                        sm.bound[tid] = walk.bound; sm.c0[tid] = walk.c0; sm.c1[tid] = walk.c1;
-                        sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0) | (walk.pendLevel ? 512 : 0) | (span << 12);
+                        sm.bound[tid] = walk.bound;
+                        sm.misc[tid] = (walk.lvl + 1) | (walk.needStep ? 256 : 0) | (span << 12);
                         sm.ray[0][tid] = ray.ex; sm.ray[1][tid] = ray.ey; sm.ray[2][tid] = ray.ez; sm.ray[3][tid] = ray.dx; sm.ray[4][tid] = ray.dy;
                         sm.ray[5][tid] = ray.dz;
                         ray = sRay;
@@ -1020,10 +1020,10 @@ k_render_volume(const __grid_constant__ DevGrid g, const __grid_constant__ DevCa
                 else {
                     sm.unpark(4, walk.cur);
                     walk.cur.t0 = sm.dt0[tid]; walk.ts0 = sm.ts0[tid]; walk.topT1 = sm.topT1[tid]; tend = sm.tend[tid];
-                    walk.bound = sm.bound[tid]; walk.c0 = sm.c0[tid]; walk.c1 = sm.c1[tid];
+                    walk.bound = sm.bound[tid];
                     tcur = sm.tcur[tid] + p.pstep;
                     const int m = sm.misc[tid];
-                    walk.lvl = (m & 255) - 1; walk.needStep = (m & 256) != 0; walk.pendLevel = (m & 512) != 0; span = m >> 12;
+                    walk.lvl = (m & 255) - 1; walk.needStep = (m & 256) != 0; span = m >> 12;
                     ray.ex = sm.ray[0][tid]; ray.ey = sm.ray[1][tid]; ray.ez = sm.ray[2][tid]; ray.dx = sm.ray[3][tid]; ray.dy = sm.ray[4][tid];
                     ray.setDir(ray.dx, ray.dy, sm.ray[5][tid]);          // invDir = 1/dir, the same division as at ray set-up
                     mode = kFogPrimary;

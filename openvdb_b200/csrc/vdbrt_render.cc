@@ -6,7 +6,9 @@
 // tools/RayTracer.h.  Differences, all forced by the scope of this library:
 //   * the input is a NanoVDB file (.nvdb: segments, codecs NONE / ZIP, or a raw grid buffer) instead of a .vdb file, or one of
 //     the built-in generators  sphere:R[,voxel[,halfwidth]]  torus:R,r  fogsphere:R  (the GPU box has no asset files);
-//   * only .ppm output (the reference needs OpenEXR / libpng for the others and says so the same way);
+//   * .ppm and .png output (the .png is the 8-bit RGB image of main.cc:335-390 -- Film::convertToBitBuffer<uint8_t>(alpha = false) --
+//     written with zlib alone, no libpng: same pixels, not the same file bytes); .exr needs OpenEXR and is refused the way the
+//     reference refuses it when built without (main.cc:248-253);
 //   * -color NAME names a Vec3f grid of the same file (the colour-grid forms of the four shaders);
 //   * -cpus is accepted and ignored, -gpu N picks the device.
 #include <vdbrt/RayTracer.h>
@@ -23,11 +25,51 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 using namespace vdbrt;
 
 namespace {
 
 const char* gProgName = "vdbrt_render";
+
+// PngWriter::write (main.cc:340-390): 8-bit RGB, no interlace, the bytes of Film::convertToBitBuffer<uint8_t>(alpha = false).
+// One IDAT chunk, filter type 0 on every row, deflated by zlib.
+void savePNG(const std::string& fname, tools::Film& film)
+{
+    const size_t w = film.width(), h = film.height();
+    auto bits = film.convertToBitBuffer<unsigned char>(/*alpha=*/false);
+    std::vector<unsigned char> rows((3 * w + 1) * h);
+    for (size_t y = 0; y < h; ++y) {
+        rows[(3 * w + 1) * y] = 0;
+        std::memcpy(&rows[(3 * w + 1) * y + 1], bits.get() + 3 * w * y, 3 * w);
+    }
+    uLongf clen = compressBound(uLong(rows.size()));
+    std::vector<unsigned char> z(clen);
+    if (compress2(z.data(), &clen, rows.data(), uLong(rows.size()), Z_DEFAULT_COMPRESSION) != Z_OK) throw RuntimeError("Error writing PNG data buffers.");
+    std::FILE* fp = std::fopen(fname.c_str(), "wb");
+    if (!fp) throw IoError("Unable to open '" + fname + "' for writing");
+    auto be32 = [](unsigned char* p, uint32_t v) { p[0] = (unsigned char)(v >> 24); p[1] = (unsigned char)(v >> 16); p[2] = (unsigned char)(v >> 8); p[3] = (unsigned char)v; };
+    auto chunk = [&](const char* type, const unsigned char* data, size_t n) {
+        unsigned char head[8];
+        be32(head, uint32_t(n)); std::memcpy(head + 4, type, 4);
+        uLong crc = crc32(0L, head + 4, 4);
+        if (n) crc = crc32(crc, data, uInt(n));
+        unsigned char tail[4]; be32(tail, uint32_t(crc));
+        std::fwrite(head, 1, 8, fp); if (n) std::fwrite(data, 1, n, fp); std::fwrite(tail, 1, 4, fp);
+    };
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::fwrite(sig, 1, 8, fp);
+    unsigned char ihdr[13];
+    be32(ihdr, uint32_t(w)); be32(ihdr + 4, uint32_t(h));
+    ihdr[8] = 8; ihdr[9] = 2 /* PNG_COLOR_TYPE_RGB */; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0 /* PNG_INTERLACE_NONE */;
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), size_t(clen));
+    chunk("IEND", nullptr, 0);
+    const bool ok = !std::ferror(fp);
+    std::fclose(fp);
+    if (!ok) throw IoError("Error writing PNG data buffers.");
+}
 const double LIGHT_DEFAULTS[] = {0.3, 0.3, 0.0, 0.7, 0.7, 0.7};
 
 struct RenderOpts {                               // main.cc:56-106
@@ -79,7 +121,7 @@ std::ostream& operator<<(std::ostream& os, const RenderOpts& o)    // RenderOpts
     const double fov = 360.0 / M_PI * std::atan(o.aperture / (2.0 * o.focal));      // focalLengthToFieldOfView (RayTracer.h:466-469)
     std::ostringstream s;
     s << std::setprecision(3) <<
-"Usage: " << gProgName << " in.nvdb out.ppm [options]\n"
+"Usage: " << gProgName << " in.nvdb out.{ppm,png} [options]\n"
 "Which: ray-traces NanoVDB volumes on the GPU (option set of OpenVDB's vdb_render)\n"
 "       in.nvdb may also be sphere:R[,voxel[,halfwidth]], torus:R,r or fogsphere:R\n"
 "Options:\n"
@@ -198,6 +240,7 @@ void render(FloatGrid& grid, const Vec3SGrid* colorgrid, const std::string& imgF
         o << gProgName << ": ...completed in " << std::setprecision(3) << std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count() << " sec";
         std::cout << o.str() << std::endl;
     }
+    if (endsWith(imgFilename, ".png")) { savePNG(imgFilename, film); return; }
     if (!endsWith(imgFilename, ".ppm")) throw ValueError("unsupported image file format (" + imgFilename + ")");
     std::string filename = imgFilename;
     filename.erase(filename.size() - 4);          // strip .ppm extension; savePPM appends it again
@@ -263,7 +306,9 @@ int main(int argc, char* argv[])
 
     int retcode = EXIT_SUCCESS;
     try {
-        if (!endsWith(imgFilename, ".ppm")) throw RuntimeError("vdbrt_render only writes .ppm files (" + imgFilename + ")");
+        // isExtensionSupported (main.cc:244-264)
+        if (endsWith(imgFilename, ".exr")) throw RuntimeError("vdbrt_render has not been compiled with .exr support.");
+        if (!endsWith(imgFilename, ".ppm") && !endsWith(imgFilename, ".png")) throw ValueError("unsupported image file format (" + imgFilename + ")");
         const auto start = std::chrono::steady_clock::now();
         if (opts.verbose) {
             std::cout << gProgName << ": reading ";

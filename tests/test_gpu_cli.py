@@ -24,6 +24,28 @@ def read_ppm(path):
     return np.frombuffer(raw[head:], np.uint8).reshape(h, w, 3)
 
 
+def read_png(path):
+    """8-bit RGB, non-interlaced PNG with filter type 0 rows, decoded with zlib alone (what vdbrt_render writes)"""
+    import struct, zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        n, kind = struct.unpack(">I4s", raw[pos:pos + 8])
+        data = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(kind + data)
+        if kind == b"IHDR":
+            w, h, depth, colour, comp, filt, lace = struct.unpack(">IIBBBBB", data)
+            assert (depth, colour, comp, filt, lace) == (8, 2, 0, 0, 0)
+        elif kind == b"IDAT":
+            idat += data
+        pos += 12 + n
+    assert kind == b"IEND"
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 3 * w + 1)
+    assert not rows[:, 0].any()
+    return rows[:, 1:].reshape(h, w, 3)
+
+
 def to_bits(film):
     return (np.float32(255.0) * film[..., :3]).astype(np.uint8)          # Film::convertToBitBuffer (tools/RayTracer.h:300-317)
 
@@ -127,3 +149,20 @@ def test_generators_and_errors(tmp_path):
     assert run("sphere:30", tmp_path / "s.ppm", "-samples", "0").returncode != 0
     assert run(tmp_path / "missing.nvdb", tmp_path / "s.ppm").returncode != 0
     assert run("sphere:30", tmp_path / "s.ppm", "-bogus").returncode != 0
+
+
+def test_png_output_has_the_pixels_of_the_ppm(ctx, oracle, tmp_path):
+    """-o x.png: PngWriter (main.cc:335-390) writes Film::convertToBitBuffer<uint8_t>(alpha=false) as 8-bit RGB; .exr is refused the way a
+    vdb_render built without OpenEXR refuses it (main.cc:248-253), other extensions the way isExtensionSupported does"""
+    W, H = 150, 90
+    png, ppm = tmp_path / "s.png", tmp_path / "s.ppm"
+    for out in (png, ppm):
+        r = run("sphere:40", out, "-res", "%dx%d" % (W, H), "-translate", "30,20,140", "-lookat", "0,0,0", "-shader", "normal")
+        assert r.returncode == 0, r.stderr
+    a, b = read_png(str(png)), read_ppm(str(ppm))
+    assert a.shape == (H, W, 3) and (b.sum(axis=2) > 0).sum() > 1000
+    assert np.array_equal(a, b)
+    r = run("sphere:40", tmp_path / "s.exr", "-res", "32x32")
+    assert r.returncode != 0 and "has not been compiled with .exr support" in r.stderr
+    r = run("sphere:40", tmp_path / "s.jpg", "-res", "32x32")
+    assert r.returncode != 0 and "unsupported image file format" in r.stderr

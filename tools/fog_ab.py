@@ -28,4 +28,4 @@ if 'c5' in what:
     g = ctx.build_spheres(api.random_spheres(10000, 20240607, 1988.0, 10.0, 60.0)); fog = ctx.build_fog(g); g.free()
     cam = api.vdb_render_camera(3840, 2160, (0.0, 0.0, 3 * 2048.0), (0.0, 0.0, 0.0))
     go('c5 1/64', fog, cam, 3840, 2160, 16, api.partition(0, 64, 64, 60), reps=2)
-    go('c5 1/8', fog, cam, 3840, 2160, 16, api.partition(0, 8, 64, 60), reps=2)
+    if "c5full" in what: go("c5 1/8", fog, cam, 3840, 2160, 16, api.partition(0, 8, 64, 60), reps=2)
