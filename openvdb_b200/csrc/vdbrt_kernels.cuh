@@ -10,7 +10,10 @@
 namespace vdbrt {
 
 constexpr int kBlockThreads = 128;       // 4 warps per CTA
-constexpr int kSubW = 8, kSubH = 4;      // pixels per warp tile
+#ifndef VDBRT_SUBW
+#define VDBRT_SUBW 8
+#endif
+constexpr int kSubW = VDBRT_SUBW, kSubH = 32 / VDBRT_SUBW;      // pixels per warp tile (8 x 4; 4 x 8 and 16 x 2 were measured, see profiles/r02_summary.md)
 
 struct TileMap {
     uint32_t width, height;
@@ -48,7 +51,7 @@ __device__ __forceinline__ bool nextPixel(const TileMap& m, unsigned int* queue,
     const uint32_t macro = m.rank + (item / m.sub_per_macro) * m.count;
     const uint32_t sub = item % m.sub_per_macro;
     const uint32_t mx = macro % m.macro_x, my = macro / m.macro_x;
-    const uint32_t lx = (sub % m.sub_x) * kSubW + (lane & 7u), ly = (sub / m.sub_x) * kSubH + (lane >> 3);
+    const uint32_t lx = (sub % m.sub_x) * kSubW + (lane % kSubW), ly = (sub / m.sub_x) * kSubH + (lane / kSubW);
     px = mx * m.tile_w + lx; py = my * m.tile_h + ly;
     valid = lx < m.tile_w && ly < m.tile_h && px < m.width && py < m.height;
     return true;
@@ -132,7 +135,7 @@ __device__ __forceinline__ bool ticketToPixel(const TileMap& m, unsigned ticket,
     const uint32_t macro = m.rank + (item / m.sub_per_macro) * m.count;
     const uint32_t sub = item % m.sub_per_macro;
     const uint32_t mx = macro % m.macro_x, my = macro / m.macro_x;
-    const uint32_t lx = (sub % m.sub_x) * kSubW + (slot & 7u), ly = (sub / m.sub_x) * kSubH + (slot >> 3);
+    const uint32_t lx = (sub % m.sub_x) * kSubW + (slot % kSubW), ly = (sub / m.sub_x) * kSubH + (slot / kSubW);
     px = mx * m.tile_w + lx; py = my * m.tile_h + ly;
     return lx < m.tile_w && ly < m.tile_h && px < m.width && py < m.height;
 }
