@@ -98,6 +98,9 @@ __device__ __forceinline__ void flushDiag(const Counters& c, unsigned long long*
 #ifndef VDBRT_MINBLOCKS
 #define VDBRT_MINBLOCKS 5
 #endif
+#ifndef VDBRT_SHADE_AT_END
+#define VDBRT_SHADE_AT_END 1
+#endif
 #ifndef VDBRT_MINBLOCKS_LONG
 #define VDBRT_MINBLOCKS_LONG 4
 #endif
@@ -303,6 +306,33 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     // up the next ray of every lane that needs one (the only place the ray registers are written).  The INNER one advances
     // the running rays and finishes the ones that end, until enough lanes are idle (or one wants its next sample) or no lane
     // is running: nothing of the outer loop's bookkeeping is executed per traversal step.
+    // shade / composite the ray that ended with `status`, then next sample or write the pixel
+    auto finishRay = [&](int& status) {
+        const bool hit = status == kWalkHit;
+        float4 s;
+        if (hit) {
+            if (COUNT) ++c.hits;
+            // the shader wants the WORLD direction of the ray: rebuilt from the camera here (the same arithmetic on the same
+            // inputs) rather than carried through the traversal in six registers
+            Ray wr;
+            const bool first = !MULTI || k == 0;
+            cameraRay(cam, px, py, first ? 0.5 : p.jitter[(n - 2) & 15], first ? 0.5 : p.jitter[(n - 1) & 15], wr);
+            s = shadeHit<AUX>(g, sh, h, ray, wr.dx, wr.dy, wr.dz, pix, aux, first);
+        } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
+        if (AUX && (!MULTI || k == 0) && aux.hit) aux.hit[pix] = hit ? 1 : 0;
+        if (MULTI) {
+            if (k == 0) col = s;
+            else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
+            if (++k > p.sub) {
+                film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
+                hasPix = false;
+            }
+        } else {
+            film[pix] = make_float4(s.x * p.frac, s.y * p.frac, s.z * p.frac, 1.0f);
+            hasPix = false;
+        }
+        status = kWalkContinue;
+    };
     for (;;) {
         __syncwarp();
         // (0) the tile has used up its budget (the inner loop leaves when that happens): suspend the rays that are still running,
@@ -438,39 +468,21 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 if (rayOn) status = r;
             }
             __syncwarp();
-            // (4) a ray ended: shade / composite, then next sample or write the pixel
+            // (4) a ray ended.  One sample per pixel: the lane just stops; its pixel is shaded and written after the loop, together with
+            // the other pixels of the tile (VDBRT_SHADE_AT_END) -- otherwise: shade / composite now, then next sample or write the pixel
             if (status != kWalkContinue) {
-                const bool hit = status == kWalkHit;
-                float4 s;
-                if (hit) {
-                    if (COUNT) ++c.hits;
-                    // the shader wants the WORLD direction of the ray: rebuilt from the camera here (the same arithmetic on the same
-                    // inputs) rather than carried through the traversal in six registers
-                    Ray wr;
-                    const bool first = !MULTI || k == 0;
-                    cameraRay(cam, px, py, first ? 0.5 : p.jitter[(n - 2) & 15], first ? 0.5 : p.jitter[(n - 1) & 15], wr);
-                    s = shadeHit<AUX>(g, sh, h, ray, wr.dx, wr.dy, wr.dz, pix, aux, first);
-                } else s = p.uniform_bg ? make_float4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]) : p.bg_film[pix];
-                if (AUX && (!MULTI || k == 0) && aux.hit) aux.hit[pix] = hit ? 1 : 0;
                 rayOn = false;
-                if (MULTI) {
-                    if (k == 0) col = s;
-                    else { col.x += s.x; col.y += s.y; col.z += s.z; col.w += s.w; }     // RGBA::operator+= (:250)
-                    if (++k > p.sub) {
-                        film[pix] = make_float4(col.x * p.frac, col.y * p.frac, col.z * p.frac, 1.0f);   // bg = c*frac, alpha rebuilt as 1 (:247)
-                        hasPix = false;
-                    }
-                } else {
-                    film[pix] = make_float4(s.x * p.frac, s.y * p.frac, s.z * p.frac, 1.0f);
-                    hasPix = false;
-                }
-                status = kWalkContinue;
+                if (MULTI || !VDBRT_SHADE_AT_END) finishRay(status);
             }
             // back to the outer loop when a lane wants its next ray, when enough lanes are idle and the strip has pixels for them,
             // or when nothing is running any more
             const unsigned running = __ballot_sync(0xffffffffu, rayOn);
             if (running == 0u || (canRefill && 32u - (unsigned)__popc(running) >= thr) || (MULTI && __any_sync(0xffffffffu, hasPix && !rayOn))) break;
             if (LONG && spent > limit && !longFull && (!lb.tail || tail)) break;
+        }
+        if (!MULTI && VDBRT_SHADE_AT_END) {
+            __syncwarp();
+            if (hasPix && !rayOn && status != kWalkContinue) finishRay(status);
         }
     }
     if (COUNT) { flushCounters(c, counters); flushDiag(c, counters + 32); }
