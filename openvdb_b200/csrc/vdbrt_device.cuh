@@ -550,8 +550,7 @@ struct LsWalk {
     enum : uint32_t {
         kSkip = 1u,       // the current cell was already handled (we just came back up): only step
         kStep = 2u,       // the current cell is done: step
-        kLazy = 4u,       // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
-        kInterp = 8u      // the crossing was found in the previous call, getWorldPosAndNml at out.time is due
+        kLazy = 4u        // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
     };
     Dda cur;
     double T0;            // LinearSearchImpl::mT[0]
@@ -592,7 +591,7 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     const uint32_t fIn = w.f; const int lvlIn = w.lvl;       // (diagnostics only)
     double tq;                           // only read under `gate`
     // ---- phase B: probe the current cell
-    if (active && !(w.f & (LsWalk::kStep | LsWalk::kInterp))) {
+    if (active && !(w.f & LsWalk::kStep)) {
         if (w.f & LsWalk::kSkip) w.f ^= LsWalk::kSkip | LsWalk::kStep;
         else {
             const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
@@ -628,56 +627,37 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
         }
     }
     if (COUNT && SYNC) {
-        const bool probed = active && (w.f & LsWalk::kStep || w.lvl != lvlIn) && !(fIn & (LsWalk::kStep | LsWalk::kInterp | LsWalk::kSkip));
+        const bool probed = active && !(fIn & (LsWalk::kStep | LsWalk::kSkip));
         const bool node = probed && lvlIn != 3, vox = probed && lvlIn == 3;
         c.diag[0] += node; c.diag[1] += vox;
         const unsigned bn = __ballot_sync(0xffffffffu, node), bv = __ballot_sync(0xffffffffu, vox);
         if ((threadIdx.x & 31) == 0) { c.diag[4] += bn != 0u; c.diag[5] += bv != 0u; }
+        c.diag[2] += gate;
+        const unsigned b = __ballot_sync(0xffffffffu, gate);
+        if ((threadIdx.x & 31) == 0) c.diag[6] += b != 0u;
     }
     if (SYNC) __syncwarp();
     // ---- phase C: stencil evaluation: interpValue(time) (:652-657): pos = ray(time); stencil.moveTo(pos); interpolation(pos) - iso
-    if (COUNT && SYNC) {
-        const bool ev = active && (gate || (w.f & LsWalk::kInterp));
-        c.diag[2] += ev;
-        const unsigned b = __ballot_sync(0xffffffffu, ev);
-        if ((threadIdx.x & 31) == 0) c.diag[6] += b != 0u;
-    }
-    if (active && (gate || (w.f & LsWalk::kInterp))) {
-        if (!gate) tq = out.time;                                         // kInterp
-        w.f &= ~LsWalk::kInterp;
-        // refinement state (REFINE, after the crossing): mT[0..1], mV[0..1] of the crossing -- mT[1] is the voxel's exit time again (the
-        // DDA has not moved), mV[1] was left in out.gx by the iteration that found the crossing
-        double rT0 = w.T0, rT1 = REFINE ? cur.next() : 0.0;
-        float rV0 = w.V0, rV1 = REFINE ? out.gx : 0.f;
+    if (gate) {
 #pragma unroll 1
-        for (int n = 0;; ++n) {
-            const bool initPass = gate && (w.f & LsWalk::kLazy);
+        for (;;) {
+            const bool initPass = (w.f & LsWalk::kLazy) != 0u;
             const double te = initPass ? w.T0 : tq;
             const double px = ray.ex + ray.dx * te, py = ray.ey + ray.dy * te, pz = ray.ez + ray.dz * te;
             st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
-            if (initPass) { w.V0 = st.interpolation(px, py, pz) - iso; w.f &= ~LsWalk::kLazy; continue; }   // mV[0] = interpValue(mT[0])
-            if (!gate) {
-                if (REFINE && n < iters) {
-                    // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
-                    const float V = st.interpolation(px, py, pz) - iso;
-                    if (rV0 * V <= 0.0f) { rV1 = V; rT1 = tq; } else { rV0 = V; rT0 = tq; }
-                    tq = rT0 + (rT1 - rT0) * rV0 / (rV0 - rV1);
-                    continue;
-                }
-                // getWorldPosAndNml (:575-582): position and stencil gradient at the hit time
-                if (REFINE) out.time = tq;
-                out.px = px; out.py = py; out.pz = pz;
-                st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
+            const float V1 = st.interpolation(px, py, pz) - iso;
+            if (initPass) { w.V0 = V1; w.f &= ~LsWalk::kLazy; continue; }          // mV[0] = interpValue(mT[0])
+            if (w.V0 * V1 <= 0.0f) {                                              // math::ZeroCrossing (math/Math.h:821)
+                // The crossing: mTime = interpTime() (:646-650, float difference promoted to double).  The walk ends here; what is left of
+                // operator() -- the refinements -- and getWorldPosAndNml are lsFinishHit(), which the caller runs when it finishes the ray
+                // (the render kernel: after the tile's loop, for all its pixels together).  out.gx carries mV[1] to it, w.T0 / w.V0 and
+                // the DDA (whose next() is mT[1]) stay as they are.
+                out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);
+                out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
+                if (REFINE) out.gx = V1;
+                w.f &= ~LsWalk::kStep;
                 status = kWalkHit;
-            } else {
-                const float V1 = st.interpolation(px, py, pz) - iso;
-                if (w.V0 * V1 <= 0.0f) {                                          // math::ZeroCrossing (math/Math.h:821)
-                    out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);          // interpTime (:646-650): float diff promoted to double
-                    out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
-                    if (REFINE) out.gx = V1;
-                    w.f = (w.f | LsWalk::kInterp) & ~LsWalk::kStep;
-                } else { w.T0 = tq; w.V0 = V1; }                                  // no crossing: slide
-            }
+            } else { w.T0 = tq; w.V0 = V1; }                                      // no crossing: slide
             break;
         }
     }
@@ -706,6 +686,35 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     return status;
 }
 
+// The rest of a hit, after lsAdvance() has returned kWalkHit: LinearSearchImpl<GridT, Iterations>'s secant refinements of the hit time
+// (tools/RayIntersector.h:630-636; REFINE instantiations only, `iters` of them, each one stencil evaluation at the current estimate) and
+// getWorldPosAndNml (:575-582): position and stencil gradient at the hit time.
+template<bool COUNT, bool REFINE, int LEAF = kLeafFloat>
+__device__ __forceinline__ void lsFinishHit(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, const Ray& ray, float iso,
+                                            const LsWalk& w, LsHit& out, Counters& c, int iters = 0)
+{
+    double tq = out.time;
+    if (REFINE) {
+        // mT[0..1], mV[0..1] of the crossing: mT[1] is the voxel's exit time again (the DDA has not moved since), mV[1] was left in out.gx
+        double rT0 = w.T0, rT1 = w.cur.next();
+        float rV0 = w.V0, rV1 = out.gx;
+#pragma unroll 1
+        for (int n = 0; n < iters; ++n) {
+            // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)
+            const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
+            st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
+            const float V = st.interpolation(px, py, pz) - iso;
+            if (rV0 * V <= 0.0f) { rV1 = V; rT1 = tq; } else { rV0 = V; rT0 = tq; }
+            tq = rT0 + (rT1 - rT0) * rV0 / (rV0 - rV1);
+        }
+        out.time = tq;
+    }
+    const double px = ray.ex + ray.dx * tq, py = ray.ey + ray.dy * tq, pz = ray.ez + ray.dz * tq;
+    st.template moveTo<COUNT, LEAF>(g, s, acc, px, py, pz, c);
+    out.px = px; out.py = py; out.pz = pz;
+    st.gradient(g, px, py, pz, out.gx, out.gy, out.gz);
+}
+
 // plain per-thread form (arbitrary-ray batches)
 template<bool COUNT, int THREADS, int LEAF = kLeafFloat>
 __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm, TreeCursor& acc, Stencil& st, Ray& ray,
@@ -715,6 +724,7 @@ __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSm
 #pragma unroll 1
     for (;;) {
         const int r = lsAdvance<COUNT, false, THREADS, true, LEAF>(true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
+        if (r == kWalkHit) lsFinishHit<COUNT, true, LEAF>(g, s, acc, st, ray, iso, w, out, c, iters);
         if (r != kWalkContinue) return r == kWalkHit;
     }
 }

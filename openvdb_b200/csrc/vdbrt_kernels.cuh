@@ -312,6 +312,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         float4 s;
         if (hit) {
             if (COUNT) ++c.hits;
+            lsFinishHit<COUNT, REFINE, LEAF>(g, root, acc, st, ray, p.iso, walk, h, c, int(p.iters));
             // the shader wants the WORLD direction of the ray: rebuilt from the camera here (the same arithmetic on the same
             // inputs) rather than carried through the traversal in six registers
             Ray wr;
@@ -338,9 +339,9 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         // (0) the tile has used up its budget (the inner loop leaves when that happens): suspend the rays that are still running,
         // they continue in the long-ray rounds.  Kept out of the inner loop so that the hot loop is the same with and without it.
         if (LONG && spent > limit && !longFull && (!lb.tail || tail)) {
-            // a ray that already found its crossing just finishes; tail rule with lb.voxel_only: only rays that are marching voxels go
+            // tail rule with lb.voxel_only: only rays that are marching voxels go
             // to the rounds (the rounds parallelise leaf marches; a ray that is crossing empty nodes is walked by the scout no faster)
-            const bool sus = rayOn && !(walk.f & LsWalk::kInterp) && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
+            const bool sus = rayOn && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
             const unsigned m = __ballot_sync(0xffffffffu, sus);
             if (lb.tail) spent = 0;                                 // the lanes that stay are looked at again `tail` iterations later
             if (m && sc.cost_out && lane == 0 && curStrip != 0xffffffffu) { sc.cost_out[curStrip] = 0x7fffffffu; curStrip = 0xffffffffu; }
@@ -760,6 +761,7 @@ k_long_finish(const __grid_constant__ DevGrid g, const __grid_constant__ DevShad
         int status;
 #pragma unroll 1
         do { status = lsAdvance<false, false, kBlockThreads>(true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
+        if (status == kWalkHit) lsFinishHit<false, false>(g, root, acc, st, ray, p.iso, walk, h, c);
         writeLongPixel<AUX>(g, sh, p, film, aux, *r, status == kWalkHit, h);
     }
 }
