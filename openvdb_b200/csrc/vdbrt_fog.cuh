@@ -268,7 +268,7 @@ k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParam
     // every ray of this kernel has the direction p.sb (kernel parameters): the six direction registers of a lane are never anything else
     FogMarch m; m.idle();
     m.ray.dx = p.sb[0]; m.ray.dy = p.sb[1]; m.ray.dz = p.sb[2]; m.ray.ix = p.sb[3]; m.ray.iy = p.sb[4]; m.ray.iz = p.sb[5];
-    bool busy = false, pendExp = false, drained = false;
+    bool busy = false, pendExp = false, pendLum = false, drained = false;
     uint32_t rec = 0;
     double dens = 0.0, Sx = 1.0, Sy = 1.0, Sz = 1.0;
 
@@ -328,17 +328,19 @@ k_fog_shadow(const __grid_constant__ DevGrid g, const __grid_constant__ VolParam
                 if (Sx * Sx + Sy * Sy + Sz * Sz < p.cutoff) lum = true;                   // goto Luminance (:1054)
                 else m.tcur += p.sstep;
             }
-            // Luminance (:1058): the term of this sample, in the reference's order of multiplications
-            if (lum) {
-                FogRec* r = fw.recs + rec;
-                const double ax = p.albedo[0] * Sx * r->a[0] * (1.0 - r->dT[0]);
-                const double ay = p.albedo[1] * Sy * r->a[1] * (1.0 - r->dT[1]);
-                const double az = p.albedo[2] * Sz * r->a[2] * (1.0 - r->dT[2]);
-                r->a[0] = ax; r->a[1] = ay; r->a[2] = az;
-                busy = false; pendExp = false;
-            }
+            // the shadow ray is done: its lane stops; the sample's term is written after the loop, with those of the other finished lanes
+            if (lum) { busy = false; pendExp = false; pendLum = true; }
             const unsigned running = __ballot_sync(0xffffffffu, busy);
             if (running == 0u || (!drained && 32u - (unsigned)__popc(running) >= fw.refill)) break;
+        }
+        // Luminance (:1058): the term of this sample, in the reference's order of multiplications
+        if (pendLum) {
+            pendLum = false;
+            FogRec* r = fw.recs + rec;
+            const double ax = p.albedo[0] * Sx * r->a[0] * (1.0 - r->dT[0]);
+            const double ay = p.albedo[1] * Sy * r->a[1] * (1.0 - r->dT[1]);
+            const double az = p.albedo[2] * Sz * r->a[2] * (1.0 - r->dT[2]);
+            r->a[0] = ax; r->a[1] = ay; r->a[2] = az;
         }
     }
 }
