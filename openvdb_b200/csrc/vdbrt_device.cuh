@@ -558,7 +558,8 @@ struct LsWalk {
     enum : uint32_t {
         kSkip = 1u,       // the current cell was already handled (we just came back up): only step
         kStep = 2u,       // the current cell is done: step
-        kLazy = 4u        // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
+        kLazy = 4u,       // tester.init(T0) of this leaf visit has not been evaluated yet (V0 is not valid)
+        kIdle = 8u        // no ray: the lane of a warp-synchronous loop that has nothing to advance (every phase tests it with its own flag)
     };
     Dda cur;
     double T0;            // LinearSearchImpl::mT[0]
@@ -578,7 +579,7 @@ struct LsWalk {
 enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 
 // SYNC = true: the caller runs a warp-synchronous loop in which ALL 32 lanes call lsAdvance every iteration (lanes
-// without a ray pass active = false).  __syncwarp() between the phases makes the warp reconverge after each phase and
+// without a ray have LsWalk::kIdle set).  __syncwarp() between the phases makes the warp reconverge after each phase and
 // stops the compiler from cloning the later phases per control-flow path.  SYNC = false: plain per-thread use.
 // REFINE = true: LinearSearchImpl<GridT, Iterations> with Iterations = `iters` > 0 -- after the zero crossing the hit time is refined by
 // `iters` secant steps, each one stencil evaluation at the current estimate (tools/RayIntersector.h:630-636).  A separate instantiation:
@@ -589,7 +590,7 @@ enum { kWalkContinue = 0, kWalkHit = 1, kWalkMiss = 2 };
 // first gated one (kLazy) and never for the leaf visits in which no voxel passes: 1.4 of 8.6 evaluations per ray on C2.  Same
 // values in the same order -- the stencil's cache only makes moveTo cheaper, never changes what it returns.
 template<bool COUNT, bool SYNC, int THREADS, bool REFINE = false, int LEAF = kLeafFloat>
-__device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
+__device__ __forceinline__ int lsAdvance(const DevGrid& g, const RootSmem& s, WalkSmem<THREADS>& sm,
                                          TreeCursor& acc, Stencil& st, const Ray& ray, float iso, float vmin, float vmax,
                                          LsWalk& w, LsHit& out, Counters& c, int iters = 0)
 {
@@ -599,7 +600,7 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     const uint32_t fIn = w.f; const int lvlIn = w.lvl;       // (diagnostics only)
     double tq;                           // only read under `gate`
     // ---- phase B: probe the current cell
-    if (active && !(w.f & LsWalk::kStep)) {
+    if (!(w.f & (LsWalk::kStep | LsWalk::kIdle))) {
         if (w.f & LsWalk::kSkip) w.f ^= LsWalk::kSkip | LsWalk::kStep;
         else {
             const int depth = acc.descend(g, s, cur.vx, cur.vy, cur.vz);
@@ -635,7 +636,7 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
         }
     }
     if (COUNT && SYNC) {
-        const bool probed = active && !(fIn & (LsWalk::kStep | LsWalk::kSkip));
+        const bool probed = !(fIn & (LsWalk::kStep | LsWalk::kSkip | LsWalk::kIdle));
         const bool node = probed && lvlIn != 3, vox = probed && lvlIn == 3;
         c.diag[0] += node; c.diag[1] += vox;
         const unsigned bn = __ballot_sync(0xffffffffu, node), bv = __ballot_sync(0xffffffffu, vox);
@@ -672,12 +673,12 @@ __device__ __forceinline__ int lsAdvance(bool active, const DevGrid& g, const Ro
     if (SYNC) __syncwarp();
     // ---- phase D: while (dda.step()) ... ; an exhausted level returns false to its parent (DDA.h:158-159,174-175)
     if (COUNT && SYNC) {
-        const bool sp = active && (w.f & LsWalk::kStep);
+        const bool sp = (w.f & (LsWalk::kStep | LsWalk::kIdle)) == LsWalk::kStep;
         c.diag[3] += sp;
         const unsigned b = __ballot_sync(0xffffffffu, sp);
         if ((threadIdx.x & 31) == 0) c.diag[7] += b != 0u;
     }
-    if (active && (w.f & LsWalk::kStep)) {
+    if ((w.f & (LsWalk::kStep | LsWalk::kIdle)) == LsWalk::kStep) {
         w.f &= ~LsWalk::kStep;
         if (!cur.step(ray, w.shift)) {
             if (w.lvl == 0) status = kWalkMiss;
@@ -731,7 +732,7 @@ __device__ __forceinline__ bool intersectLevelSet(const DevGrid& g, const RootSm
     LsWalk w; w.begin(ray);
 #pragma unroll 1
     for (;;) {
-        const int r = lsAdvance<COUNT, false, THREADS, true, LEAF>(true, g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
+        const int r = lsAdvance<COUNT, false, THREADS, true, LEAF>(g, s, sm, acc, st, ray, iso, vmin, vmax, w, out, c, iters);
         if (r == kWalkHit) lsFinishHit<COUNT, true, LEAF>(g, s, acc, st, ray, iso, w, out, c, iters);
         if (r != kWalkContinue) return r == kWalkHit;
     }

@@ -274,14 +274,14 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     Stencil st; st.reset();
     Counters c = {};
     // per-lane pixel / ray state
-    bool hasPix = false, rayOn = false, drained = false;
+    bool hasPix = false, drained = false;               // a lane has a ray while !(walk.f & LsWalk::kIdle)
     uint32_t px = 0, py = 0, k = 0;
     size_t pix = 0;
     unsigned long long n = 0;
     float4 col = make_float4(0.f, 0.f, 0.f, 1.f);       // the pixel's background is re-read when a ray misses (the film is written once, at the end)
     Ray ray;
     LsWalk walk; LsHit h;
-    ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray);
+    ray.ex = ray.ey = ray.ez = 0.0; ray.setDir(1.0, 1.0, 1.0); ray.t0 = ray.t1 = 0.0; walk.begin(ray); walk.f = LsWalk::kIdle;
     h.time = 0.0; h.ix = h.iy = h.iz = 0; h.px = h.py = h.pz = 0.0; h.gx = h.gy = h.gz = 0.f;
     walk.cur.t0 = walk.cur.t1 = walk.cur.nx = walk.cur.ny = walk.cur.nz = 0.0; walk.cur.vx = walk.cur.vy = walk.cur.vz = 0;
     unsigned sNext = 0, sEnd = 0;                       // pixel slots of the warp's strip that are still to be handed out (warp-uniform)
@@ -341,7 +341,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         if (LONG && spent > limit && !longFull && (!lb.tail || tail)) {
             // tail rule with lb.voxel_only: only rays that are marching voxels go
             // to the rounds (the rounds parallelise leaf marches; a ray that is crossing empty nodes is walked by the scout no faster)
-            const bool sus = rayOn && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
+            const bool sus = !(walk.f & LsWalk::kIdle) && (!(lb.tail && lb.voxel_only) || walk.lvl == 3);
             const unsigned m = __ballot_sync(0xffffffffu, sus);
             if (lb.tail) spent = 0;                                 // the lanes that stay are looked at again `tail` iterations later
             if (m && sc.cost_out && lane == 0 && curStrip != 0xffffffffu) { sc.cost_out[curStrip] = 0x7fffffffu; curStrip = 0xffffffffu; }
@@ -355,7 +355,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                     Ray wr;
                     cameraRay(cam, px, py, 0.5, 0.5, wr);                 // LONG kernels are one sample per pixel
                     suspendRay(lb.rays[idx], ray, wr.dx, wr.dy, wr.dz, walk, wsm, acc, pix);
-                    rayOn = false; hasPix = false;
+                    walk.f = LsWalk::kIdle; hasPix = false;
                 }
             }
         }
@@ -426,7 +426,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             if (!hasPix) {
                 const unsigned ticket = sNext + __popc(idle & ((1u << lane) - 1u));
                 if (ticket < sEnd && ticketToPixel(tm, ticket, px, py)) {
-                    hasPix = true; rayOn = false; k = 0;
+                    hasPix = true; walk.f = LsWalk::kIdle; k = 0;
                     pix = size_t(py) * tm.width + px;
                     if (MULTI) n = 2ull * p.sub * pix;
                 }
@@ -436,14 +436,14 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         }
         // (2) start the next ray of the lane's pixel
         int status = kWalkContinue;
-        if (hasPix && !rayOn) {
+        if (hasPix && (walk.f & LsWalk::kIdle)) {
             const bool first = !MULTI || k == 0;
             cameraRay(cam, px, py, first ? 0.5 : p.jitter[n & 15], first ? 0.5 : p.jitter[(n + 1) & 15], ray);
             if (MULTI && !first) n += 2;
             if (COUNT) ++c.rays;
             // intersectsWS: setWorldRay = worldToIndex + clip (tools/RayIntersector.h:558-562)
             worldToIndex(g, ray);
-            if (clipRay(ray, g, 0)) { walk.begin(ray); rayOn = true; }
+            if (clipRay(ray, g, 0)) walk.begin(ray);                 // clears kIdle
             else status = kWalkMiss;
         }
         const bool canRefill = thr < 32u && (sNext < sEnd || (sc.eager && !drained));
@@ -451,7 +451,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         for (;;) {
             __syncwarp();
             if (COUNT) {
-                const unsigned live = __popc(__ballot_sync(0xffffffffu, rayOn));
+                const unsigned live = __popc(__ballot_sync(0xffffffffu, !(walk.f & LsWalk::kIdle)));
                 ++tileIters; tileActive += live;
                 if (lane == 0) atomicAdd(counters + 16 + (live + 3u) / 4u, 1ull);      // histogram of running lanes per iteration: 0, 1-4, 5-8, ..., 29-32
             }
@@ -465,25 +465,25 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
             // (3) advance running rays by one step (all lanes call it: it re-synchronises the warp between its phases).
             // Deferring the rare phases (level set-up, stencil) until several lanes want them was measured: no gain.
             {
-                const int r = lsAdvance<COUNT, true, kBlockThreads, REFINE, LEAF>(rayOn, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
-                if (rayOn) status = r;
+                const int r = lsAdvance<COUNT, true, kBlockThreads, REFINE, LEAF>(g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c, int(p.iters));
+                if (r != kWalkContinue) status = r;          // (idle lanes return kWalkContinue and keep the status of their finished ray)
             }
             __syncwarp();
             // (4) a ray ended.  One sample per pixel: the lane just stops; its pixel is shaded and written after the loop, together with
             // the other pixels of the tile (VDBRT_SHADE_AT_END) -- otherwise: shade / composite now, then next sample or write the pixel
             if (status != kWalkContinue) {
-                rayOn = false;
+                walk.f = LsWalk::kIdle;
                 if (MULTI || !VDBRT_SHADE_AT_END) finishRay(status);
             }
             // back to the outer loop when a lane wants its next ray, when enough lanes are idle and the strip has pixels for them,
             // or when nothing is running any more
-            const unsigned running = __ballot_sync(0xffffffffu, rayOn);
-            if (running == 0u || (canRefill && 32u - (unsigned)__popc(running) >= thr) || (MULTI && __any_sync(0xffffffffu, hasPix && !rayOn))) break;
+            const unsigned running = __ballot_sync(0xffffffffu, !(walk.f & LsWalk::kIdle));
+            if (running == 0u || (canRefill && 32u - (unsigned)__popc(running) >= thr) || (MULTI && __any_sync(0xffffffffu, hasPix && (walk.f & LsWalk::kIdle)))) break;
             if (LONG && spent > limit && !longFull && (!lb.tail || tail)) break;
         }
         if (!MULTI && VDBRT_SHADE_AT_END) {
             __syncwarp();
-            if (hasPix && !rayOn && status != kWalkContinue) finishRay(status);
+            if (hasPix && status != kWalkContinue) finishRay(status);
         }
     }
     if (COUNT) { flushCounters(c, counters); flushDiag(c, counters + 32); }
@@ -534,7 +534,7 @@ k_probe_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevC
                 LsHit h = {};
 #pragma unroll 1
                 for (; it < cap; ++it)
-                    if (lsAdvance<false, false, kBlockThreads>(true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, w, h, c) != kWalkContinue) break;
+                    if (lsAdvance<false, false, kBlockThreads>(g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, w, h, c) != kWalkContinue) break;
             }
         }
         const uint32_t strip = item / stripTiles;
@@ -760,7 +760,7 @@ k_long_finish(const __grid_constant__ DevGrid g, const __grid_constant__ DevShad
         resumeRay(*r, ray, walk, wsm, acc);
         int status;
 #pragma unroll 1
-        do { status = lsAdvance<false, false, kBlockThreads>(true, g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
+        do { status = lsAdvance<false, false, kBlockThreads>(g, root, wsm, acc, st, ray, p.iso, p.vmin, p.vmax, walk, h, c); } while (status == kWalkContinue);
         if (status == kWalkHit) lsFinishHit<false, false>(g, root, acc, st, ray, p.iso, walk, h, c);
         writeLongPixel<AUX>(g, sh, p, film, aux, *r, status == kWalkHit, h);
     }
