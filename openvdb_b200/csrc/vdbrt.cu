@@ -326,10 +326,11 @@ int vdbrt_create(int device, vdbrt_ctx** out)
     ev = std::getenv("VDBRT_LS_ROUNDS");
     ctx->ls_rounds = ev ? uint32_t(std::strtoul(ev, nullptr, 10)) : uint32_t(kDefaultRounds);
     if (ctx->ls_rounds > uint32_t(kMaxRounds)) ctx->ls_rounds = kMaxRounds;
-    // leaf visits per ray and round: small first (most suspended rays hit within a few leaves), then everything (every
-    // round costs the latency of one scout walk and one leaf march whatever the number of rays: two rounds measured best,
-    // 1.00 -> 0.83 ms per rank at 1/8 of C2 against the six rounds 2,4,12,32,64,128)
-    static const uint32_t kLeaves[kMaxRounds] = {8, 128, 128, 128, 128, 128, 128, 128};
+    // leaf visits per ray and round.  Every round costs the latency of one scout walk and one leaf march whatever the number of rays.
+    // With the tail rule (only the rays of the last tiles are suspended, and late) ONE round of 64 leaf visits measured best -- C2 at 1/8 of
+    // the frame 0.56 -> 0.51 ms, at 1/4 0.80 -> 0.73 ms against the two rounds (8, then 128) that were best under round 1's per-tile budget;
+    // what is still alive after it is walked in line by k_long_finish (profiles/r02_summary.md 8c).
+    static const uint32_t kLeaves[kMaxRounds] = {64, 256, 256, 256, 256, 256, 256, 256};
     for (int r = 0; r < kMaxRounds; ++r) ctx->ls_leaves[r] = kLeaves[r];
     // feeding of the render warps (Sched, vdbrt_kernels.cuh); defaults measured on the B200 (profiles/r02_summary.md)
     auto envU = [](const char* name, uint32_t dflt) { const char* e = std::getenv(name); return e ? uint32_t(std::strtoul(e, nullptr, 10)) : dflt; };

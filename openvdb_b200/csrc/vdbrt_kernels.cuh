@@ -168,7 +168,7 @@ __device__ __forceinline__ float4 shadeHit(const DevGrid& g, const DevShader& sh
 // Long rays.  A ray that grazes the surface marches hundreds of narrow-band voxels; one such ray per warp keeps the
 // whole warp (and, at the end of the frame, the whole GPU) waiting.  The render kernel therefore gives every 8x4 tile a
 // BUDGET of warp iterations; rays still running after that are suspended into LongRay records and finished by
-// "rounds" of two homogeneous kernels (default: two rounds, K = 8 then 128 leaf visits per ray):
+// "rounds" of two homogeneous kernels (default: one round of K = 64 leaf visits per ray):
 //   scout   one thread per long ray first RESOLVES the previous round -- the first segment with a hit wins -> shade + film;
 //           walked out of the grid -> miss -- and otherwise walks the node levels only (root/upper/lower DDAs) and writes
 //           the next K leaf visits (time range + leaf handle) it finds as segments;
@@ -182,7 +182,7 @@ constexpr int kMaxRounds = 8;
 constexpr uint32_t kDefaultTail = 24;     // tail rule: warp iterations a tile may still spend once the queue has run dry
 constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
-constexpr int kDefaultRounds = 2;
+constexpr int kDefaultRounds = 1;
 constexpr double kRoundsMaxTilesPerSm = 192.0;   // rounds are on by default only below this (12 tiles per warp at 16 warps / SM; see launchLevelSet)
 
 struct LongRay {
