@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 600 python tools/sweep14.py < /dev/null 2>&1 | tail -14
+timeout 600 python tools/sweep15.py < /dev/null 2>&1 | tail -14
