@@ -730,6 +730,9 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
                             : (multi ? k_render_levelset<false, false, false, true, true> : k_render_levelset<false, false, false, false, true>))
         : wantAux ? (rounds ? k_render_levelset<true, false, true, false> : multi ? k_render_levelset<true, false, false, true> : k_render_levelset<true, false, false, false>)
                   : (rounds ? k_render_levelset<false, false, true, false> : multi ? k_render_levelset<false, false, false, true> : k_render_levelset<false, false, false, false>);
+    // very many tiles per SM: the throughput-bound instantiation (6 CTAs per SM)
+    if (ctx->ls_dense && grid->leaf_kind == kLeafFloat && !dCounters && !refine && !rounds && !multi && double(tm.items) / double(ctx->sm_count) >= kDenseMinTilesPerSm)
+        kern = wantAux ? (KernT)k_render_levelset<true, false, false, false, false, kLeafFloat, true> : (KernT)k_render_levelset<false, false, false, false, false, kLeafFloat, true>;
     const int blocks = persistentGrid(ctx, (const void*)kern, nStrips);
     static const bool debugExit = std::getenv("VDBRT_DEBUG_EXIT") != nullptr;
     const size_t nWarps = size_t(blocks) * (kBlockThreads / 32);
@@ -1151,7 +1154,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     struct { const char* name; uint32_t* field; } table[] = {
         {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order}, {"ls_history", &ctx->ls_history}, {"ls_hist_a", &ctx->ls_hist_a}, {"ls_hist_b", &ctx->ls_hist_b},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
-        {"ls_rounds", &ctx->ls_rounds}, {"fog_wave", &ctx->fog_wave}, {"quant_native", &ctx->quant_native}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
+        {"ls_rounds", &ctx->ls_rounds}, {"ls_dense", &ctx->ls_dense}, {"fog_wave", &ctx->fog_wave}, {"quant_native", &ctx->quant_native}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };
     for (auto& t : table) if (k == t.name) {
         if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;

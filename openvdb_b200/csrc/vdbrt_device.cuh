@@ -657,13 +657,11 @@ __device__ __forceinline__ int lsAdvance(const DevGrid& g, const RootSmem& s, Wa
             const float V1 = st.interpolation(px, py, pz) - iso;
             if (initPass) { w.V0 = V1; w.f &= ~LsWalk::kLazy; continue; }          // mV[0] = interpValue(mT[0])
             if (w.V0 * V1 <= 0.0f) {                                              // math::ZeroCrossing (math/Math.h:821)
-                // The crossing: mTime = interpTime() (:646-650, float difference promoted to double).  The walk ends here; what is left of
-                // operator() -- the refinements -- and getWorldPosAndNml are lsFinishHit(), which the caller runs when it finishes the ray
-                // (the render kernel: after the tile's loop, for all its pixels together).  out.gx carries mV[1] to it, w.T0 / w.V0 and
-                // the DDA (whose next() is mT[1]) stay as they are.
-                out.time = w.T0 + (tq - w.T0) * w.V0 / (w.V0 - V1);
-                out.ix = cur.vx; out.iy = cur.vy; out.iz = cur.vz;
-                if (REFINE) out.gx = V1;
+                // The crossing.  The walk ends here; what is left of operator() -- mTime = interpTime(), the refinements -- and
+                // getWorldPosAndNml are lsFinishHit(), which the caller runs when it finishes the ray (the render kernel: after the tile's
+                // loop, for all its pixels together).  ONE register carries the hit to it: mV[1] in out.gx; mT[0] / mV[0] are w.T0 / w.V0,
+                // mT[1] is the next() and the hit voxel the position of the DDA, which stays where it is.
+                out.gx = V1;
                 w.f &= ~LsWalk::kStep;
                 status = kWalkHit;
             } else { w.T0 = tq; w.V0 = V1; }                                      // no crossing: slide
@@ -702,11 +700,13 @@ template<bool COUNT, bool REFINE, int LEAF = kLeafFloat>
 __device__ __forceinline__ void lsFinishHit(const DevGrid& g, const RootSmem& s, TreeCursor& acc, Stencil& st, const Ray& ray, float iso,
                                             const LsWalk& w, LsHit& out, Counters& c, int iters = 0)
 {
-    double tq = out.time;
+    // mT[0..1], mV[0..1] of the crossing: mT[1] is the voxel's exit time again (the DDA has not moved since), mV[1] was left in out.gx
+    double rT0 = w.T0, rT1 = w.cur.next();
+    float rV0 = w.V0, rV1 = out.gx;
+    double tq = rT0 + (rT1 - rT0) * rV0 / (rV0 - rV1);                            // interpTime (:646-650): float difference promoted to double
+    out.time = tq;
+    out.ix = w.cur.vx; out.iy = w.cur.vy; out.iz = w.cur.vz;
     if (REFINE) {
-        // mT[0..1], mV[0..1] of the crossing: mT[1] is the voxel's exit time again (the DDA has not moved since), mV[1] was left in out.gx
-        double rT0 = w.T0, rT1 = w.cur.next();
-        float rV0 = w.V0, rV1 = out.gx;
 #pragma unroll 1
         for (int n = 0; n < iters; ++n) {
             // V = interpValue(mTime); m = ZeroCrossing(mV[0], V); mV[m] = V; mT[m] = mTime; mTime = interpTime() (:631-635)

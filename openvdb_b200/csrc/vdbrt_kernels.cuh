@@ -101,6 +101,9 @@ __device__ __forceinline__ void flushDiag(const Counters& c, unsigned long long*
 #ifndef VDBRT_SHADE_AT_END
 #define VDBRT_SHADE_AT_END 1
 #endif
+#ifndef VDBRT_MINBLOCKS_DENSE
+#define VDBRT_MINBLOCKS_DENSE 6
+#endif
 #ifndef VDBRT_MINBLOCKS_LONG
 #define VDBRT_MINBLOCKS_LONG 4
 #endif
@@ -183,6 +186,7 @@ constexpr uint32_t kDefaultTail = 24;     // tail rule: warp iterations a tile m
 constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
 constexpr int kDefaultRounds = 1;
+constexpr double kDenseMinTilesPerSm = 800.0;   // the 6-CTA instantiation from this many 8x4 tiles per SM on (one-sample float frames without rounds)
 constexpr double kRoundsMaxTilesPerSm = 192.0;   // rounds are on by default only below this (12 tiles per warp at 16 warps / SM; see launchLevelSet)
 
 struct LongRay {
@@ -243,8 +247,11 @@ __device__ __forceinline__ void resumeRay(const LongRay& r, Ray& ray, LsWalk& w,
 
 // MULTI = false: one sample per pixel (no sample accumulator, sample counter or jitter index in registers).
 // REFINE = true: LinearSearchImpl's secant refinements (p.iters > 0), see lsAdvance.
-template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false, int LEAF = kLeafFloat>
-__global__ void __launch_bounds__(kBlockThreads, LONG ? VDBRT_MINBLOCKS_LONG : VDBRT_MINBLOCKS)
+// DENSE = true: 6 CTAs per SM (80 registers, some spills inside the loop) -- for launches with very many tiles per SM, which are bound by
+// throughput (C4, 1 751 tiles per SM: 26.4 -> 24.7 ms); with fewer tiles the longer critical path of the heaviest tile costs more than the
+// extra warps bring (C2, 438 tiles per SM: 1.76 -> 1.88 ms), see launchLevelSet.
+template<bool AUX, bool COUNT, bool LONG, bool MULTI, bool REFINE = false, int LEAF = kLeafFloat, bool DENSE = false>
+__global__ void __launch_bounds__(kBlockThreads, LONG ? VDBRT_MINBLOCKS_LONG : (DENSE ? VDBRT_MINBLOCKS_DENSE : VDBRT_MINBLOCKS))
 k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ DevCamera cam, const __grid_constant__ DevShader sh,
                   const __grid_constant__ LsParams p, const __grid_constant__ TileMap tm, float4* film,
                   AuxOut aux, unsigned int* queue, unsigned long long* counters, const __grid_constant__ LongBufs lb,
@@ -275,8 +282,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     Counters c = {};
     // per-lane pixel / ray state
     bool hasPix = false, drained = false;               // a lane has a ray while !(walk.f & LsWalk::kIdle)
-    uint32_t px = 0, py = 0, k = 0;
-    size_t pix = 0;
+    uint32_t px = 0, py = 0, k = 0;                      // (the pixel's index in the film is rebuilt from these where it is needed)
     unsigned long long n = 0;
     float4 col = make_float4(0.f, 0.f, 0.f, 1.f);       // the pixel's background is re-read when a ray misses (the film is written once, at the end)
     Ray ray;
@@ -308,6 +314,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
     // is running: nothing of the outer loop's bookkeeping is executed per traversal step.
     // shade / composite the ray that ended with `status`, then next sample or write the pixel
     auto finishRay = [&](int& status) {
+        const size_t pix = size_t(py) * tm.width + px;
         const bool hit = status == kWalkHit;
         float4 s;
         if (hit) {
@@ -354,7 +361,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 if (sus && idx < lb.capLong) {
                     Ray wr;
                     cameraRay(cam, px, py, 0.5, 0.5, wr);                 // LONG kernels are one sample per pixel
-                    suspendRay(lb.rays[idx], ray, wr.dx, wr.dy, wr.dz, walk, wsm, acc, pix);
+                    suspendRay(lb.rays[idx], ray, wr.dx, wr.dy, wr.dz, walk, wsm, acc, size_t(py) * tm.width + px);
                     walk.f = LsWalk::kIdle; hasPix = false;
                 }
             }
@@ -427,8 +434,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
                 const unsigned ticket = sNext + __popc(idle & ((1u << lane) - 1u));
                 if (ticket < sEnd && ticketToPixel(tm, ticket, px, py)) {
                     hasPix = true; walk.f = LsWalk::kIdle; k = 0;
-                    pix = size_t(py) * tm.width + px;
-                    if (MULTI) n = 2ull * p.sub * pix;
+                    if (MULTI) n = 2ull * p.sub * (size_t(py) * tm.width + px);
                 }
             }
             sNext += nIdle;

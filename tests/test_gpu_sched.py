@@ -127,3 +127,33 @@ def test_history_ordering_over_a_sequence_of_frames(tuned, oracle, torus_small, 
         ctx.render_levelset(g, cam, sh, film, opts=ctx.ls_opts(spp=3, seed=1))
         assert np.array_equal(film, want5)
     g.free(); g2.free()
+
+
+def test_dense_instantiation_for_frames_with_many_tiles(ctx, oracle, torus_small):
+    """from kDenseMinTilesPerSm (800) 8x4 tiles per SM on, one-sample float frames run the 6-CTA instantiation of the render kernel
+    (ls_dense, default on): the same film and records as the standard instantiation, and as the oracle on a sample of the pixels"""
+    g = ctx.upload(torus_small.buf)
+    W, H = 2560, 1600                     # 128 000 tiles: 865 per SM on a B200
+    cam = api.vdb_render_camera(W, H, (0.0, 90.0, 255.0), (0, 0, 0))
+    sh = api.make_shader(abi.SHADER_DIFFUSE)
+    out = {}
+    try:
+        for dense in (1, 0):
+            ctx.set_tuning(ls_dense=dense)
+            for want_aux in (True, False):
+                film = refapi.new_film(W, H)
+                aux = refapi.AuxArrays(W, H)
+                ctx.render_levelset(g, cam, sh, film, aux=aux.pod() if want_aux else None)
+                out[dense, want_aux] = (film, aux)
+    finally:
+        ctx.set_tuning(ls_dense=1)
+    assert out[1, True][1].hit.sum() > 500000
+    assert np.array_equal(out[1, True][0], out[0, True][0]) and np.array_equal(out[1, False][0], out[0, False][0])
+    assert np.array_equal(out[1, True][0], out[1, False][0])
+    assert_records_equal(out[1, True][1], out[0, True][1])
+    # against the oracle: a band of rows through the middle of the frame (a partition of the oracle's render)
+    ofilm = refapi.new_film(W, H)
+    oaux, _ = oracle.render_levelset(torus_small.oracle_handle, cam, sh, ofilm, aux=True, threads=8, part=api.partition(3, 16, 2560, 100))
+    rows = slice(300, 400)
+    assert np.array_equal(ofilm[rows], out[1, True][0][rows])
+    assert np.array_equal(oaux.hit[rows], out[1, True][1].hit[rows]) and np.array_equal(oaux.ijk[rows], out[1, True][1].ijk[rows])
