@@ -308,7 +308,7 @@ int  vdbrt_count_volume(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_came
 int  vdbrt_last_kernel_ms(vdbrt_ctx* ctx, float* ms, uint32_t* launches);
 /* Scheduling knobs of one context (the environment variables VDBRT_LS_* / VDBRT_FOG_* set the same values when the
  * context is created; this call is for tests and for measuring one setting against another in one process).  Keys:
- * "ls_strip", "ls_strip_ratio", "ls_refill", "ls_eager", "ls_order", "ls_history", "ls_hist_a", "ls_hist_b", "ls_probe_cap", "ls_probe_b", "ls_tail", "ls_budget", "ls_factor", "ls_rounds", "ls_dense", "ls_leaves0" .. "ls_leaves7", "fog_wave", "fog_refill", "fog_rec_per_ray", "fog_cap_mb".
+ * "ls_strip", "ls_strip_ratio", "ls_refill", "ls_eager", "ls_order", "ls_history", "ls_hist_a", "ls_hist_b", "ls_probe_cap", "ls_probe_b", "ls_tail", "ls_budget", "ls_factor", "ls_rounds", "ls_dense", "ls_dense_factor", "ls_leaves0" .. "ls_leaves7", "fog_wave", "fog_refill", "fog_rec_per_ray", "fog_cap_mb".
  * None of them changes a pixel.  Unknown key -> VDBRT_ERR_INVALID_ARG.                                           */
 int  vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value);
 

@@ -371,6 +371,7 @@ void vdbrt_destroy(vdbrt_ctx* ctx)
     if (ctx->ord) cudaFree(ctx->ord);
     if (ctx->hist) cudaFree(ctx->hist);
     if (ctx->fog) cudaFree(ctx->fog);
+    if (ctx->hist_host) cudaFreeHost(ctx->hist_host);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -677,7 +678,9 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
             ctx->hist_valid = 0;
         }
         uint8_t* hb = static_cast<uint8_t*>(ctx->hist);
-        sc.cost_sum = reinterpret_cast<unsigned long long*>(hb); sc.cost_out = reinterpret_cast<uint32_t*>(hb + oCost);
+        sc.cost_sum = reinterpret_cast<unsigned long long*>(hb); sc.cost_max = reinterpret_cast<uint32_t*>(hb + 8); sc.cost_out = reinterpret_cast<uint32_t*>(hb + oCost);
+        if (!ctx->hist_host) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hist_host), 16, cudaHostAllocDefault));
+        if (!same) ctx->hist_host[0] = ctx->hist_host[1] = 0ull;
         if (same) {
             const size_t oCls = 256, oA = oCls + up(n), oB = oA + up(4 * n), totalB = oB + up(4 * n);
             if (int rc = ensureBuffer(&ctx->ord, &ctx->ord_cap, totalB)) return rc;
@@ -690,7 +693,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
             sc.ctl = ob.ctl; sc.listA = ob.listA; sc.listB = ob.listB; sc.cls = ob.cls;
             ++launches;
         }
-        CUDA_TRY(cudaMemsetAsync(sc.cost_sum, 0, 8, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(sc.cost_sum, 0, 16, ctx->stream));                    // sum and max
         static_assert(sizeof(TileMap) <= sizeof(ctx->hist_tm), "history key");
         std::memcpy(ctx->hist_tm, &tm, sizeof(tm)); ctx->hist_grid = grid; ctx->hist_spp = opts->spp; ctx->hist_valid = 1;
     }
@@ -730,8 +733,25 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
                             : (multi ? k_render_levelset<false, false, false, true, true> : k_render_levelset<false, false, false, false, true>))
         : wantAux ? (rounds ? k_render_levelset<true, false, true, false> : multi ? k_render_levelset<true, false, false, true> : k_render_levelset<true, false, false, false>)
                   : (rounds ? k_render_levelset<false, false, true, false> : multi ? k_render_levelset<false, false, false, true> : k_render_levelset<false, false, false, false>);
-    // very many tiles per SM: the throughput-bound instantiation (6 CTAs per SM)
-    if (ctx->ls_dense && grid->leaf_kind == kLeafFloat && !dCounters && !refine && !rounds && !multi && double(tm.items) / double(ctx->sm_count) >= kDenseMinTilesPerSm)
+    // The throughput-bound instantiation (6 CTAs per SM, DENSE).  It pays unless the launch is as long as the critical path of its heaviest
+    // tile, which more warps per SM only stretch (C4 whole and at 1/2, 1/4, 1/8 of the frame: -6 %; C1: -4 %; C2 whole / at 1/2: +5 / +3 %).
+    // With the tile costs of the previous frame of this sequence (sum and max, copied back asynchronously after every frame and read here
+    // without a sync: a hint, possibly one frame old) the rule is just that: a warp's share of the summed tile times against the longest tile
+    // (measured ratios: C2 at 1/2 0.50, C2 0.84 | C1 1.16, C4 at 1/8 1.42, 1/4 2.75, 1/2 5.6, whole 11.0 -- the bar is the threshold, 1.0).
+    // Without them: very many tiles per SM only.
+    bool dense = false;
+    if (ctx->ls_dense && grid->leaf_kind == kLeafFloat && !dCounters && !refine && !rounds && !multi) {
+        const unsigned long long hsum = history && ctx->hist_host ? *reinterpret_cast<volatile unsigned long long*>(ctx->hist_host) : 0ull;
+        const unsigned long long hmax = history && ctx->hist_host ? (*reinterpret_cast<volatile unsigned long long*>(ctx->hist_host + 1) & 0xffffffffull) : 0ull;
+        if (hsum && hmax && hmax < 0x7fffffffull)
+            dense = double(hsum) / (double(ctx->sm_count) * VDBRT_MINBLOCKS_DENSE * (kBlockThreads / 32)) >= 0.01 * double(ctx->ls_dense_factor) * double(hmax);
+        else dense = double(tm.items) / double(ctx->sm_count) >= double(ctx->ls_dense);
+        static const bool debugDense = std::getenv("VDBRT_DEBUG_DENSE") != nullptr;
+        if (debugDense)
+            std::fprintf(stderr, "[vdbrt] dense? tiles %u, previous frame: sum %llu max %llu -> a warp's share / heaviest tile = %.3f -> %s\n", tm.items, hsum, hmax,
+                         hmax ? double(hsum) / (double(ctx->sm_count) * VDBRT_MINBLOCKS_DENSE * (kBlockThreads / 32)) / double(hmax) : 0.0, dense ? "6 CTAs" : "5 CTAs");
+    }
+    if (dense)
         kern = wantAux ? (KernT)k_render_levelset<true, false, false, false, false, kLeafFloat, true> : (KernT)k_render_levelset<false, false, false, false, false, kLeafFloat, true>;
     const int blocks = persistentGrid(ctx, (const void*)kern, nStrips);
     static const bool debugExit = std::getenv("VDBRT_DEBUG_EXIT") != nullptr;
@@ -741,6 +761,7 @@ static int launchLevelSet(vdbrt_ctx* ctx, const vdbrt_grid* grid, const vdbrt_ca
         sc.warp_exit = static_cast<unsigned long long*>(ctx->io);
     }
     kern<<<blocks, kBlockThreads, 0, ctx->stream>>>(grid->dgrid, dc, sh, p, tm, dFilm, aux, queue, dCounters, lb, sc);
+    if (history && ctx->hist_host) CUDA_TRY(cudaMemcpyAsync(ctx->hist_host, sc.cost_sum, 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (debugExit) {
         // when did the warps leave?  (the tail of the frame: time between the mean and the last exit)
         std::vector<unsigned long long> t(nWarps + 1);
@@ -1154,7 +1175,7 @@ int vdbrt_set_tuning(vdbrt_ctx* ctx, const char* key, uint32_t value)
     struct { const char* name; uint32_t* field; } table[] = {
         {"ls_strip", &ctx->ls_strip}, {"ls_strip_ratio", &ctx->ls_strip_ratio}, {"ls_refill", &ctx->ls_refill}, {"ls_eager", &ctx->ls_eager}, {"ls_affine", &ctx->ls_affine}, {"ls_order", &ctx->ls_order}, {"ls_history", &ctx->ls_history}, {"ls_hist_a", &ctx->ls_hist_a}, {"ls_hist_b", &ctx->ls_hist_b},
         {"ls_probe_cap", &ctx->ls_probe_cap}, {"ls_probe_b", &ctx->ls_probe_b}, {"ls_budget", &ctx->ls_budget}, {"ls_tail", &ctx->ls_tail}, {"ls_voxel_only", &ctx->ls_voxel_only}, {"ls_factor", &ctx->ls_factor},
-        {"ls_rounds", &ctx->ls_rounds}, {"ls_dense", &ctx->ls_dense}, {"fog_wave", &ctx->fog_wave}, {"quant_native", &ctx->quant_native}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
+        {"ls_rounds", &ctx->ls_rounds}, {"ls_dense", &ctx->ls_dense}, {"ls_dense_factor", &ctx->ls_dense_factor}, {"fog_wave", &ctx->fog_wave}, {"quant_native", &ctx->quant_native}, {"fog_refill", &ctx->fog_refill}, {"fog_rec_per_ray", &ctx->fog_rec_per_ray}, {"fog_cap_mb", &ctx->fog_cap_mb},
     };
     for (auto& t : table) if (k == t.name) {
         if (t.field == &ctx->ls_rounds && value > uint32_t(kMaxRounds)) value = kMaxRounds;

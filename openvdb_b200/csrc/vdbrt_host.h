@@ -25,7 +25,9 @@ struct vdbrt_ctx {
     uint32_t quant_native = 1;                  // NanoGrid<Fp8|Fp16> rendered as they are (their own kernel instantiations) instead of expanded to float leaves
     uint32_t fog_wave = 1, fog_refill = 8, fog_rec_per_ray = 12, fog_cap_mb = 4096;
     uint32_t ls_voxel_only = 0;                 // tail rule: only rays that are marching voxels are suspended
-    uint32_t ls_dense = 1;                      // 1: launches with very many tiles per SM use the 6-CTA instantiation (kDenseMinTilesPerSm)
+    uint32_t ls_dense_factor = 100;             // percent, see launchLevelSet
+    unsigned long long* hist_host = nullptr;    // pinned: {sum, max} of the previous frame's tile costs, copied back asynchronously (a hint, read without a sync)
+    uint32_t ls_dense = 800;                    // launches with at least this many 8x4 tiles per SM use the 6-CTA instantiation (0: never; kDenseMinTilesPerSm)
     uint32_t ls_tail = 0;                       // tail rule: iterations a tile may still spend once the work queue has run dry (0: per-tile rule below)
     uint32_t ls_budget = 0;                     // warp iterations a tile may spend before its running rays are suspended (0 = never)
     uint32_t ls_factor = 0;                     // ... or this many percent of a warp's share of the launch, if that is more

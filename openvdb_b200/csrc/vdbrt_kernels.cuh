@@ -128,6 +128,7 @@ struct Sched {
     uint32_t nq;
     uint32_t* cost_out;          // history: SM clock cycles / 16 each tile of THIS frame took (null: not recorded); cost_sum: their sum
     unsigned long long* cost_sum;
+    uint32_t* cost_max;          // history: the largest of them (the critical path of the frame's heaviest tile)
     unsigned long long* warp_exit;   // diagnostics (VDBRT_DEBUG_EXIT): %globaltimer of every warp when it leaves the kernel, [0] = launch start
     const uint32_t* ctl;         // [0], [1]: strips in the two heavy lists (null: no ordering)
     const uint32_t* listA; const uint32_t* listB;
@@ -186,7 +187,8 @@ constexpr uint32_t kDefaultTail = 24;     // tail rule: warp iterations a tile m
 constexpr uint32_t kDefaultBudget = 160;  // per-tile rule (VDBRT_LS_TAIL=0): warp iterations per 8x4 tile before its running rays are suspended ...
 constexpr uint32_t kDefaultFactor = 50;   // ... or this many percent of a warp's fair share of the launch
 constexpr int kDefaultRounds = 1;
-constexpr double kDenseMinTilesPerSm = 800.0;   // the 6-CTA instantiation from this many 8x4 tiles per SM on (one-sample float frames without rounds)
+constexpr uint32_t kDenseMinTilesPerSm = 800;   // default of ls_dense: without tile costs of a previous frame, the 6-CTA instantiation from this many 8x4 tiles per SM on
+constexpr uint32_t kDenseFactor = 100;          // default of ls_dense_factor (percent): with them, when a warp's share of the summed tile times is at least this much of the heaviest tile
 constexpr double kRoundsMaxTilesPerSm = 192.0;   // rounds are on by default only below this (12 tiles per warp at 16 warps / SM; see launchLevelSet)
 
 struct LongRay {
@@ -380,7 +382,7 @@ k_render_levelset(const __grid_constant__ DevGrid g, const __grid_constant__ Dev
         if (sc.cost_out && idle == 0xffffffffu && sNext >= sEnd && curStrip != 0xffffffffu) {
             if (lane == 0) {
                 const unsigned cost = (unsigned(clock()) - tileT0) >> 4;            // 16-cycle units: stays far below the 'suspended' mark
-                sc.cost_out[curStrip] = cost; atomicAdd(sc.cost_sum, (unsigned long long)cost);
+                sc.cost_out[curStrip] = cost; atomicAdd(sc.cost_sum, (unsigned long long)cost); atomicMax(sc.cost_max, cost);
             }
             curStrip = 0xffffffffu;
         }

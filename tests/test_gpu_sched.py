@@ -139,14 +139,14 @@ def test_dense_instantiation_for_frames_with_many_tiles(ctx, oracle, torus_small
     out = {}
     try:
         for dense in (1, 0):
-            ctx.set_tuning(ls_dense=dense)
+            ctx.set_tuning(ls_dense=800 if dense else 0)
             for want_aux in (True, False):
                 film = refapi.new_film(W, H)
                 aux = refapi.AuxArrays(W, H)
                 ctx.render_levelset(g, cam, sh, film, aux=aux.pod() if want_aux else None)
                 out[dense, want_aux] = (film, aux)
     finally:
-        ctx.set_tuning(ls_dense=1)
+        ctx.set_tuning(ls_dense=800)
     assert out[1, True][1].hit.sum() > 500000
     assert np.array_equal(out[1, True][0], out[0, True][0]) and np.array_equal(out[1, False][0], out[0, False][0])
     assert np.array_equal(out[1, True][0], out[1, False][0])
