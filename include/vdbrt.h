@@ -261,6 +261,9 @@ int  vdbrt_camera_orthographic(vdbrt_camera* cam, uint32_t width, uint32_t heigh
                                const double translation[3], double frame_width, double near_plane, double far_plane);
 /* BaseCamera::lookAt (RayTracer.h:379-389); like the reference it silently keeps the camera on failure.         */
 int  vdbrt_camera_look_at(vdbrt_camera* cam, const double xyz[3], const double up[3]);
+/* PerspectiveCamera::getRay (RayTracer.h:452-462) / OrthographicCamera::getRay (:505-512) for n pixels, on the host: `pixels` holds n
+ * (i, j) pairs, `offsets` n (iOffset, jOffset) pairs or NULL for the pixel centres.  World-space rays, as the render kernels build them. */
+int  vdbrt_camera_get_rays(const vdbrt_camera* cam, const uint32_t* pixels, const double* offsets, uint64_t n, vdbrt_ray* rays);
 /* the 16 doubles LevelSetRayTracer::setPixelSamples draws (RayTracer.h:883-885)                                 */
 int  vdbrt_jitter_table(unsigned int seed, double out[16]);
 /* VolumeRender defaults (RayTracer.h:929-936)                                                                   */

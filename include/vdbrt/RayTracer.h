@@ -206,6 +206,15 @@ private:
     RGBA mFill;
 };
 
+/// math::Ray<double> as the facade's callers hand it over: eye, direction, times (math/Ray.h:57-63: t0 = 1e-9, t1 = max by default)
+struct Ray : vdbrt_ray
+{
+    Ray(const Vec3R& e = Vec3R(0.0), const Vec3R& d = Vec3R(1.0, 0.0, 0.0), double t0_ = 1e-9, double t1_ = std::numeric_limits<double>::max())
+    { eye[0] = e.x; eye[1] = e.y; eye[2] = e.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; t0 = t0_; t1 = t1_; }
+    explicit Ray(const vdbrt_ray& r) : vdbrt_ray(r) {}
+    Vec3R operator()(double t) const { return Vec3R(eye[0] + dir[0] * t, eye[1] + dir[1] * t, eye[2] + dir[2] * t); }      // math/Ray.h:109
+};
+
 class BaseCamera
 {
 public:
@@ -218,6 +227,20 @@ public:
     {
         const double t[3] = {xyz.x, xyz.y, xyz.z}, u[3] = {up.x, up.y, up.z};
         check(vdbrt_camera_look_at(&mPod, t, u));
+    }
+    /// BaseCamera::rasterToScreen (RayTracer.h:391-395)
+    Vec3R rasterToScreen(double i, double j, double z) const
+    {
+        return Vec3R((2 * i / double(mFilm->width()) - 1) * mPod.scale_w, (1 - 2 * j / double(mFilm->height())) * mPod.scale_h, z);
+    }
+    /// getRay (RayTracer.h:452-462, 505-512): the world-space ray through pixel (i, j); the offsets in [0, 1], 0.5 = the pixel's centre
+    Ray getRay(size_t i, size_t j, double iOffset = 0.5, double jOffset = 0.5) const
+    {
+        const uint32_t ij[2] = {uint32_t(i), uint32_t(j)};
+        const double off[2] = {iOffset, jOffset};
+        vdbrt_ray r;
+        check(vdbrt_camera_get_rays(&mPod, ij, off, 1, &r));
+        return Ray(r);
     }
     const vdbrt_camera& pod() const { return mPod; }
     Film& film() const { return *mFilm; }
@@ -237,6 +260,9 @@ public:
         const double r[3] = {rotation.x, rotation.y, rotation.z}, t[3] = {translation.x, translation.y, translation.z};
         check(vdbrt_camera_perspective(&mPod, uint32_t(film.width()), uint32_t(film.height()), r, t, focalLength, aperture, nearPlane, farPlane));
     }
+    /// horizontal field of view in degrees from a focal length and an aperture in mm, and back (RayTracer.h:466-475)
+    static double focalLengthToFieldOfView(double length, double aperture) { return 360.0 / 3.14159265358979323846 * std::atan(aperture / (2.0 * length)); }
+    static double fieldOfViewToFocalLength(double fov, double aperture) { return aperture / (2.0 * (std::tan(fov * 3.14159265358979323846 / 360.0))); }
 };
 
 class OrthographicCamera : public BaseCamera
@@ -304,15 +330,6 @@ template<> class PositionShader<Vec3SGrid> : public BaseShader { public:
 template<> class DiffuseShader<Vec3SGrid> : public BaseShader { public:
     DiffuseShader(const Vec3SGrid& grid) : BaseShader(VDBRT_SHADER_DIFFUSE, Film::RGBA(1.0f)) { mPod.color_grid = grid.get(); }
     BaseShader* copy() const override { return new DiffuseShader(*this); } };
-
-/// math::Ray<double> as the facade's callers hand it over: eye, direction, times (math/Ray.h:57-63: t0 = 1e-9, t1 = max by default)
-struct Ray : vdbrt_ray
-{
-    Ray(const Vec3R& e = Vec3R(0.0), const Vec3R& d = Vec3R(1.0, 0.0, 0.0), double t0_ = 1e-9, double t1_ = std::numeric_limits<double>::max())
-    { eye[0] = e.x; eye[1] = e.y; eye[2] = e.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; t0 = t0_; t1 = t1_; }
-    explicit Ray(const vdbrt_ray& r) : vdbrt_ray(r) {}
-    Vec3R operator()(double t) const { return Vec3R(eye[0] + dir[0] * t, eye[1] + dir[1] * t, eye[2] + dir[2] * t); }      // math/Ray.h:109
-};
 
 /// tools::LinearSearchImpl<GridT, Iterations> (RayIntersector.h:514-668) as a tag: the facade's intersector only needs the iteration count
 template<typename GridT, int Iterations = 0>

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("VDBRT_LIBRARY") or os.path.join(os.path.dirname(os.pa
 SYMBOLS = [
     "vdbrt_create", "vdbrt_destroy", "vdbrt_last_error", "vdbrt_device_count", "vdbrt_set_stream", "vdbrt_synchronize",
     "vdbrt_host_alloc", "vdbrt_host_free", "vdbrt_host_register", "vdbrt_host_unregister", "vdbrt_upload_grid", "vdbrt_free_grid", "vdbrt_grid_get_info",
-    "vdbrt_grid_download", "vdbrt_camera_perspective", "vdbrt_camera_orthographic", "vdbrt_camera_look_at",
+    "vdbrt_grid_download", "vdbrt_camera_perspective", "vdbrt_camera_orthographic", "vdbrt_camera_look_at", "vdbrt_camera_get_rays",
     "vdbrt_jitter_table", "vdbrt_vol_opts_default", "vdbrt_render_levelset", "vdbrt_render_volume",
     "vdbrt_intersect_levelset", "vdbrt_volume_spans", "vdbrt_count_levelset", "vdbrt_count_volume",
     "vdbrt_last_kernel_ms", "vdbrt_build_levelset_sphere", "vdbrt_build_levelset_torus",
@@ -69,6 +69,7 @@ def load_library():
     L.vdbrt_camera_perspective.argtypes = [P(abi.Camera), u32, u32, P(dbl), P(dbl), dbl, dbl, dbl, dbl]
     L.vdbrt_camera_orthographic.argtypes = [P(abi.Camera), u32, u32, P(dbl), P(dbl), dbl, dbl, dbl]
     L.vdbrt_camera_look_at.argtypes = [P(abi.Camera), P(dbl), P(dbl)]
+    L.vdbrt_camera_get_rays.argtypes = [P(abi.Camera), vp, vp, u64, vp]
     L.vdbrt_jitter_table.argtypes = [C.c_uint, P(dbl)]
     L.vdbrt_vol_opts_default.argtypes = [P(abi.VolOpts)]
     L.vdbrt_render_levelset.argtypes = [vp, vp, P(abi.Camera), P(abi.Shader), P(abi.LsOpts), P(abi.Film), P(abi.Aux)]
@@ -165,6 +166,15 @@ def make_shader(kind=abi.SHADER_DIFFUSE, rgba=(1, 1, 1, 1), bbox_min=(0, 0, 0), 
     s.inv_dim = abi.vec3(inv_dim)
     s.color_grid = color_grid.handle if color_grid is not None else None
     return s
+
+
+def camera_rays(cam, ij, offsets=None):
+    """BaseCamera::getRay for an (n, 2) array of pixel indices (and optional (n, 2) offsets in [0, 1]); returns (abi.Ray * n)"""
+    ij = np.ascontiguousarray(ij, dtype=np.uint32).reshape(-1, 2)
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64).reshape(-1, 2)
+    rays = (abi.Ray * len(ij))()
+    _check(load_library().vdbrt_camera_get_rays(C.byref(cam), ij.ctypes.data, None if off is None else off.ctypes.data, len(ij), rays))
+    return rays
 
 
 def partition(rank=0, count=1, tile_w=0, tile_h=0):

@@ -148,6 +148,40 @@ int vdbrt_camera_look_at(vdbrt_camera* cam, const double xyz[3], const double up
     return VDBRT_OK;
 }
 
+// PerspectiveCamera::getRay (tools/RayTracer.h:452-462) / OrthographicCamera::getRay (:505-512) on the host: the rays the render kernels
+// build themselves (cameraRay, vdbrt_device.cuh), for callers that trace their own batches (vdbrt_intersect_levelset, vdbrt_volume_spans).
+// pixels: n (i, j) pairs; offsets: n (iOffset, jOffset) pairs or NULL for the pixel centres (0.5, 0.5).
+int vdbrt_camera_get_rays(const vdbrt_camera* c, const uint32_t* pixels, const double* offsets, uint64_t n, vdbrt_ray* rays)
+{
+    if (!c || !pixels || !rays) return vdbrt::setError(VDBRT_ERR_INVALID_ARG, "null argument");
+    if (c->kind > VDBRT_CAMERA_ORTHOGRAPHIC) return vdbrt::setError(VDBRT_ERR_INVALID_ARG, "unknown camera kind");
+    const double* m = c->m;
+    for (uint64_t k = 0; k < n; ++k) {
+        const double io = offsets ? offsets[2 * k] : 0.5, jo = offsets ? offsets[2 * k + 1] : 0.5;
+        // rasterToScreen (:391-395)
+        const double sx = (2 * (double(pixels[2 * k]) + io) / double(c->width) - 1) * c->scale_w;
+        const double sy = (1 - 2 * (double(pixels[2 * k + 1]) + jo) / double(c->height)) * c->scale_h;
+        vdbrt_ray& r = rays[k];
+        r.t0 = c->t0; r.t1 = c->t1;
+        if (c->kind == VDBRT_CAMERA_PERSPECTIVE) {
+            const double sz = -1.0;
+            double d[3] = {sx * m[0] + sy * m[4] + sz * m[8], sx * m[1] + sy * m[5] + sz * m[9], sx * m[2] + sy * m[6] + sz * m[10]};   // applyJacobian
+            const double len = length3(d);
+            if (std::fabs(len - 0.0) > 1.0e-7) { const double s = 1.0 / len; d[0] *= s; d[1] *= s; d[2] *= s; }    // Vec3::normalize (math/Vec3.h:363-371)
+            const double sc = 1.0 / (d[0] * c->dir[0] + d[1] * c->dir[1] + d[2] * c->dir[2]);
+            r.t0 *= sc; r.t1 *= sc;                                                                                  // scaleTimes
+            for (int a = 0; a < 3; ++a) { r.eye[a] = c->eye[a]; r.dir[a] = d[a]; }
+        } else {
+            const double sz = 0.0;
+            r.eye[0] = sx * m[0] + sy * m[4] + sz * m[8] + m[12];                                                    // applyMap
+            r.eye[1] = sx * m[1] + sy * m[5] + sz * m[9] + m[13];
+            r.eye[2] = sx * m[2] + sy * m[6] + sz * m[10] + m[14];
+            for (int a = 0; a < 3; ++a) r.dir[a] = c->dir[a];
+        }
+    }
+    return VDBRT_OK;
+}
+
 // LevelSetRayTracer::setPixelSamples (tools/RayTracer.h:883-885): math::Rand01<double>(seed) = std::mt19937 +
 // std::uniform_real_distribution<double> (math/Math.h:176-206)
 int vdbrt_jitter_table(unsigned int seed, double out[16])
