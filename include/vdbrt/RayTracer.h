@@ -443,6 +443,13 @@ public:
         return tr ? Vec3R(p.x * mScale[0] + i.translation[0], p.y * mScale[1] + i.translation[1], p.z * mScale[2] + i.translation[2])
                   : Vec3R(p.x * mScale[0], p.y * mScale[1], p.z * mScale[2]);
     }
+    /// getWorldTime (:442-445): time * |J dir| of the current index ray (diagonal maps, like getWorldPos above; a grid with a general affine
+    /// map -- the tolerance path -- reports its hit positions and times through the batch calls of the C ABI instead)
+    double getWorldTime(double time) const
+    {
+        const double x = mRay.dir[0] * mScale[0], y = mRay.dir[1] * mScale[1], z = mRay.dir[2] * mScale[2];
+        return time * std::sqrt(x * x + y * y + z * z);
+    }
     /// print (:459-469): "BBox: [min] -> [max]" (levels 2 and 3 of the reference add statistics of its bool tree, which does not exist here)
     void print(std::ostream& os = std::cout, int verboseLevel = 1) const
     {
