@@ -443,7 +443,7 @@ public:
         return tr ? Vec3R(p.x * mScale[0] + i.translation[0], p.y * mScale[1] + i.translation[1], p.z * mScale[2] + i.translation[2])
                   : Vec3R(p.x * mScale[0], p.y * mScale[1], p.z * mScale[2]);
     }
-    /// getWorldTime (:442-445): time * |J dir| of the current index ray (diagonal maps, like getWorldPos above; a grid with a general affine
+    /// getWorldTime (:442-445): time * |J dir| of the current index ray, whose direction has unit length (diagonal maps, like getWorldPos above; a grid with a general affine
     /// map -- the tolerance path -- reports its hit positions and times through the batch calls of the C ABI instead)
     double getWorldTime(double time) const
     {

@@ -118,6 +118,22 @@ int main(int argc, char** argv)
         EXPECT(os.str().find("BBox: [-104, -104, -104] -> [104, 104, 104]") != std::string::npos);
         std::printf("%s", os.str().c_str());
     }
+    // ---- BaseCamera::getRay / rasterToScreen, the field-of-view helpers (RayTracer.h:391-395,452-475), getWorldTime (RayIntersector.h:442-445)
+    {
+        // the ray through a pixel that the render above has marked as hit must hit, one that it left alone must miss
+        const size_t c = size_t(res) / 2;
+        const tools::Ray centre = camera.getRay(c, c), corner = camera.getRay(0, 0, 0.25, 0.75);
+        EXPECT(centre.eye[2] == 300.0 && centre.dir[2] < -0.999 && corner.dir[0] < 0.0 && corner.dir[1] > 0.0);
+        EXPECT((film.pixel(c, c).r > 0.f) == inter.intersectsWS(centre));
+        EXPECT((film.pixel(0, 0).r > 0.f) == inter.intersectsWS(camera.getRay(0, 0)));
+        const Vec3R s = camera.rasterToScreen(double(res), 0.0, -1.0);
+        EXPECT(s.x > 0.0 && s.y > 0.0 && s.z == -1.0 && std::fabs(s.x - 0.5 * double(41.2136f) / double(50.0f)) < 1e-12);
+        const double fov = tools::PerspectiveCamera::focalLengthToFieldOfView(50.0, 41.2136);
+        EXPECT(std::fabs(fov - 44.8) < 0.1 && std::fabs(tools::PerspectiveCamera::fieldOfViewToFocalLength(fov, 41.2136) - 50.0) < 1e-9);
+        tools::Ray wr(Vec3R(0.0, 0.0, 300.0), Vec3R(0.0, 0.0, -2.0));
+        // the index ray's direction is normalised and its times scaled (Ray::applyInverseMap, math/Ray.h:204-213): voxel size 1 -> |J dir| = 1
+        EXPECT(vinter.setWorldRay(wr) && std::fabs(vinter.getWorldTime(3.0) - 3.0) < 1e-12);
+    }
     if (argc > 2) film.savePPM(argv[2]);
     std::printf("facade ok\n");
     return 0;
