@@ -63,7 +63,7 @@ def test_levelset_records_bit_exact(ref, oracle, sphere100):
     assert octr.hits == int(raux.hit.sum())
 
 
-def test_lazy_tester_init_is_exact(ref, oracle, sphere100, torus_small):
+def test_lazy_tester_init_is_exact(ref, oracle, sphere100, torus_small, sphere_small, union_small):
     """The CUDA kernels evaluate tester.init's mV[0] only when the first voxel of a leaf visit passes the value gate (lsAdvance).  The
     same change made to the oracle must leave every record of every pixel as the REFERENCE has it, and only drop stencil refills."""
     d = refapi.camera_desc(160, 120, translation=(0, 0, 300), lookat=(0, 0, 0))
@@ -86,6 +86,17 @@ def test_lazy_tester_init_is_exact(ref, oracle, sphere100, torus_small):
             oracle.render_levelset(torus_small.oracle_handle, ref.camera_pod(d2), refapi.shader(abi.SHADER_NORMAL), f_orc, spp=2,
                                    jitter=ref.jitter_table(3), iterations=iters)
             assert np.array_equal(f_ref, f_orc)
+        # orthographic camera with iso != 0, a scaled + translated grid, a union of spheres: render_both compares reference and oracle films
+        d3 = refapi.camera_desc(128, 96, translation=(10, 5, 250), rotation=(5, -10, 20), kind=abi.CAMERA_ORTHOGRAPHIC, frame=260.0)
+        for iso in (1.25, -2.0):
+            f_ref, f_orc = render_both(ref, oracle, sphere100, d3, refapi.shader(abi.SHADER_NORMAL), iso=iso)
+            assert np.array_equal(f_ref, f_orc), iso
+        d4 = refapi.camera_desc(128, 128, translation=(2, 3, 30), lookat=(20, 0, 0))
+        f_ref, f_orc = render_both(ref, oracle, sphere_small, d4, refapi.shader())
+        assert (f_ref[..., 0] > 0).sum() > 500 and np.array_equal(f_ref, f_orc)
+        d5 = refapi.camera_desc(160, 120, translation=(30.0, 40.0, 150.0), lookat=(0, 0, 0))
+        f_ref, f_orc = render_both(ref, oracle, union_small, d5, refapi.shader(abi.SHADER_POSITION, bbox_min=(-60, -60, -60), inv_dim=(1 / 120.0,) * 3))
+        assert np.array_equal(f_ref, f_orc)
     finally:
         oracle.set_lazy_init(False)
 
